@@ -1,0 +1,146 @@
+/*
+ * seqalign_b200.h -- C-ABI of the B200-native batch alignment engine.
+ *
+ * The reference (noporpoise/seq-align) has no batch API: its only entry to
+ * the DP is aligner_align() (reference src/alignment.h:56-59, one pair per
+ * call, src/alignment.c:170-193), driven pair-by-pair from
+ * src/alignment_cmdline.c:611-622.  A GPU needs thousands of independent
+ * pairs per launch, so this header adds the batch entry points a maintainer
+ * would bind (SURVEY.md 8b "NEW (additive) batch entry points"); the classic
+ * single-pair functions in alignment.h / needleman_wunsch.h /
+ * smith_waterman.h are implemented on top of them as batches of one.
+ *
+ * Plain C: pointers, sizes and ints only.  No CUDA or torch types appear in
+ * any signature (device pointers and streams travel as void* / const void*).
+ * The library fails loudly (error code + message, never a CPU fallback) when
+ * no sm_100 device is usable.
+ *
+ * Each function cites the reference code whose work it takes over.
+ */
+#ifndef SEQALIGN_B200_H
+#define SEQALIGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "alignment.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct seqalign_batch seqalign_batch_t;
+
+/* algorithm: is_sw argument of aligner_align (reference src/alignment.h:59) */
+#define SEQALIGN_NW 0
+#define SEQALIGN_SW 1
+
+/* what a submit computes */
+#define SEQALIGN_MODE_SCORE 0 /* score (+ best SW cell): fill only           */
+#define SEQALIGN_MODE_ALIGN 1 /* + traceback: gapped strings, pos/len fields */
+
+/* error codes (negative returns) */
+#define SEQALIGN_OK 0
+#define SEQALIGN_ERR_CUDA (-1)      /* CUDA runtime / no usable device         */
+#define SEQALIGN_ERR_UNKNOWN_PAIR (-2) /* reference alignment_scoring.c:179-181 */
+#define SEQALIGN_ERR_TRACEBACK (-3) /* reference alignment.c:328-349           */
+#define SEQALIGN_ERR_ARG (-4)
+#define SEQALIGN_ERR_NOMEM (-5)
+
+/* number of usable sm_100 devices (0 if none / no driver) */
+int seqalign_device_count(void);
+const char *seqalign_version(void);
+
+/* One engine per device and host thread.  NULL on failure (message through
+ * seqalign_last_create_error()). */
+seqalign_batch_t *seqalign_batch_create(int device);
+void seqalign_batch_destroy(seqalign_batch_t *eng);
+const char *seqalign_last_create_error(void);
+/* message of the last failing call on this engine ("" if none) */
+const char *seqalign_batch_error(const seqalign_batch_t *eng);
+
+/* Snapshot the scoring model.  Takes over the per-cell scoring_lookup()
+ * (reference src/alignment.c:98 -> src/alignment_scoring.c:133-182): the
+ * 256x256 table, wildcards, case folding and match/mismatch fallback are
+ * flattened into a dense code table on the host, once per batch.
+ * min_penalty is carried verbatim (it defines the NW sentinel,
+ * reference src/alignment.c:41). */
+int seqalign_batch_set_scoring(seqalign_batch_t *eng, const scoring_t *scoring);
+
+/* Align n independent pairs: replaces n calls of aligner_align()
+ * (+ the traceback of needleman_wunsch_align2 / the first
+ * smith_waterman_fetch in MODE_ALIGN).  Sequences are raw characters with
+ * explicit lengths, no NUL needed (as aligner_align).  Blocking: results are
+ * on the host when it returns. */
+int seqalign_batch_submit(seqalign_batch_t *eng, int algo, int mode,
+                          const char *const *seq_a, const size_t *len_a,
+                          const char *const *seq_b, const size_t *len_b,
+                          size_t n);
+
+/* Same, sequences packed back to back: pair i is
+ * seq_a[off_a[i] .. off_a[i+1]) vs seq_b[off_b[i] .. off_b[i+1]);
+ * off_* have n+1 entries.  One host->device copy per array. */
+int seqalign_batch_submit_packed(seqalign_batch_t *eng, int algo, int mode,
+                                 const char *seq_a, const int64_t *off_a,
+                                 const char *seq_b, const int64_t *off_b,
+                                 size_t n);
+
+/* Results of the last submit (host arrays of n entries each).
+ * score: NW = max of the three matrices at [len_a,len_b]
+ *        (reference needleman_wunsch.c:53-66); SW = best match score, 0 if
+ *        the pair has no hit.
+ * x_end/y_end: SW = 1-based cell of the best hit under the reference's hit
+ *        order (score desc, x asc, y asc: smith_waterman.c:71-86 + stable
+ *        glibc qsort_r); 0,0 if no hit.  NW = len_a,len_b. */
+int seqalign_batch_scores(seqalign_batch_t *eng, int32_t *score);
+int seqalign_batch_ends(seqalign_batch_t *eng, int32_t *score,
+                        int32_t *x_end, int32_t *y_end);
+size_t seqalign_batch_size(const seqalign_batch_t *eng);
+
+/* MODE_ALIGN: copy pair i of the last submit into a reference alignment_t
+ * (grown with alignment_ensure_capacity).  NW fills result_a/result_b/
+ * length/score like needleman_wunsch_align2 (needleman_wunsch.c:34-145); SW
+ * fills them plus pos_a/pos_b/len_a/len_b like the first
+ * smith_waterman_fetch on a fresh aligner (smith_waterman.c:165-277).
+ * Returns 1 if an alignment was written, 0 if the SW pair has no hit,
+ * negative on error. */
+int seqalign_batch_alignment(seqalign_batch_t *eng, size_t i, alignment_t *out);
+
+/* Device-resident variant (score mode): all pointers are device memory on
+ * the engine's device, stream is a cudaStream_t (NULL = engine's own).
+ * d_x_end/d_y_end may be NULL.  Asynchronous w.r.t. the host except for one
+ * 64-byte readback that sizes the alphabet. */
+int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
+                              const void *d_seq_a, const void *d_off_a,
+                              const void *d_seq_b, const void *d_off_b,
+                              size_t n, void *d_score, void *d_x_end,
+                              void *d_y_end, void *stream);
+
+/* Materialise mode, one pair: the literal aligner_align() contract
+ * (reference src/alignment.c:28-168).  match/gap_a/gap_b are host arrays of
+ * (len_a+1)*(len_b+1) ints, row-major, index = y*(len_a+1)+x, borders
+ * included. */
+int seqalign_fill_matrices(seqalign_batch_t *eng,
+                           const char *seq_a, size_t len_a,
+                           const char *seq_b, size_t len_b, int is_sw,
+                           int32_t *match, int32_t *gap_a, int32_t *gap_b);
+
+/* characters of the first unknown pair after SEQALIGN_ERR_UNKNOWN_PAIR
+ * (case-folded, as the reference prints them) */
+void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b);
+
+/* Instrumentation for bench.py: device time (ms, CUDA events on the
+ * engine's stream) and launch count of the DP kernels of the last
+ * submit/run, and the name of the kernel variant that ran. */
+double seqalign_batch_last_kernel_ms(const seqalign_batch_t *eng);
+int seqalign_batch_last_launches(const seqalign_batch_t *eng);
+const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng);
+
+/* tuning knob: 0 = automatic.  Forces the general kernel when set to 1
+ * (tests use it to cross-check the specialised kernels). */
+void seqalign_batch_force_general(seqalign_batch_t *eng, int on);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,810 @@
+/*
+ * sa_engine.cu -- batch alignment engine behind include/seqalign_b200.h.
+ *
+ * Owns one CUDA stream, grow-only device / pinned-host buffers and the
+ * launch logic: scan the batch's alphabet, flatten scoring_t into a dense
+ * table, pick a kernel variant, fill (+ direction bytes + walk in align
+ * mode, in memory-bounded waves), copy results back.  There is no CPU
+ * implementation of the DP in here: without a usable device every entry
+ * point fails with SEQALIGN_ERR_CUDA.
+ */
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "seqalign_b200.h"
+#include "sa_platform.h"
+#include "sa_flatten.h"
+#include "sa_kernels.cuh"
+#include "sa_fast.cuh"
+
+using namespace sa;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void release() { if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct seqalign_batch {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  char unk_a = 0, unk_b = 0;
+
+  bool have_scoring = false;
+  scoring_t *scoring = nullptr;
+  FlatTable ft;
+  bool force_general = false;
+
+  /* inputs on device */
+  DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
+  /* scratch */
+  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd;
+  /* score-mode results */
+  DevBuf d_score, d_xend, d_yend, d_state;
+  /* align-mode wave buffers */
+  DevBuf d_dir, d_dir_off, d_out_a, d_out_b, d_out_off, d_walk;
+  /* materialise mode */
+  DevBuf d_mats;
+  PinBuf h_in_a, h_in_b, h_off_a, h_off_b, h_meta, h_res, h_walk, h_str_a, h_str_b;
+
+  /* last batch */
+  size_t n = 0;
+  int algo = 0, mode = 0;
+  std::vector<int32_t> score, xend, yend;
+  std::vector<int64_t> res_off;          /* n+1, into res_a/res_b */
+  std::vector<char> res_a, res_b;        /* right-aligned strings per pair */
+  std::vector<int32_t> aln_start, aln_len, pos_a, pos_b, len_a, len_b, status;
+
+  double last_ms = 0;
+  int last_launches = 0;
+  const char *last_kernel = "none";
+};
+
+namespace {
+
+#define CU_TRY(call)                                                          \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if(e__ != cudaSuccess) {                                                  \
+      char m__[512];                                                          \
+      snprintf(m__, sizeof(m__), "CUDA error %d (%s) at %s:%d: %s", (int)e__, \
+               cudaGetErrorString(e__), __FILE__, __LINE__, #call);           \
+      eng->err = m__;                                                         \
+      return SEQALIGN_ERR_CUDA;                                               \
+    }                                                                         \
+  } while(0)
+
+int fail(seqalign_batch *eng, int code, const char *msg)
+{
+  eng->err = msg;
+  return code;
+}
+
+int ensure_dev(seqalign_batch *eng, DevBuf &b, size_t bytes)
+{
+  bytes = (bytes + 255) / 256 * 256 + 256; /* slack: vector loads may over-read 16 B */
+  if(b.cap >= bytes) return 0;
+  b.release();
+  size_t want = bytes + bytes / 4;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if(e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+  if(e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return fail(eng, SEQALIGN_ERR_NOMEM, "out of device memory");
+  }
+  b.cap = want;
+  return 0;
+}
+
+int ensure_pin(seqalign_batch *eng, PinBuf &b, size_t bytes)
+{
+  bytes = (bytes + 255) / 256 * 256 + 256;
+  if(b.cap >= bytes) return 0;
+  b.release();
+  size_t want = bytes + bytes / 4;
+  if(cudaMallocHost(&b.p, want) != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return fail(eng, SEQALIGN_ERR_NOMEM, "out of pinned host memory");
+  }
+  b.cap = want;
+  return 0;
+}
+
+#define TRY(call) do { int r__ = (call); if(r__ != 0) return r__; } while(0)
+
+ScoreParams make_params(const scoring_t *s, int is_sw, int ncodes)
+{
+  ScoreParams sp;
+  sp.open = (int)((unsigned)s->gap_open + (unsigned)s->gap_extend);
+  sp.ext = s->gap_extend;
+  sp.gap_open = s->gap_open;
+  /* reference alignment.c:41 */
+  sp.minv = is_sw ? 0 : (int)((unsigned)INT_MIN + (unsigned)abs(s->min_penalty));
+  sp.is_sw = is_sw ? 1 : 0;
+  sp.no_start = s->no_start_gap_penalty;
+  sp.no_end = s->no_end_gap_penalty;
+  sp.no_gaps_a = s->no_gaps_in_a;
+  sp.no_gaps_b = s->no_gaps_in_b;
+  sp.no_mismatches = s->no_mismatches;
+  sp.ncodes = ncodes;
+  return sp;
+}
+
+struct BatchMeta {
+  uint64_t pres_a[4], pres_b[4];
+  int64_t max_la, max_lb, cells, max_cells;
+};
+
+/* scan the device-resident batch: alphabet, longest sequences, cell count */
+int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
+               const int64_t *d_off_a, const int64_t *d_off_b, size_t n,
+               int64_t total_a, int64_t total_b, cudaStream_t st, BatchMeta *bm)
+{
+  TRY(ensure_dev(eng, eng->d_meta, META_WORDS * 8));
+  TRY(ensure_pin(eng, eng->h_meta, META_WORDS * 8));
+  CU_TRY(cudaMemsetAsync(eng->d_meta.p, 0, META_WORDS * 8, st));
+  int64_t work = (total_a + total_b) / 16 + (int64_t)n;
+  int grid = (int)((work + 255) / 256);
+  if(grid > eng->num_sms * 8) grid = eng->num_sms * 8;
+  if(grid < 1) grid = 1;
+  SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, total_a, d_b, total_b, d_off_a, d_off_b,
+            (int64_t)n, (unsigned long long *)eng->d_meta.p);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(eng->h_meta.p, eng->d_meta.p, META_WORDS * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  const uint64_t *m = (const uint64_t *)eng->h_meta.p;
+  for(int i = 0; i < 4; i++) { bm->pres_a[i] = m[META_PRES_A + i]; bm->pres_b[i] = m[META_PRES_B + i]; }
+  bm->max_la = (int64_t)m[META_MAX_LA];
+  bm->max_lb = (int64_t)m[META_MAX_LB];
+  bm->cells = (int64_t)m[META_CELLS];
+  bm->max_cells = (int64_t)m[META_MAX_CELLS];
+  return 0;
+}
+
+/* flatten scoring for this batch's alphabet and upload the tables */
+int upload_tables(seqalign_batch *eng, const BatchMeta &bm, cudaStream_t st)
+{
+  flatten_scoring(eng->scoring, bm.pres_a, bm.pres_b, &eng->ft);
+  const FlatTable &ft = eng->ft;
+  const size_t nn = (size_t)ft.ncodes * ft.ncodes;
+  TRY(ensure_dev(eng, eng->d_sub, nn * 4));
+  TRY(ensure_dev(eng, eng->d_forbid, nn));
+  TRY(ensure_dev(eng, eng->d_lut, 256));
+  CU_TRY(cudaMemcpyAsync(eng->d_sub.p, ft.sub.data(), nn * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_forbid.p, ft.forbid.data(), nn, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_lut.p, ft.lut, 256, cudaMemcpyHostToDevice, st));
+  /* pageable sources: the copies above are staged before they return, but
+   * the vectors are rebuilt per batch, so make that explicit */
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* the reference exits on the first unknown character pair it meets while
+ * filling (row-major: seq_b outer, seq_a inner).  Only reached when the
+ * flattened table has an unknown entry among the batch's characters. */
+int check_unknown_pairs(seqalign_batch *eng, const char *seq_a, const int64_t *off_a,
+                        const char *seq_b, const int64_t *off_b, size_t n)
+{
+  const FlatTable &ft = eng->ft;
+  const int nc = ft.ncodes;
+  for(size_t i = 0; i < n; i++) {
+    const int64_t la = off_a[i + 1] - off_a[i], lb = off_b[i + 1] - off_b[i];
+    if(la == 0 || lb == 0) continue;
+    const unsigned char *a = (const unsigned char *)seq_a + off_a[i];
+    const unsigned char *b = (const unsigned char *)seq_b + off_b[i];
+    std::vector<uint8_t> seen_a(nc, 0);
+    for(int64_t x = 0; x < la; x++) seen_a[ft.lut[a[x]]] = 1;
+    for(int64_t y = 0; y < lb; y++) {
+      const int cb = ft.lut[b[y]];
+      bool bad = false;
+      for(int ca = 0; ca < nc && !bad; ca++) bad = seen_a[ca] && ft.unknown[(size_t)cb * nc + ca];
+      if(!bad) continue;
+      for(int64_t x = 0; x < la; x++) {
+        const int ca = ft.lut[a[x]];
+        if(ft.unknown[(size_t)cb * nc + ca]) {
+          eng->unk_a = (char)ft.rep[ca];
+          eng->unk_b = (char)ft.rep[cb];
+          char m[160];
+          snprintf(m, sizeof(m), "Error: Unknown character pair (%c,%c) and match/mismatch have not been set",
+                   eng->unk_a, eng->unk_b);
+          eng->err = m;
+          return SEQALIGN_ERR_UNKNOWN_PAIR;
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+int general_grid(const seqalign_batch *eng, size_t npairs)
+{
+  int64_t g = (int64_t)eng->num_sms * 4;
+  int64_t need = ((int64_t)npairs + GEN_WARPS - 1) / GEN_WARPS;
+  if(g > need) g = need;
+  return g < 1 ? 1 : (int)g;
+}
+
+struct DevBatch {
+  const uint8_t *a, *b;
+  const int64_t *off_a, *off_b;
+  size_t n;
+};
+
+template <int MODE>
+int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &sp,
+                   int64_t pair0, int64_t npairs, const BatchMeta &bm, GenArgs extra,
+                   cudaStream_t st)
+{
+  GenArgs A = extra;
+  A.seq_a = db.a; A.seq_b = db.b; A.off_a = db.off_a; A.off_b = db.off_b;
+  A.pair0 = pair0; A.npairs = npairs; A.sp = sp;
+  A.sub = (const int32_t *)eng->d_sub.p;
+  A.forbid = (const uint8_t *)eng->d_forbid.p;
+  A.lut = (const uint8_t *)eng->d_lut.p;
+  A.table_in_smem = sp.ncodes <= SMEM_TABLE_MAX_CODES;
+  const int grid = general_grid(eng, (size_t)npairs);
+  A.bnd = nullptr; A.bnd_rows = 0;
+  if(bm.max_la > GSTRIP) {
+    A.bnd_rows = bm.max_lb + 1;
+    TRY(ensure_dev(eng, eng->d_bnd, (size_t)grid * GEN_WARPS * (size_t)A.bnd_rows * sizeof(int4)));
+    A.bnd = (int4 *)eng->d_bnd.p;
+  }
+  TRY(ensure_dev(eng, eng->d_counter, 8));
+  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+  A.counter = (unsigned long long *)eng->d_counter.p;
+  const size_t smem = general_smem_bytes(sp.ncodes, A.table_in_smem);
+  SA_LAUNCH(general_kernel<MODE>, grid, GEN_WARPS * 32, smem, st, A);
+  CU_TRY(cudaGetLastError());
+  eng->last_launches++;
+  return 0;
+}
+
+/* score mode over a device-resident batch; results into d_score/d_xend/d_yend */
+int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta &bm,
+              int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st)
+{
+  const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
+  FastPlan plan;
+  if(!eng->force_general && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, &plan)) {
+    TRY(ensure_dev(eng, eng->d_tab8, (size_t)eng->ft.ncodes * eng->ft.ncodes + 256));
+    TRY(ensure_dev(eng, eng->d_counter, 8));
+    CU_TRY(cudaMemcpyAsync(eng->d_tab8.p, plan.tab8.data(), plan.tab8.size(), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+    FastArgs F;
+    F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
+    F.npairs = (int64_t)db.n; F.sp = sp;
+    F.tab8 = (const int8_t *)eng->d_tab8.p;
+    F.lut = (const uint8_t *)eng->d_lut.p;
+    F.counter = (unsigned long long *)eng->d_counter.p;
+    F.score = d_score; F.xend = d_xend; F.yend = d_yend;
+    F.max_lb = (int)bm.max_lb;
+    CU_TRY(cudaEventRecord(eng->ev0, st));
+    int r = fast_launch(plan, F, eng->num_sms, eng->smem_optin, st);
+    if(r != 0) return fail(eng, SEQALIGN_ERR_CUDA, "fast kernel launch failed");
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(eng->ev1, st));
+    eng->last_launches++;
+    eng->last_kernel = plan.name;
+    return 0;
+  }
+  GenArgs X;
+  memset(&X, 0, sizeof(X));
+  X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = nullptr;
+  CU_TRY(cudaEventRecord(eng->ev0, st));
+  TRY(launch_general<MODE_SCORE>(eng, db, sp, 0, (int64_t)db.n, bm, X, st));
+  CU_TRY(cudaEventRecord(eng->ev1, st));
+  eng->last_kernel = "general_score";
+  return 0;
+}
+
+int64_t dir_bytes(int64_t la, int64_t lb)
+{
+  return (dir_stride((int)la) * lb + 15) & ~(int64_t)15;
+}
+
+/* align mode: waves of pairs bounded by direction-byte memory */
+int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta &bm,
+              const int64_t *h_off_a, const int64_t *h_off_b, cudaStream_t st)
+{
+  const size_t n = db.n;
+  const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
+  TRY(ensure_dev(eng, eng->d_score, n * 4));
+  TRY(ensure_dev(eng, eng->d_xend, n * 4));
+  TRY(ensure_dev(eng, eng->d_yend, n * 4));
+  TRY(ensure_dev(eng, eng->d_state, n * 4));
+  int32_t *d_score = (int32_t *)eng->d_score.p, *d_xend = (int32_t *)eng->d_xend.p;
+  int32_t *d_yend = (int32_t *)eng->d_yend.p, *d_state = (int32_t *)eng->d_state.p;
+
+  eng->last_ms = 0;
+  float ms = 0;
+  if(algo == SEQALIGN_SW) {
+    /* best cell first: the direction pass stores no scores */
+    TRY(run_score(eng, algo, db, bm, d_score, d_xend, d_yend, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    eng->last_ms += ms;
+  }
+
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  int64_t budget = (int64_t)(free_b / 2);
+  const char *env = getenv("SEQALIGN_DIR_BUDGET");
+  if(env) budget = atoll(env);
+  if(budget > ((int64_t)48 << 30)) budget = (int64_t)48 << 30;
+
+  eng->res_off.assign(n + 1, 0);
+  for(size_t i = 0; i < n; i++)
+    eng->res_off[i + 1] = eng->res_off[i] + (h_off_a[i + 1] - h_off_a[i]) + (h_off_b[i + 1] - h_off_b[i]);
+  eng->res_a.resize((size_t)eng->res_off[n] + 1);
+  eng->res_b.resize((size_t)eng->res_off[n] + 1);
+  eng->aln_start.resize(n); eng->aln_len.resize(n); eng->pos_a.resize(n); eng->pos_b.resize(n);
+  eng->len_a.resize(n); eng->len_b.resize(n); eng->status.resize(n);
+
+  std::vector<int64_t> dir_off, out_off;
+  size_t c0 = 0;
+  while(c0 < n) {
+    /* wave [c0, c1) */
+    size_t c1 = c0;
+    int64_t dbytes = 0;
+    dir_off.clear(); out_off.clear();
+    while(c1 < n) {
+      const int64_t la = h_off_a[c1 + 1] - h_off_a[c1], lb = h_off_b[c1 + 1] - h_off_b[c1];
+      const int64_t need = dir_bytes(la, lb);
+      if(c1 > c0 && dbytes + need > budget) break;
+      dir_off.push_back(dbytes);
+      out_off.push_back(eng->res_off[c1] - eng->res_off[c0]);
+      dbytes += need;
+      c1++;
+    }
+    const size_t m = c1 - c0;
+    const int64_t obytes = eng->res_off[c1] - eng->res_off[c0];
+    TRY(ensure_dev(eng, eng->d_dir, (size_t)dbytes + 16));
+    TRY(ensure_dev(eng, eng->d_dir_off, m * 8));
+    TRY(ensure_dev(eng, eng->d_out_off, m * 8));
+    TRY(ensure_dev(eng, eng->d_out_a, (size_t)obytes + 16));
+    TRY(ensure_dev(eng, eng->d_out_b, (size_t)obytes + 16));
+    TRY(ensure_dev(eng, eng->d_walk, m * 4 * 7));
+    TRY(ensure_pin(eng, eng->h_walk, m * 4 * 7));
+    TRY(ensure_pin(eng, eng->h_str_a, (size_t)obytes + 16));
+    TRY(ensure_pin(eng, eng->h_str_b, (size_t)obytes + 16));
+    CU_TRY(cudaMemcpyAsync(eng->d_dir_off.p, dir_off.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(eng->d_out_off.p, out_off.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+
+    GenArgs X;
+    memset(&X, 0, sizeof(X));
+    X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = d_state;
+    X.dir = (uint8_t *)eng->d_dir.p;
+    X.dir_off = (const int64_t *)eng->d_dir_off.p;
+    CU_TRY(cudaEventRecord(eng->ev0, st));
+    TRY(launch_general<MODE_DIR>(eng, db, sp, (int64_t)c0, (int64_t)m, bm, X, st));
+    CU_TRY(cudaEventRecord(eng->ev1, st));
+
+    WalkArgs W;
+    memset(&W, 0, sizeof(W));
+    W.seq_a = db.a; W.seq_b = db.b; W.off_a = db.off_a; W.off_b = db.off_b;
+    W.pair0 = (int64_t)c0; W.npairs = (int64_t)m; W.sp = sp;
+    W.sub = (const int32_t *)eng->d_sub.p; W.lut = (const uint8_t *)eng->d_lut.p;
+    W.score = d_score; W.xend = d_xend; W.yend = d_yend; W.state = d_state;
+    W.dir = (const uint8_t *)eng->d_dir.p; W.dir_off = (const int64_t *)eng->d_dir_off.p;
+    W.out_a = (uint8_t *)eng->d_out_a.p; W.out_b = (uint8_t *)eng->d_out_b.p;
+    W.out_off = (const int64_t *)eng->d_out_off.p;
+    int32_t *wk = (int32_t *)eng->d_walk.p;
+    W.aln_start = wk; W.aln_len = wk + m; W.pos_a = wk + 2 * m; W.pos_b = wk + 3 * m;
+    W.len_a = wk + 4 * m; W.len_b = wk + 5 * m; W.status = wk + 6 * m;
+    int wgrid = (int)((m + 127) / 128);
+    if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
+    SA_LAUNCH(walk_kernel, wgrid, 128, 0, st, W);
+    CU_TRY(cudaGetLastError());
+    eng->last_launches++;
+
+    CU_TRY(cudaMemcpyAsync(eng->h_walk.p, eng->d_walk.p, m * 4 * 7, cudaMemcpyDeviceToHost, st));
+    if(obytes > 0) {
+      CU_TRY(cudaMemcpyAsync(eng->h_str_a.p, eng->d_out_a.p, (size_t)obytes, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(eng->h_str_b.p, eng->d_out_b.p, (size_t)obytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    eng->last_ms += ms;
+
+    const int32_t *hw = (const int32_t *)eng->h_walk.p;
+    memcpy(&eng->aln_start[c0], hw, m * 4);
+    memcpy(&eng->aln_len[c0], hw + m, m * 4);
+    memcpy(&eng->pos_a[c0], hw + 2 * m, m * 4);
+    memcpy(&eng->pos_b[c0], hw + 3 * m, m * 4);
+    memcpy(&eng->len_a[c0], hw + 4 * m, m * 4);
+    memcpy(&eng->len_b[c0], hw + 5 * m, m * 4);
+    memcpy(&eng->status[c0], hw + 6 * m, m * 4);
+    if(obytes > 0) {
+      memcpy(&eng->res_a[(size_t)eng->res_off[c0]], eng->h_str_a.p, (size_t)obytes);
+      memcpy(&eng->res_b[(size_t)eng->res_off[c0]], eng->h_str_b.p, (size_t)obytes);
+    }
+    c0 = c1;
+  }
+  eng->last_kernel = algo == SEQALIGN_SW ? "general_score+general_dir+walk" : "general_dir+walk";
+
+  /* scores to host */
+  eng->score.resize(n); eng->xend.resize(n); eng->yend.resize(n);
+  TRY(ensure_pin(eng, eng->h_res, n * 12));
+  int32_t *hr = (int32_t *)eng->h_res.p;
+  CU_TRY(cudaMemcpyAsync(hr, d_score, n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(hr + n, d_xend, n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(hr + 2 * n, d_yend, n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  memcpy(eng->score.data(), hr, n * 4);
+  memcpy(eng->xend.data(), hr + n, n * 4);
+  memcpy(eng->yend.data(), hr + 2 * n, n * 4);
+
+  for(size_t i = 0; i < n; i++)
+    if(eng->status[i] == WALK_FAIL) {
+      char msg[128];
+      snprintf(msg, sizeof(msg), "Program error: traceback fail (get_reverse_move), pair %zu", i);
+      eng->err = msg;
+      return SEQALIGN_ERR_TRACEBACK;
+    }
+  return 0;
+}
+
+int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
+                  const char *h_b, const int64_t *h_off_b, size_t n)
+{
+  eng->err.clear();
+  eng->n = 0;
+  eng->last_launches = 0;
+  eng->last_ms = 0;
+  if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
+  if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN))
+    return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
+  eng->algo = algo; eng->mode = mode;
+  eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);
+  if(n == 0) return 0;
+  cudaStream_t st = eng->stream;
+  const int64_t total_a = h_off_a[n], total_b = h_off_b[n];
+  for(size_t i = 0; i < n; i++) {
+    const int64_t la = h_off_a[i + 1] - h_off_a[i], lb = h_off_b[i + 1] - h_off_b[i];
+    if(la < 0 || lb < 0 || la > (1 << 30) || lb > (1 << 30))
+      return fail(eng, SEQALIGN_ERR_ARG, "bad offsets / sequence too long");
+  }
+  TRY(ensure_dev(eng, eng->d_seq_a, (size_t)total_a + 32));
+  TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
+  TRY(ensure_dev(eng, eng->d_off_a, (n + 1) * 8));
+  TRY(ensure_dev(eng, eng->d_off_b, (n + 1) * 8));
+  if(total_a) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, h_a, (size_t)total_a, cudaMemcpyHostToDevice, st));
+  if(total_b) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, h_b, (size_t)total_b, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+
+  DevBatch db;
+  db.a = (const uint8_t *)eng->d_seq_a.p; db.b = (const uint8_t *)eng->d_seq_b.p;
+  db.off_a = (const int64_t *)eng->d_off_a.p; db.off_b = (const int64_t *)eng->d_off_b.p;
+  db.n = n;
+  BatchMeta bm;
+  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a, total_b, st, &bm));
+  TRY(upload_tables(eng, bm, st));
+  if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
+
+  if(mode == SEQALIGN_MODE_SCORE) {
+    TRY(ensure_dev(eng, eng->d_score, n * 4));
+    TRY(ensure_dev(eng, eng->d_xend, n * 4));
+    TRY(ensure_dev(eng, eng->d_yend, n * 4));
+    TRY(run_score(eng, algo, db, bm, (int32_t *)eng->d_score.p, (int32_t *)eng->d_xend.p,
+                  (int32_t *)eng->d_yend.p, st));
+    TRY(ensure_pin(eng, eng->h_res, n * 12));
+    int32_t *hr = (int32_t *)eng->h_res.p;
+    CU_TRY(cudaMemcpyAsync(hr, eng->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hr + n, eng->d_xend.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hr + 2 * n, eng->d_yend.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    eng->last_ms = ms;
+    memcpy(eng->score.data(), hr, n * 4);
+    memcpy(eng->xend.data(), hr + n, n * 4);
+    memcpy(eng->yend.data(), hr + 2 * n, n * 4);
+  } else {
+    TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
+  }
+  eng->n = n;
+  return 0;
+}
+
+} // namespace
+
+/* =========================================================================
+ * C-ABI
+ */
+extern "C" {
+
+int seqalign_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for(int i = 0; i < n; i++) {
+    cudaDeviceProp p;
+    if(cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+
+const char *seqalign_version(void) { return "seqalign_b200 0.1 (sm_100a)"; }
+
+const char *seqalign_last_create_error(void) { return g_create_error.c_str(); }
+
+seqalign_batch_t *seqalign_batch_create(int device)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if(e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (this library has no CPU path)";
+    cudaGetLastError();
+    return nullptr;
+  }
+  if(device < 0 || device >= n) { g_create_error = "device index out of range"; return nullptr; }
+  cudaDeviceProp p;
+  if(cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&p, device) != cudaSuccess) {
+    g_create_error = "cannot select device";
+    return nullptr;
+  }
+  if(p.major != 10) {
+    g_create_error = std::string("device '") + p.name + "' is not sm_100: kernels are built for sm_100a only";
+    return nullptr;
+  }
+  seqalign_batch *eng = new seqalign_batch();
+  eng->device = device;
+  eng->num_sms = p.multiProcessorCount;
+  eng->smem_optin = p.sharedMemPerBlockOptin;
+  if(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking) != cudaSuccess ||
+     cudaEventCreate(&eng->ev0) != cudaSuccess || cudaEventCreate(&eng->ev1) != cudaSuccess) {
+    g_create_error = "cannot create stream/events";
+    delete eng;
+    return nullptr;
+  }
+  eng->scoring = (scoring_t *)malloc(sizeof(scoring_t));
+  return eng;
+}
+
+void seqalign_batch_destroy(seqalign_batch_t *eng)
+{
+  if(!eng) return;
+  cudaSetDevice(eng->device);
+  DevBuf *d[] = {&eng->d_seq_a, &eng->d_seq_b, &eng->d_off_a, &eng->d_off_b, &eng->d_meta, &eng->d_counter,
+                 &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
+                 &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
+                 &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats};
+  for(DevBuf *b : d) b->release();
+  PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
+                 &eng->h_walk, &eng->h_str_a, &eng->h_str_b};
+  for(PinBuf *b : h) b->release();
+  if(eng->ev0) cudaEventDestroy(eng->ev0);
+  if(eng->ev1) cudaEventDestroy(eng->ev1);
+  if(eng->stream) cudaStreamDestroy(eng->stream);
+  free(eng->scoring);
+  delete eng;
+}
+
+const char *seqalign_batch_error(const seqalign_batch_t *eng) { return eng ? eng->err.c_str() : "null engine"; }
+
+int seqalign_batch_set_scoring(seqalign_batch_t *eng, const scoring_t *scoring)
+{
+  if(!eng || !scoring) return SEQALIGN_ERR_ARG;
+  memcpy(eng->scoring, scoring, sizeof(scoring_t));
+  eng->have_scoring = true;
+  return 0;
+}
+
+void seqalign_batch_force_general(seqalign_batch_t *eng, int on) { if(eng) eng->force_general = on != 0; }
+
+int seqalign_batch_submit_packed(seqalign_batch_t *eng, int algo, int mode,
+                                 const char *seq_a, const int64_t *off_a,
+                                 const char *seq_b, const int64_t *off_b, size_t n)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  if(n > 0 && (!off_a || !off_b)) return fail(eng, SEQALIGN_ERR_ARG, "null offsets");
+  CU_TRY(cudaSetDevice(eng->device));
+  if(n > 0 && (off_a[0] != 0 || off_b[0] != 0)) return fail(eng, SEQALIGN_ERR_ARG, "offsets must start at 0");
+  return submit_common(eng, algo, mode, seq_a, off_a, seq_b, off_b, n);
+}
+
+int seqalign_batch_submit(seqalign_batch_t *eng, int algo, int mode,
+                          const char *const *seq_a, const size_t *len_a,
+                          const char *const *seq_b, const size_t *len_b, size_t n)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  CU_TRY(cudaSetDevice(eng->device));
+  size_t ta = 0, tb = 0;
+  for(size_t i = 0; i < n; i++) { ta += len_a[i]; tb += len_b[i]; }
+  TRY(ensure_pin(eng, eng->h_in_a, ta + 16));
+  TRY(ensure_pin(eng, eng->h_in_b, tb + 16));
+  TRY(ensure_pin(eng, eng->h_off_a, (n + 1) * 8));
+  TRY(ensure_pin(eng, eng->h_off_b, (n + 1) * 8));
+  char *pa = (char *)eng->h_in_a.p, *pb = (char *)eng->h_in_b.p;
+  int64_t *oa = (int64_t *)eng->h_off_a.p, *ob = (int64_t *)eng->h_off_b.p;
+  oa[0] = ob[0] = 0;
+  for(size_t i = 0; i < n; i++) {
+    memcpy(pa + oa[i], seq_a[i], len_a[i]);
+    memcpy(pb + ob[i], seq_b[i], len_b[i]);
+    oa[i + 1] = oa[i] + (int64_t)len_a[i];
+    ob[i + 1] = ob[i] + (int64_t)len_b[i];
+  }
+  return submit_common(eng, algo, mode, pa, oa, pb, ob, n);
+}
+
+size_t seqalign_batch_size(const seqalign_batch_t *eng) { return eng ? eng->n : 0; }
+
+int seqalign_batch_scores(seqalign_batch_t *eng, int32_t *score)
+{
+  if(!eng || !score) return SEQALIGN_ERR_ARG;
+  memcpy(score, eng->score.data(), eng->n * 4);
+  return 0;
+}
+
+int seqalign_batch_ends(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  if(score) memcpy(score, eng->score.data(), eng->n * 4);
+  if(x_end) memcpy(x_end, eng->xend.data(), eng->n * 4);
+  if(y_end) memcpy(y_end, eng->yend.data(), eng->n * 4);
+  return 0;
+}
+
+int seqalign_batch_alignment(seqalign_batch_t *eng, size_t i, alignment_t *out)
+{
+  if(!eng || !out) return SEQALIGN_ERR_ARG;
+  if(eng->mode != SEQALIGN_MODE_ALIGN || i >= eng->n) return fail(eng, SEQALIGN_ERR_ARG, "no alignment for this index");
+  if(eng->status[i] == WALK_FAIL) return fail(eng, SEQALIGN_ERR_TRACEBACK, "traceback fail");
+  if(eng->status[i] == WALK_NOHIT) return 0;
+  const size_t len = (size_t)eng->aln_len[i];
+  /* grow like alignment_ensure_capacity (reference alignment.c:219-233) */
+  if(out->capacity < len + 1) {
+    size_t cap = ROUNDUP2POW(len + 1);
+    out->result_a = (char *)realloc(out->result_a, cap);
+    out->result_b = (char *)realloc(out->result_b, cap);
+    out->capacity = cap;
+    if(!out->result_a || !out->result_b) return fail(eng, SEQALIGN_ERR_NOMEM, "Out of memory");
+  }
+  const size_t base = (size_t)eng->res_off[i] + (size_t)eng->aln_start[i];
+  memcpy(out->result_a, &eng->res_a[base], len);
+  memcpy(out->result_b, &eng->res_b[base], len);
+  out->result_a[len] = out->result_b[len] = '\0';
+  out->length = len;
+  out->score = eng->score[i];
+  if(eng->algo == SEQALIGN_SW) {
+    out->pos_a = (size_t)eng->pos_a[i]; out->pos_b = (size_t)eng->pos_b[i];
+    out->len_a = (size_t)eng->len_a[i]; out->len_b = (size_t)eng->len_b[i];
+  }
+  return 1;
+}
+
+int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
+                              const void *d_seq_a, const void *d_off_a,
+                              const void *d_seq_b, const void *d_off_b,
+                              size_t n, void *d_score, void *d_x_end, void *d_y_end, void *stream)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  eng->err.clear();
+  eng->last_launches = 0;
+  if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
+  if(n == 0) return 0;
+  CU_TRY(cudaSetDevice(eng->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : eng->stream;
+  /* totals: last offsets */
+  int64_t tot[2];
+  CU_TRY(cudaMemcpyAsync(&tot[0], (const int64_t *)d_off_a + n, 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&tot[1], (const int64_t *)d_off_b + n, 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  DevBatch db;
+  db.a = (const uint8_t *)d_seq_a; db.b = (const uint8_t *)d_seq_b;
+  db.off_a = (const int64_t *)d_off_a; db.off_b = (const int64_t *)d_off_b;
+  db.n = n;
+  BatchMeta bm;
+  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, tot[0], tot[1], st, &bm));
+  TRY(upload_tables(eng, bm, st));
+  if(eng->ft.any_unknown) {
+    std::vector<char> ha((size_t)tot[0] + 1), hb((size_t)tot[1] + 1);
+    std::vector<int64_t> oa(n + 1), ob(n + 1);
+    CU_TRY(cudaMemcpy(ha.data(), d_seq_a, (size_t)tot[0], cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(hb.data(), d_seq_b, (size_t)tot[1], cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(oa.data(), d_off_a, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ob.data(), d_off_b, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    TRY(check_unknown_pairs(eng, ha.data(), oa.data(), hb.data(), ob.data(), n));
+  }
+  TRY(run_score(eng, algo, db, bm, (int32_t *)d_score, (int32_t *)d_x_end, (int32_t *)d_y_end, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+  eng->last_ms = ms;
+  return 0;
+}
+
+int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_a,
+                           const char *seq_b, size_t len_b, int is_sw,
+                           int32_t *match, int32_t *gap_a, int32_t *gap_b)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  eng->err.clear();
+  eng->last_launches = 0;
+  if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
+  if(len_a > (1u << 30) || len_b > (1u << 30)) return fail(eng, SEQALIGN_ERR_ARG, "sequence too long");
+  CU_TRY(cudaSetDevice(eng->device));
+  cudaStream_t st = eng->stream;
+  const int64_t off_a[2] = {0, (int64_t)len_a}, off_b[2] = {0, (int64_t)len_b};
+  TRY(ensure_dev(eng, eng->d_seq_a, len_a + 32));
+  TRY(ensure_dev(eng, eng->d_seq_b, len_b + 32));
+  TRY(ensure_dev(eng, eng->d_off_a, 16));
+  TRY(ensure_dev(eng, eng->d_off_b, 16));
+  if(len_a) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, seq_a, len_a, cudaMemcpyHostToDevice, st));
+  if(len_b) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, seq_b, len_b, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, off_a, 16, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, off_b, 16, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  DevBatch db;
+  db.a = (const uint8_t *)eng->d_seq_a.p; db.b = (const uint8_t *)eng->d_seq_b.p;
+  db.off_a = (const int64_t *)eng->d_off_a.p; db.off_b = (const int64_t *)eng->d_off_b.p;
+  db.n = 1;
+  BatchMeta bm;
+  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, 1, off_a[1], off_b[1], st, &bm));
+  TRY(upload_tables(eng, bm, st));
+  if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, seq_a, off_a, seq_b, off_b, 1));
+
+  const ScoreParams sp = make_params(eng->scoring, is_sw, eng->ft.ncodes);
+  const int64_t pitch = ((int64_t)len_a + 4 + 3) & ~(int64_t)3;
+  const size_t mat_ints = (size_t)pitch * (len_b + 1) + 16;
+  TRY(ensure_dev(eng, eng->d_mats, mat_ints * 4 * 3));
+  GenArgs X;
+  memset(&X, 0, sizeof(X));
+  X.mat_m = (int32_t *)eng->d_mats.p;
+  X.mat_ga = X.mat_m + mat_ints;
+  X.mat_gb = X.mat_ga + mat_ints;
+  X.pitch = pitch;
+  CU_TRY(cudaEventRecord(eng->ev0, st));
+  TRY(launch_general<MODE_MATS>(eng, db, sp, 0, 1, bm, X, st));
+  CU_TRY(cudaEventRecord(eng->ev1, st));
+  const size_t w = (len_a + 1) * 4;
+  int32_t *dst[3] = {match, gap_a, gap_b};
+  int32_t *src[3] = {X.mat_m, X.mat_ga, X.mat_gb};
+  for(int k = 0; k < 3; k++)
+    CU_TRY(cudaMemcpy2DAsync(dst[k], w, src[k] + 3, (size_t)pitch * 4, w, len_b + 1, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+  eng->last_ms = ms;
+  eng->last_kernel = "general_mats";
+  return 0;
+}
+
+void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b)
+{
+  if(!eng) return;
+  if(a) *a = eng->unk_a;
+  if(b) *b = eng->unk_b;
+}
+
+double seqalign_batch_last_kernel_ms(const seqalign_batch_t *eng) { return eng ? eng->last_ms : 0; }
+int seqalign_batch_last_launches(const seqalign_batch_t *eng) { return eng ? eng->last_launches : 0; }
+const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng) { return eng ? eng->last_kernel : "none"; }
+
+} /* extern "C" */

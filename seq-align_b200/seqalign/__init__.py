@@ -1,0 +1,399 @@
+"""seqalign -- Python binding of the B200-native seq-align hot path.
+
+Thin ctypes layer over ``libseqalign_b200.so`` (CUDA engine + C-ABI, see
+``include/seqalign_b200.h``) that mirrors the reference's C API names:
+``Scoring`` wraps ``scoring_t`` (reference src/alignment_scoring.h:19-40),
+``needleman_wunsch`` / ``smith_waterman`` are the single-pair calls
+(reference src/needleman_wunsch.h:22-32, src/smith_waterman.h:21-39) and
+``BatchAligner`` is the batch entry point the GPU needs.
+
+There is no CPU implementation behind this module: loading fails loudly if
+the shared library has not been built (``make``), and creating an engine
+fails loudly when no sm_100 device is usable.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "lib", "libseqalign_b200.so")
+
+NW = 0
+SW = 1
+MODE_SCORE = 0
+MODE_ALIGN = 1
+
+ERR_CUDA = -1
+ERR_UNKNOWN_PAIR = -2
+ERR_TRACEBACK = -3
+ERR_ARG = -4
+ERR_NOMEM = -5
+
+
+class SeqAlignError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("seqalign error %d: %s" % (code, message))
+        self.code = code
+
+
+class ScoringT(ctypes.Structure):
+    """Field-for-field image of scoring_t (the layout is ABI)."""
+
+    _fields_ = [
+        ("gap_open", ctypes.c_int),
+        ("gap_extend", ctypes.c_int),
+        ("no_start_gap_penalty", ctypes.c_bool),
+        ("no_end_gap_penalty", ctypes.c_bool),
+        ("no_gaps_in_a", ctypes.c_bool),
+        ("no_gaps_in_b", ctypes.c_bool),
+        ("no_mismatches", ctypes.c_bool),
+        ("use_match_mismatch", ctypes.c_bool),
+        ("match", ctypes.c_int),
+        ("mismatch", ctypes.c_int),
+        ("case_sensitive", ctypes.c_bool),
+        ("wildcards", ctypes.c_uint32 * 8),
+        ("swap_set", (ctypes.c_uint32 * 8) * 256),
+        ("wildscores", ctypes.c_int * 256),
+        ("swap_scores", (ctypes.c_int * 256) * 256),
+        ("min_penalty", ctypes.c_int),
+        ("max_penalty", ctypes.c_int),
+    ]
+
+
+class AlignmentT(ctypes.Structure):
+    """alignment_t (reference src/alignment.h:33-40)."""
+
+    _fields_ = [
+        ("result_a", ctypes.c_void_p),
+        ("result_b", ctypes.c_void_p),
+        ("capacity", ctypes.c_size_t),
+        ("length", ctypes.c_size_t),
+        ("pos_a", ctypes.c_size_t),
+        ("pos_b", ctypes.c_size_t),
+        ("len_a", ctypes.c_size_t),
+        ("len_b", ctypes.c_size_t),
+        ("score", ctypes.c_int),
+    ]
+
+
+class AlignerT(ctypes.Structure):
+    """aligner_t (reference src/alignment.h:23-30)."""
+
+    _fields_ = [
+        ("scoring", ctypes.c_void_p),
+        ("seq_a", ctypes.c_void_p),
+        ("seq_b", ctypes.c_void_p),
+        ("score_width", ctypes.c_size_t),
+        ("score_height", ctypes.c_size_t),
+        ("match_scores", ctypes.POINTER(ctypes.c_int)),
+        ("gap_a_scores", ctypes.POINTER(ctypes.c_int)),
+        ("gap_b_scores", ctypes.POINTER(ctypes.c_int)),
+        ("capacity", ctypes.c_size_t),
+    ]
+
+
+_lib = None
+
+
+def lib_path():
+    return os.environ.get("SEQALIGN_LIB", _DEFAULT_LIB)
+
+
+def load():
+    """Load the shared library (once).  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s not found: build it with `make` (nvcc, sm_100a). "
+            "This package has no CPU implementation." % path
+        )
+    L = ctypes.CDLL(path)
+    vp, sz, i32p = ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)
+    L.seqalign_device_count.restype = ctypes.c_int
+    L.seqalign_version.restype = ctypes.c_char_p
+    L.seqalign_last_create_error.restype = ctypes.c_char_p
+    L.seqalign_batch_create.restype = vp
+    L.seqalign_batch_create.argtypes = [ctypes.c_int]
+    L.seqalign_batch_destroy.argtypes = [vp]
+    L.seqalign_batch_error.restype = ctypes.c_char_p
+    L.seqalign_batch_error.argtypes = [vp]
+    L.seqalign_batch_set_scoring.argtypes = [vp, vp]
+    L.seqalign_batch_submit.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, sz]
+    L.seqalign_batch_submit_packed.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, sz]
+    L.seqalign_batch_scores.argtypes = [vp, vp]
+    L.seqalign_batch_ends.argtypes = [vp, vp, vp, vp]
+    L.seqalign_batch_size.restype = sz
+    L.seqalign_batch_size.argtypes = [vp]
+    L.seqalign_batch_alignment.argtypes = [vp, sz, vp]
+    L.seqalign_batch_run_device.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.seqalign_fill_matrices.argtypes = [vp, vp, sz, vp, sz, ctypes.c_int, vp, vp, vp]
+    L.seqalign_batch_unknown_pair.argtypes = [vp, vp, vp]
+    L.seqalign_batch_last_kernel_ms.restype = ctypes.c_double
+    L.seqalign_batch_last_kernel_ms.argtypes = [vp]
+    L.seqalign_batch_last_launches.restype = ctypes.c_int
+    L.seqalign_batch_last_launches.argtypes = [vp]
+    L.seqalign_batch_last_kernel.restype = ctypes.c_char_p
+    L.seqalign_batch_last_kernel.argtypes = [vp]
+    L.seqalign_batch_force_general.argtypes = [vp, ctypes.c_int]
+    # reference C API
+    L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
+    L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
+    L.scoring_add_mutation.argtypes = [vp, ctypes.c_char, ctypes.c_char, ctypes.c_int]
+    L.scoring_add_mutations.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_char]
+    L.scoring_lookup.argtypes = [vp, ctypes.c_char, ctypes.c_char, vp, vp]
+    for name in ("PAM30", "PAM70", "BLOSUM80", "BLOSUM62", "DNA_hybridization", "default"):
+        getattr(L, "scoring_system_" + name).argtypes = [vp]
+    L.alignment_create.restype = ctypes.POINTER(AlignmentT)
+    L.alignment_create.argtypes = [sz]
+    L.alignment_free.argtypes = [ctypes.POINTER(AlignmentT)]
+    L.needleman_wunsch_new.restype = ctypes.POINTER(AlignerT)
+    L.needleman_wunsch_free.argtypes = [ctypes.POINTER(AlignerT)]
+    L.needleman_wunsch_align2.argtypes = [vp, vp, sz, sz, vp, ctypes.POINTER(AlignerT), ctypes.POINTER(AlignmentT)]
+    L.smith_waterman_new.restype = vp
+    L.smith_waterman_free.argtypes = [vp]
+    L.smith_waterman_get_aligner.restype = ctypes.POINTER(AlignerT)
+    L.smith_waterman_get_aligner.argtypes = [vp]
+    L.smith_waterman_align2.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.smith_waterman_fetch.argtypes = [vp, ctypes.POINTER(AlignmentT)]
+    L.aligner_align.argtypes = [ctypes.POINTER(AlignerT), vp, vp, sz, sz, vp, ctypes.c_char]
+    L.aligner_destroy.argtypes = [ctypes.POINTER(AlignerT)]
+    _lib = L
+    return L
+
+
+def device_count():
+    return load().seqalign_device_count()
+
+
+class Scoring:
+    """scoring_t with the reference's constructors.
+
+    ``Scoring(match, mismatch, gap_open, gap_extend, ...)`` is scoring_init;
+    ``Scoring.system("BLOSUM62")`` the built-in systems; ``poke`` overwrites
+    fields in place the way the CLI does (reference
+    src/alignment_cmdline.c:401-439, src/tools/sw_cmdline.c:42-45), leaving
+    min_penalty/max_penalty untouched.
+    """
+
+    def __init__(self, match=1, mismatch=-2, gap_open=-4, gap_extend=-1,
+                 no_start_gap_penalty=False, no_end_gap_penalty=False,
+                 no_gaps_in_a=False, no_gaps_in_b=False,
+                 no_mismatches=False, case_sensitive=False):
+        self.s = ScoringT()
+        load().scoring_init(ctypes.byref(self.s), match, mismatch, gap_open, gap_extend,
+                            no_start_gap_penalty, no_end_gap_penalty, no_gaps_in_a,
+                            no_gaps_in_b, no_mismatches, case_sensitive)
+
+    @classmethod
+    def system(cls, name):
+        self = cls.__new__(cls)
+        self.s = ScoringT()
+        getattr(load(), "scoring_system_" + name)(ctypes.byref(self.s))
+        return self
+
+    @classmethod
+    def nw_default(cls):
+        """needleman_wunsch default: 1/-2/-4/-1 (reference alignment_scoring.c:380-392)."""
+        return cls.system("default")
+
+    @classmethod
+    def sw_cli_default(cls):
+        """smith_waterman CLI default: default system poked to 2/-2/-2/-1
+        (reference src/tools/sw_cmdline.c:37-46)."""
+        return cls.system("default").poke(match=2, mismatch=-2, gap_open=-2, gap_extend=-1)
+
+    def poke(self, **fields):
+        for k, v in fields.items():
+            setattr(self.s, k, v)
+        return self
+
+    def add_wildcard(self, c, score):
+        load().scoring_add_wildcard(ctypes.byref(self.s), c.encode() if isinstance(c, str) else c, score)
+        return self
+
+    def add_mutation(self, a, b, score):
+        enc = lambda c: c.encode() if isinstance(c, str) else c
+        load().scoring_add_mutation(ctypes.byref(self.s), enc(a), enc(b), score)
+        return self
+
+    def add_mutations(self, letters, scores, use_match_mismatch=True):
+        n = len(letters)
+        arr = (ctypes.c_int * (n * n))(*[int(v) for v in scores])
+        load().scoring_add_mutations(ctypes.byref(self.s), letters.encode(), arr,
+                                     bytes([1 if use_match_mismatch else 0]))
+        return self
+
+    def lookup(self, a, b):
+        score = ctypes.c_int()
+        is_match = ctypes.c_bool()
+        enc = lambda c: c.encode() if isinstance(c, str) else c
+        load().scoring_lookup(ctypes.byref(self.s), enc(a), enc(b), ctypes.byref(score), ctypes.byref(is_match))
+        return score.value, bool(is_match.value)
+
+    @property
+    def ptr(self):
+        return ctypes.byref(self.s)
+
+
+def pack(seqs):
+    """list of bytes/str -> (uint8 array, int64 offsets[n+1])"""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return data, off
+
+
+class Alignment:
+    __slots__ = ("result_a", "result_b", "score", "pos_a", "pos_b", "len_a", "len_b", "length")
+
+    def __init__(self, al):
+        n = al.length
+        self.result_a = ctypes.string_at(al.result_a, n)
+        self.result_b = ctypes.string_at(al.result_b, n)
+        self.length = n
+        self.score = al.score
+        self.pos_a, self.pos_b, self.len_a, self.len_b = al.pos_a, al.pos_b, al.len_a, al.len_b
+
+    def __repr__(self):
+        return "Alignment(%r, %r, score=%d)" % (self.result_a, self.result_b, self.score)
+
+
+class BatchAligner:
+    """One engine on one device (seqalign_batch_t)."""
+
+    def __init__(self, device=0, scoring=None):
+        L = load()
+        self._L = L
+        self._h = L.seqalign_batch_create(device)
+        if not self._h:
+            raise SeqAlignError(ERR_CUDA, L.seqalign_last_create_error().decode())
+        self._res = L.alignment_create(256)
+        self._keep = None
+        if scoring is not None:
+            self.set_scoring(scoring)
+
+    def close(self):
+        if self._h:
+            self._L.alignment_free(self._res)
+            self._L.seqalign_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise SeqAlignError(rc, self._L.seqalign_batch_error(self._h).decode())
+        return rc
+
+    def set_scoring(self, scoring):
+        self._check(self._L.seqalign_batch_set_scoring(self._h, scoring.ptr))
+
+    def force_general(self, on=True):
+        self._L.seqalign_batch_force_general(self._h, 1 if on else 0)
+
+    def submit_packed(self, algo, mode, seq_a, off_a, seq_b, off_b):
+        """Host arrays (numpy uint8 / int64, or anything exposing ctypes.data)."""
+        n = len(off_a) - 1
+        self._keep = (seq_a, off_a, seq_b, off_b)
+        self._check(self._L.seqalign_batch_submit_packed(
+            self._h, algo, mode, seq_a.ctypes.data, off_a.ctypes.data,
+            seq_b.ctypes.data, off_b.ctypes.data, n))
+        return n
+
+    def submit_ptrs(self, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n):
+        """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        self._check(self._L.seqalign_batch_submit_packed(self._h, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n))
+        return n
+
+    def submit(self, algo, mode, seqs_a, seqs_b):
+        a, oa = pack(seqs_a)
+        b, ob = pack(seqs_b)
+        return self.submit_packed(algo, mode, a, oa, b, ob)
+
+    def scores(self):
+        n = self._L.seqalign_batch_size(self._h)
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self._L.seqalign_batch_scores(self._h, out.ctypes.data))
+        return out
+
+    def ends(self):
+        n = self._L.seqalign_batch_size(self._h)
+        s, x, y = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        self._check(self._L.seqalign_batch_ends(self._h, s.ctypes.data, x.ctypes.data, y.ctypes.data))
+        return s, x, y
+
+    def alignment(self, i):
+        """Alignment of pair i (None for an SW pair without a hit)."""
+        rc = self._check(self._L.seqalign_batch_alignment(self._h, i, self._res))
+        return Alignment(self._res.contents) if rc == 1 else None
+
+    def run_device(self, algo, d_seq_a, d_off_a, d_seq_b, d_off_b, n, d_score, d_xend=0, d_yend=0, stream=0):
+        """Device pointers (ints); results stay on the device."""
+        self._check(self._L.seqalign_batch_run_device(self._h, algo, d_seq_a, d_off_a, d_seq_b, d_off_b,
+                                                       n, d_score, d_xend or None, d_yend or None,
+                                                       stream or None))
+
+    def fill_matrices(self, a, b, is_sw):
+        a = a.encode() if isinstance(a, str) else bytes(a)
+        b = b.encode() if isinstance(b, str) else bytes(b)
+        cells = (len(a) + 1) * (len(b) + 1)
+        m, ga, gb = (np.zeros(cells, dtype=np.int32) for _ in range(3))
+        self._check(self._L.seqalign_fill_matrices(self._h, a, len(a), b, len(b), 1 if is_sw else 0,
+                                                    m.ctypes.data, ga.ctypes.data, gb.ctypes.data))
+        shape = (len(b) + 1, len(a) + 1)
+        return m.reshape(shape), ga.reshape(shape), gb.reshape(shape)
+
+    @property
+    def last_kernel_ms(self):
+        return self._L.seqalign_batch_last_kernel_ms(self._h)
+
+    @property
+    def last_launches(self):
+        return self._L.seqalign_batch_last_launches(self._h)
+
+    @property
+    def last_kernel(self):
+        return self._L.seqalign_batch_last_kernel(self._h).decode()
+
+
+def needleman_wunsch(a, b, scoring):
+    """needleman_wunsch_align through the C API (single pair)."""
+    L = load()
+    a = a.encode() if isinstance(a, str) else bytes(a)
+    b = b.encode() if isinstance(b, str) else bytes(b)
+    nw = L.needleman_wunsch_new()
+    res = L.alignment_create(256)
+    try:
+        L.needleman_wunsch_align2(a, b, len(a), len(b), scoring.ptr, nw, res)
+        return Alignment(res.contents)
+    finally:
+        L.alignment_free(res)
+        L.needleman_wunsch_free(nw)
+
+
+def smith_waterman(a, b, scoring, max_hits=None):
+    """smith_waterman_align + fetch loop through the C API (single pair)."""
+    L = load()
+    a = a.encode() if isinstance(a, str) else bytes(a)
+    b = b.encode() if isinstance(b, str) else bytes(b)
+    sw = L.smith_waterman_new()
+    res = L.alignment_create(256)
+    hits = []
+    try:
+        L.smith_waterman_align2(a, b, len(a), len(b), scoring.ptr, sw)
+        while (max_hits is None or len(hits) < max_hits) and L.smith_waterman_fetch(sw, res):
+            hits.append(Alignment(res.contents))
+        return hits
+    finally:
+        L.alignment_free(res)
+        L.smith_waterman_free(sw)
