@@ -224,26 +224,51 @@ def ragged_batch(seed, npairs, max_a, max_b, alphabet=b"ACGT", min_len=0, relate
     return sa, sb
 
 
-# scoring specs used across the suites: name -> constructor
-def scoring_specs():
+# ---------------------------------------------------------------------------
+# scoring specs: plain data, so the same spec can drive the product
+# (seqalign.Scoring), the oracle (via orc_from_scoring) and the compiled
+# reference (tools/gen_golden.py)
+#   init: match, mismatch, gap_open, gap_extend, no_start, no_end,
+#         no_gaps_in_a, no_gaps_in_b, no_mismatches, case_sensitive
+SPECS = {
+    "nw_default": dict(system="default"),
+    "sw_cli": dict(system="default", poke=dict(match=2, mismatch=-2, gap_open=-2, gap_extend=-1)),
+    "free_ends": dict(init=[1, -2, -4, -1, 1, 1, 0, 0, 0, 0]),
+    "free_start": dict(init=[1, -1, -4, -1, 1, 0, 0, 0, 0, 0]),
+    "free_end": dict(init=[1, -1, -4, -1, 0, 1, 0, 0, 0, 0]),
+    "linear_gap": dict(init=[2, -3, 0, -2, 0, 0, 0, 0, 0, 0]),
+    "no_gaps_a": dict(init=[1, -2, -4, -1, 0, 0, 1, 0, 0, 0]),
+    "no_gaps_b": dict(init=[1, -2, -4, -1, 0, 0, 0, 1, 0, 0]),
+    "no_mismatch": dict(init=[1, -2, -4, -1, 0, 0, 0, 0, 1, 0]),
+    "case_sens": dict(init=[1, -2, -4, -1, 0, 0, 0, 0, 0, 1]),
+    "wild_n": dict(init=[1, -2, -4, -1, 0, 0, 0, 0, 0, 0], wildcards=[["N", 0]]),
+    "no_mismatch_wild": dict(init=[1, -2, -4, -1, 0, 0, 0, 0, 1, 0], wildcards=[["N", -1]]),
+    "mutations": dict(init=[3, -3, -5, -2, 0, 0, 0, 0, 0, 0],
+                      mutations=[["a", "g", -1], ["g", "a", -1], ["c", "t", 1]]),
+    "big_scores": dict(init=[300, -400, -500, -100, 0, 0, 0, 0, 0, 0]),
+    "blosum62": dict(system="BLOSUM62"),
+    "pam30": dict(system="PAM30"),
+    "pam70": dict(system="PAM70"),
+    "blosum80": dict(system="BLOSUM80"),
+    "dna_hyb": dict(system="DNA_hybridization"),
+}
+
+
+def scoring_from_spec(spec):
     S = seqalign.Scoring
-    return {
-        "nw_default": lambda: S.nw_default(),
-        "sw_cli": lambda: S.sw_cli_default(),
-        "free_ends": lambda: S(1, -2, -4, -1, True, True),
-        "free_start": lambda: S(1, -1, -4, -1, True, False),
-        "free_end": lambda: S(1, -1, -4, -1, False, True),
-        "linear_gap": lambda: S(2, -3, 0, -2),
-        "no_gaps_a": lambda: S(1, -2, -4, -1, no_gaps_in_a=True),
-        "no_gaps_b": lambda: S(1, -2, -4, -1, no_gaps_in_b=True),
-        "no_mismatch": lambda: S(1, -2, -4, -1, no_mismatches=True),
-        "case_sens": lambda: S(1, -2, -4, -1, case_sensitive=True),
-        "wild_n": lambda: S(1, -2, -4, -1).add_wildcard("N", 0),
-        "no_mismatch_wild": lambda: S(1, -2, -4, -1, no_mismatches=True).add_wildcard("N", -1),
-        "mutations": lambda: S(3, -3, -5, -2).add_mutation("a", "g", -1).add_mutation("g", "a", -1)
-                                            .add_mutation("c", "t", 1),
-        "big_scores": lambda: S(300, -400, -500, -100),
-        "blosum62": lambda: S.system("BLOSUM62"),
-        "pam30": lambda: S.system("PAM30"),
-        "dna_hyb": lambda: S.system("DNA_hybridization"),
-    }
+    if "system" in spec:
+        sc = S.system(spec["system"])
+    else:
+        i = spec["init"]
+        sc = S(i[0], i[1], i[2], i[3], *[bool(v) for v in i[4:]])
+    if "poke" in spec:
+        sc.poke(**spec["poke"])
+    for c, v in spec.get("wildcards", []):
+        sc.add_wildcard(c, v)
+    for a, b, v in spec.get("mutations", []):
+        sc.add_mutation(a, b, v)
+    return sc
+
+
+def scoring_specs():
+    return {k: (lambda spec=v: scoring_from_spec(spec)) for k, v in SPECS.items()}

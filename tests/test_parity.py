@@ -1,0 +1,339 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI.
+
+Every test here goes product library -> oracle comparison, bit-exact (int32
+scores, end cells, alignment strings, matrices).  On the GPU box these run
+on cuda:0 against libseqalign_b200.so at full sizes (marked `gpu` by
+conftest); in the build container the same tests drive the same kernel
+sources through the lane emulator at small sizes.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import seqalign
+from seqalign import NW, SW, MODE_SCORE, MODE_ALIGN
+from helpers import (ROOT, SPECS, orc_batch_nw, orc_batch_sw, orc_fill, orc_from_scoring, orc_nw,
+                     orc_sw_hits, ragged_batch, scoring_from_spec, synthetic_batch)
+
+pytestmark = pytest.mark.parity
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+PROTEIN_SPECS = ("blosum62", "pam30", "pam70", "blosum80")
+# no_gaps_* with unequal lengths are fine one flag at a time; both flags
+# together overflow in the reference itself and are excluded
+SWEEP = [n for n in SPECS]
+
+
+def _h(name):
+    return zlib.crc32(name.encode())
+
+
+def _alphabet(name):
+    if name in PROTEIN_SPECS:
+        return b"ARNDCQEGHILKMFPSTWYVBZX"
+    if name == "dna_hyb":
+        return b"ACGTacgt"
+    return b"ACGTNacgtn"
+
+
+def _score_check(engine, sc, algo, a, oa, b, ob, general):
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(general)
+    engine.submit_packed(algo, MODE_SCORE, a, oa, b, ob)
+    s, x, y = engine.ends()
+    if algo == SW:
+        es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+        assert np.array_equal(s, es), np.nonzero(s != es)[0][:8]
+        assert np.array_equal(x, ex) and np.array_equal(y, ey)
+    else:
+        es = orc_batch_nw(o, a, oa, b, ob)
+        assert np.array_equal(s, es), np.nonzero(s != es)[0][:8]
+        assert np.array_equal(x, np.diff(oa)) and np.array_equal(y, np.diff(ob))
+    assert engine.last_launches >= 1
+    return engine.last_kernel
+
+
+@pytest.mark.parametrize("algo", [SW, NW], ids=["sw", "nw"])
+@pytest.mark.parametrize("name", SWEEP)
+def test_scores_ragged(engine, big, name, algo):
+    """ragged lengths (including empty sequences), every scoring variant,
+    specialised and general kernels"""
+    n, maxlen = (300, 220) if big else (20, 44)
+    sa, sb = ragged_batch(_h(name) % 1000, n, maxlen, maxlen, alphabet=_alphabet(name))
+    a, oa = seqalign.pack(sa)
+    b, ob = seqalign.pack(sb)
+    sc = scoring_from_spec(SPECS[name])
+    _score_check(engine, sc, algo, a, oa, b, ob, general=False)
+    _score_check(engine, sc, algo, a, oa, b, ob, general=True)
+
+
+def test_headline_config_sample(engine, big):
+    """BASELINE config 2 shape: SW, DNA 150x150, smith_waterman CLI scoring"""
+    n = 4000 if big else 6
+    a, oa, b, ob = synthetic_batch(2, n, 150, 150)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    k = _score_check(engine, sc, SW, a, oa, b, ob, general=False)
+    assert k == "fast_sw_score"
+    # unrelated pairs too (throughput must not depend on the data; scores do)
+    a, oa, b, ob = synthetic_batch(12, n // 2, 150, 150, related=False)
+    _score_check(engine, sc, SW, a, oa, b, ob, general=False)
+    # library-default scoring on the same shape
+    _score_check(engine, scoring_from_spec(SPECS["nw_default"]), SW, a, oa, b, ob, general=False)
+
+
+def test_protein_config_sample(engine, big):
+    """BASELINE config 4 shape: SW, protein 400x400, BLOSUM62"""
+    n, L = (400, 400) if big else (2, 70)
+    a, oa, b, ob = synthetic_batch(4, n, L, L, kind="protein")
+    sc = scoring_from_spec(SPECS["blosum62"])
+    _score_check(engine, sc, SW, a, oa, b, ob, general=False)
+    _score_check(engine, sc, NW, a, oa, b, ob, general=False)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 37), (37, 1), (255, 20), (256, 9), (257, 9), (513, 30), (700, 3), (3, 700)])
+def test_shapes(engine, big, shape):
+    """strip boundaries of both kernels (8/256/512 columns), degenerate shapes"""
+    la, lb = shape
+    if not big and la * lb > 16000:
+        lb = max(1, 16000 // la)
+    a, oa, b, ob = synthetic_batch(la * 1000 + lb, 5 if big else 2, la, lb)
+    for name in ("sw_cli", "free_ends"):
+        sc = scoring_from_spec(SPECS[name])
+        for algo in (SW, NW):
+            _score_check(engine, sc, algo, a, oa, b, ob, general=False)
+            _score_check(engine, sc, algo, a, oa, b, ob, general=True)
+
+
+def test_empty_inputs(engine):
+    sc = scoring_from_spec(SPECS["nw_default"])
+    engine.set_scoring(sc)
+    engine.submit(NW, MODE_SCORE, [], [])
+    assert len(engine.scores()) == 0
+    engine.submit(NW, MODE_SCORE, [b"", b"", b"ACGT"], [b"", b"ACG", b""])
+    assert engine.scores().tolist() == [0, -7, -8]
+    engine.submit(SW, MODE_SCORE, [b"", b"", b"ACGT"], [b"", b"ACG", b""])
+    s, x, y = engine.ends()
+    assert s.tolist() == [0, 0, 0] and x.tolist() == [0, 0, 0] and y.tolist() == [0, 0, 0]
+    engine.submit(NW, MODE_ALIGN, [b"", b"ACGT", b""], [b"ACG", b"", b""])
+    al = [engine.alignment(i) for i in range(3)]
+    assert (al[0].result_a, al[0].result_b, al[0].score) == (b"---", b"ACG", -7)
+    assert (al[1].result_a, al[1].result_b, al[1].score) == (b"ACGT", b"----", -8)
+    assert (al[2].result_a, al[2].result_b, al[2].score) == (b"", b"", 0)
+
+
+def _check_alignment(al, algo, o, a, b):
+    if algo == NW:
+        rc, es, ea, eb = orc_nw(o, a, b)
+        assert rc == 0
+        assert al is not None
+        assert (al.score, al.result_a, al.result_b) == (es, ea, eb), (a, b)
+    else:
+        n, hits = orc_sw_hits(o, a, b, 1)
+        if n == 0:
+            assert al is None, (a, b)
+        else:
+            h = hits[0]
+            assert al is not None, (a, b)
+            assert (al.score, al.result_a, al.result_b, al.pos_a, al.pos_b, al.len_a, al.len_b) == (
+                h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"], h["len_a"], h["len_b"]), (a, b)
+
+
+@pytest.mark.parametrize("algo", [SW, NW], ids=["sw", "nw"])
+@pytest.mark.parametrize("name", SWEEP)
+def test_alignments_ragged(engine, big, name, algo):
+    """score + traceback: alignment strings byte for byte"""
+    n, maxlen = (120, 180) if big else (10, 40)
+    sa, sb = ragged_batch(7000 + _h(name) % 1000, n, maxlen, maxlen, alphabet=_alphabet(name))
+    sc = scoring_from_spec(SPECS[name])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(False)
+    engine.submit(algo, MODE_ALIGN, sa, sb)
+    for i, (a, b) in enumerate(zip(sa, sb)):
+        _check_alignment(engine.alignment(i), algo, o, a, b)
+
+
+def test_alignments_wide_and_waves(engine, big, monkeypatch):
+    """pairs wider than one strip; direction bytes processed in several waves"""
+    monkeypatch.setenv("SEQALIGN_DIR_BUDGET", "60000")
+    sa, sb = ragged_batch(77, 6 if big else 3, 640 if big else 300, 200 if big else 60, min_len=40)
+    for name, algo in (("nw_default", NW), ("free_ends", NW), ("sw_cli", SW)):
+        sc = scoring_from_spec(SPECS[name])
+        o = orc_from_scoring(sc)
+        engine.set_scoring(sc)
+        engine.submit(algo, MODE_ALIGN, sa, sb)
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            _check_alignment(engine.alignment(i), algo, o, a, b)
+
+
+@pytest.mark.parametrize("name", ["nw_default", "sw_cli", "free_ends", "no_gaps_a", "no_gaps_b",
+                                  "no_mismatch_wild", "blosum62", "big_scores"])
+def test_matrices(engine, big, name):
+    """materialise mode: all three int32 matrices, borders and sentinels included"""
+    sa, sb = ragged_batch(900 + _h(name) % 100, 8 if big else 4, 300 if big else 40, 120 if big else 40,
+                          alphabet=_alphabet(name))
+    sa.append(b"ACGT" * (70 if big else 66))   # > 256 columns: two strips
+    sb.append(b"AGGT" * 5)
+    sc = scoring_from_spec(SPECS[name])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    for a, b in zip(sa, sb):
+        for is_sw in (0, 1):
+            m, ga, gb = engine.fill_matrices(a, b, is_sw)
+            rc, em, ega, egb = orc_fill(o, a, b, is_sw)
+            assert rc == 0
+            assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (a, b, is_sw)
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_reference_golden_vectors(engine, chunk):
+    """tests/golden/reference_vectors.json (made by the unmodified reference)
+    straight against the CUDA path: batch API and classic single-pair API"""
+    cases = GOLD["cases"][chunk::4]
+    by_spec = {}
+    for c in cases:
+        by_spec.setdefault(c["spec"], []).append(c)
+    for spec, cs in by_spec.items():
+        sc = scoring_from_spec(GOLD["specs"][spec])
+        engine.set_scoring(sc)
+        engine.force_general(False)
+        sa = [c["a"].encode() for c in cs]
+        sb = [c["b"].encode() for c in cs]
+        engine.submit(NW, MODE_ALIGN, sa, sb)
+        for i, c in enumerate(cs):
+            al = engine.alignment(i)
+            assert (al.score, al.result_a.decode(), al.result_b.decode()) == (
+                c["nw"]["score"], c["nw"]["result_a"], c["nw"]["result_b"]), c
+        engine.submit(SW, MODE_ALIGN, sa, sb)
+        for i, c in enumerate(cs):
+            al = engine.alignment(i)
+            if not c["sw"]:
+                assert al is None
+                continue
+            e = c["sw"][0]
+            assert (al.score, al.result_a.decode(), al.result_b.decode(), al.pos_a, al.pos_b, al.len_a, al.len_b) == (
+                e["score"], e["result_a"], e["result_b"], e["pos_a"], e["pos_b"], e["len_a"], e["len_b"]), c
+        for c in cs:
+            for key, is_sw in (("nw_mats", 0), ("sw_mats", 1)):
+                if key in c:
+                    m, ga, gb = engine.fill_matrices(c["a"], c["b"], is_sw)
+                    assert m.ravel().tolist() == c[key][0]
+                    assert ga.ravel().tolist() == c[key][1]
+                    assert gb.ravel().tolist() == c[key][2]
+
+
+def test_classic_api_single_pair(engine):
+    """needleman_wunsch_align / smith_waterman_align + fetch (all hits) via the
+    reference's own function names; hit order and visited-mask semantics"""
+    # BASELINE config 1 / README.md:71-74
+    al = seqalign.needleman_wunsch("CAGACGT", "CGATA", seqalign.Scoring.nw_default())
+    assert (al.result_a, al.result_b, al.score) == (b"C-AGACGT", b"CGATA---", -11)
+    for c in GOLD["cases"][::5]:
+        sc = scoring_from_spec(GOLD["specs"][c["spec"]])
+        al = seqalign.needleman_wunsch(c["a"], c["b"], sc)
+        assert (al.score, al.result_a.decode(), al.result_b.decode()) == (
+            c["nw"]["score"], c["nw"]["result_a"], c["nw"]["result_b"])
+        hits = seqalign.smith_waterman(c["a"], c["b"], sc, max_hits=6)
+        assert len(hits) == len(c["sw"]), c
+        for h, e in zip(hits, c["sw"]):
+            assert (h.score, h.result_a.decode(), h.result_b.decode(), h.pos_a, h.pos_b, h.len_a, h.len_b) == (
+                e["score"], e["result_a"], e["result_b"], e["pos_a"], e["pos_b"], e["len_a"], e["len_b"]), c
+
+
+def test_classic_api_reused_aligner(engine):
+    """one sw_aligner_t across pairs must behave like a fresh one per pair
+    (the reference's reused mask is stale: SURVEY.md 8c H1)"""
+    L = seqalign.load()
+    import ctypes
+    sc = seqalign.Scoring.sw_cli_default()
+    o = orc_from_scoring(sc)
+    sw = L.smith_waterman_new()
+    res = L.alignment_create(256)
+    sa, sb = ragged_batch(5, 6, 60, 60)
+    for a, b in list(zip(sa, sb)) * 2:
+        L.smith_waterman_align2(a, b, len(a), len(b), sc.ptr, sw)
+        got = []
+        while len(got) < 4 and L.smith_waterman_fetch(sw, res):
+            r = res.contents
+            got.append((r.score, ctypes.string_at(r.result_a, r.length), ctypes.string_at(r.result_b, r.length),
+                        r.pos_a, r.pos_b))
+        n, hits = orc_sw_hits(o, a, b, 4)
+        assert got == [(h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"]) for h in hits]
+    L.alignment_free(res)
+    L.smith_waterman_free(sw)
+
+
+def test_unknown_character_pair(engine):
+    """DNA_hybridization has no match/mismatch fallback: the reference exits on
+    the first unknown pair (alignment_scoring.c:179-181); the batch API reports it"""
+    sc = seqalign.Scoring.system("DNA_hybridization")
+    engine.set_scoring(sc)
+    engine.submit(SW, MODE_SCORE, [b"ACGT", b"ACCA"], [b"ACGT", b"TTGA"])   # fine
+    with pytest.raises(seqalign.SeqAlignError) as e:
+        engine.submit(SW, MODE_SCORE, [b"ACGT", b"ACNA"], [b"ACGT", b"TTGA"])
+    assert e.value.code == seqalign.ERR_UNKNOWN_PAIR
+    assert "Unknown character pair (n,t)" in str(e.value)
+    # 'N' present in the batch but never paired with an unknown partner is fine:
+    # a-side N only meets an empty b
+    engine.submit(SW, MODE_SCORE, [b"ACGT", b"NN"], [b"ACGT", b""])
+    assert engine.scores().tolist()[1] == 0
+
+
+def test_full_size_invariants(engine, big):
+    """BASELINE full size (100k pairs, 150x150): properties that need no oracle,
+    plus specialised-vs-general kernel agreement and an oracle-checked sample"""
+    if not big:
+        pytest.skip("full size runs on the GPU only")
+    n = 100000
+    a, oa, b, ob = synthetic_batch(2, n, 150, 150)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    engine.set_scoring(sc)
+    engine.force_general(False)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s, x, y = engine.ends()
+    assert engine.last_kernel == "fast_sw_score"
+    engine.force_general(True)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s2, x2, y2 = engine.ends()
+    assert np.array_equal(s, s2) and np.array_equal(x, x2) and np.array_equal(y, y2)
+    engine.force_general(False)
+    # symmetry of the score under swapping the sequences (symmetric scoring)
+    engine.submit_packed(SW, MODE_SCORE, b, ob, a, oa)
+    assert np.array_equal(engine.scores(), s)
+    # self alignment: 150 matches
+    engine.submit_packed(SW, MODE_SCORE, a, oa, a, oa)
+    s3, x3, y3 = engine.ends()
+    assert (s3 == 300).all() and (x3 == 150).all() and (y3 == 150).all()
+    assert s.min() >= 0 and s.max() <= 300 and (x >= 0).all() and (x <= 150).all()
+    # oracle on a strided sample
+    idx = np.arange(0, n, 97)
+    o = orc_from_scoring(sc)
+    A, B = a.reshape(n, 150)[idx].reshape(-1), b.reshape(n, 150)[idx].reshape(-1)
+    off = np.arange(len(idx) + 1, dtype=np.int64) * 150
+    es, ex, ey = orc_batch_sw(o, A, off, B, off)
+    assert np.array_equal(s[idx], es) and np.array_equal(x[idx], ex) and np.array_equal(y[idx], ey)
+
+
+def test_device_resident_api(engine, big):
+    """seqalign_batch_run_device: inputs and outputs stay in HBM"""
+    if not big:
+        pytest.skip("needs torch CUDA tensors")
+    import torch
+    a, oa, b, ob = synthetic_batch(9, 3000, 150, 150)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    engine.set_scoring(sc)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s, x, y = engine.ends()
+    dev = torch.device("cuda:0")
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    toa, tob = torch.from_numpy(oa).to(dev), torch.from_numpy(ob).to(dev)
+    ds, dx, dy = (torch.zeros(3000, dtype=torch.int32, device=dev) for _ in range(3))
+    torch.cuda.synchronize()
+    engine.run_device(SW, ta.data_ptr(), toa.data_ptr(), tb.data_ptr(), tob.data_ptr(), 3000,
+                      ds.data_ptr(), dx.data_ptr(), dy.data_ptr())
+    assert np.array_equal(ds.cpu().numpy(), s)
+    assert np.array_equal(dx.cpu().numpy(), x) and np.array_equal(dy.cpu().numpy(), y)
