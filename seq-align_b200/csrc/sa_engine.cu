@@ -171,6 +171,7 @@ int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
   SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, total_a, d_b, total_b, d_off_a, d_off_b,
             (int64_t)n, (unsigned long long *)eng->d_meta.p);
   CU_TRY(cudaGetLastError());
+  eng->last_launches++;
   CU_TRY(cudaMemcpyAsync(eng->h_meta.p, eng->d_meta.p, META_WORDS * 8, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   const uint64_t *m = (const uint64_t *)eng->h_meta.p;
@@ -443,7 +444,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     }
     c0 = c1;
   }
-  eng->last_kernel = algo == SEQALIGN_SW ? "general_score+general_dir+walk" : "general_dir+walk";
+  eng->last_kernel = algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk";
 
   /* scores to host */
   eng->score.resize(n); eng->xend.resize(n); eng->yend.resize(n);
