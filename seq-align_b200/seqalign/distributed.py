@@ -1,0 +1,117 @@
+"""Sharding a batch of pairs over one process per GPU (torch.distributed).
+
+Pairs are independent (the reference itself loops pair by pair,
+src/alignment_cmdline.c:611-622), so the DP needs no exchange step: a job is
+cut into contiguous pair ranges balanced by cell count, every rank aligns its
+range on its own device, and the only communication is moving inputs out from
+and results back to the rank that owns them.  With the NCCL backend the
+tensors are CUDA tensors and travel over NVLink; the engine then runs on the
+received device buffers directly (seqalign_batch_run_device).  The same code
+runs on the gloo backend with CPU tensors (host-buffer submit), which is how
+the logic is tested without GPUs.
+
+Ranks that can load or generate their own shard should do that instead and
+skip scatter_pairs (bench.py does): the input scatter from one rank is
+bounded by that rank's PCIe link, not by NVLink.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import MODE_SCORE
+
+
+def shard_bounds(off_a, off_b, world):
+    """Contiguous pair ranges [b[r], b[r+1]) with near-equal sum(len_a*len_b)."""
+    la = np.diff(np.asarray(off_a, dtype=np.int64))
+    lb = np.diff(np.asarray(off_b, dtype=np.int64))
+    n = len(la)
+    # +1 so that empty pairs still spread out
+    w = np.cumsum(la * lb + 1)
+    total = int(w[-1]) if n else 0
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(w, total * r / world, side="right")) if n else 0)
+    bounds.append(n)
+    for r in range(1, world + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return bounds
+
+
+def _as_tensor(x, device):
+    t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+    return t.to(device)
+
+
+def scatter_pairs(seq_a, off_a, seq_b, off_b, src=0, device="cpu", group=None):
+    """Rank `src` passes the packed batch (numpy arrays or tensors; other ranks
+    pass None) and every rank gets back its shard as tensors on `device`:
+    (seq_a, off_a, seq_b, off_b, first_pair, bounds), offsets rebased to 0."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    meta = torch.zeros(3 * (world + 1), dtype=torch.int64, device=device)
+    if rank == src:
+        off_a = np.asarray(off_a, dtype=np.int64)
+        off_b = np.asarray(off_b, dtype=np.int64)
+        bounds = shard_bounds(off_a, off_b, world)
+        meta[: world + 1] = torch.tensor(bounds)
+        meta[world + 1: 2 * (world + 1)] = torch.tensor(off_a[bounds])
+        meta[2 * (world + 1):] = torch.tensor(off_b[bounds])
+    dist.broadcast(meta, src, group=group)
+    m = meta.cpu().numpy()
+    bounds, ba, bb = m[: world + 1], m[world + 1: 2 * (world + 1)], m[2 * (world + 1):]
+    n_local = int(bounds[rank + 1] - bounds[rank])
+    mine = [torch.empty(int(ba[rank + 1] - ba[rank]), dtype=torch.uint8, device=device),
+            torch.empty(n_local + 1, dtype=torch.int64, device=device),
+            torch.empty(int(bb[rank + 1] - bb[rank]), dtype=torch.uint8, device=device),
+            torch.empty(n_local + 1, dtype=torch.int64, device=device)]
+    if rank == src:
+        ta, tb = _as_tensor(seq_a, device), _as_tensor(seq_b, device)
+        toa, tob = _as_tensor(off_a, device), _as_tensor(off_b, device)
+        reqs = []
+        for r in range(world):
+            parts = [ta[ba[r]: ba[r + 1]], toa[bounds[r]: bounds[r + 1] + 1] - int(ba[r]),
+                     tb[bb[r]: bb[r + 1]], tob[bounds[r]: bounds[r + 1] + 1] - int(bb[r])]
+            if r == src:
+                for dst_t, p in zip(mine, parts):
+                    dst_t.copy_(p)
+            else:
+                reqs += [dist.isend(p.contiguous(), r, group=group) for p in parts]
+        for q in reqs:
+            q.wait()
+    else:
+        for t in mine:
+            dist.recv(t, src, group=group)
+    return mine[0], mine[1], mine[2], mine[3], int(bounds[rank]), [int(v) for v in bounds]
+
+
+def gather_results(local, bounds, dst=0, group=None):
+    """local: int32 tensor [k, n_local] (e.g. score/x_end/y_end rows).  Rank
+    `dst` gets [k, n_total] in the original pair order, others None."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    width = max(counts) if counts else 0
+    k = local.shape[0]
+    padded = torch.zeros((k, width), dtype=local.dtype, device=local.device)
+    padded[:, : local.shape[1]] = local
+    bucket = [torch.zeros_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bucket[r][:, : counts[r]] for r in range(world)], dim=1)
+
+
+def align_sharded(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, src=0, device="cpu", group=None):
+    """Score mode over all ranks: scatter from `src`, align locally, gather
+    (score, x_end, y_end) back to `src` as an int32 tensor [3, n]."""
+    a, oa, b, ob, _, bounds = scatter_pairs(seq_a, off_a, seq_b, off_b, src, device, group)
+    n_local = oa.numel() - 1
+    if a.is_cuda:
+        out = torch.zeros((3, n_local), dtype=torch.int32, device=a.device)
+        if n_local:
+            engine.run_device(algo, a.data_ptr(), oa.data_ptr(), b.data_ptr(), ob.data_ptr(), n_local,
+                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              torch.cuda.current_stream().cuda_stream)
+    else:
+        engine.submit_packed(algo, MODE_SCORE, a.numpy(), oa.numpy(), b.numpy(), ob.numpy())
+        out = torch.from_numpy(np.stack(engine.ends()).astype(np.int32))
+    return gather_results(out, bounds, src, group)
