@@ -37,6 +37,8 @@ typedef struct seqalign_batch seqalign_batch_t;
 /* what a submit computes */
 #define SEQALIGN_MODE_SCORE 0 /* score (+ best SW cell): fill only           */
 #define SEQALIGN_MODE_ALIGN 1 /* + traceback: gapped strings, pos/len fields */
+#define SEQALIGN_MODE_SCORE_ONLY 2 /* scores only (x_end/y_end = 0): lets the
+                                      engine use its packed 16-bit SW kernel   */
 
 /* error codes (negative returns) */
 #define SEQALIGN_OK 0
@@ -135,8 +137,10 @@ double seqalign_batch_last_kernel_ms(const seqalign_batch_t *eng);
 int seqalign_batch_last_launches(const seqalign_batch_t *eng);
 const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng);
 
-/* tuning knob: 0 = automatic.  Forces the general kernel when set to 1
- * (tests use it to cross-check the specialised kernels). */
+/* kernel selection knob for tests: 0 = automatic; 1 = general kernel only;
+ * 2 = specialised kernel with per-column end-cell keys; 3 = specialised
+ * kernel without end-cell tracking (x_end/y_end come back 0; packed 16-bit
+ * kernel when the batch qualifies); 4 = like 3 but int32 arithmetic only. */
 void seqalign_batch_force_general(seqalign_batch_t *eng, int on);
 
 #ifdef __cplusplus

@@ -52,7 +52,7 @@ struct seqalign_batch {
   bool have_scoring = false;
   scoring_t *scoring = nullptr;
   FlatTable ft;
-  bool force_general = false;
+  int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only */
 
   /* inputs on device */
   DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
@@ -153,7 +153,7 @@ ScoreParams make_params(const scoring_t *s, int is_sw, int ncodes)
 
 struct BatchMeta {
   uint64_t pres_a[4], pres_b[4];
-  int64_t max_la, max_lb, cells, max_cells;
+  int64_t max_la, max_lb, cells, max_cells, min_la, min_lb;
 };
 
 /* scan the device-resident batch: alphabet, longest sequences, cell count */
@@ -164,6 +164,7 @@ int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
   TRY(ensure_dev(eng, eng->d_meta, META_WORDS * 8));
   TRY(ensure_pin(eng, eng->h_meta, META_WORDS * 8));
   CU_TRY(cudaMemsetAsync(eng->d_meta.p, 0, META_WORDS * 8, st));
+  CU_TRY(cudaMemsetAsync((unsigned long long *)eng->d_meta.p + META_MIN_LA, 0xff, 16, st));
   int64_t work = (total_a + total_b) / 16 + (int64_t)n;
   int grid = (int)((work + 255) / 256);
   if(grid > eng->num_sms * 8) grid = eng->num_sms * 8;
@@ -180,6 +181,8 @@ int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
   bm->max_lb = (int64_t)m[META_MAX_LB];
   bm->cells = (int64_t)m[META_CELLS];
   bm->max_cells = (int64_t)m[META_MAX_CELLS];
+  bm->min_la = n ? (int64_t)m[META_MIN_LA] : 0;
+  bm->min_lb = n ? (int64_t)m[META_MIN_LB] : 0;
   return 0;
 }
 
@@ -287,16 +290,24 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
 {
   const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
   FastPlan plan;
-  if(!eng->force_general && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, &plan)) {
-    TRY(ensure_dev(eng, eng->d_tab8, (size_t)eng->ft.ncodes * eng->ft.ncodes + 256));
+  const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
+  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb && eng->force_mode != 4;
+  if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &plan)) {
+    if(eng->force_mode == 2 && plan.track == TRACK_TREE) { plan.track = TRACK_COLUMN; plan.name = "fast_sw_score_endcol"; }
+    const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+    TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
     TRY(ensure_dev(eng, eng->d_counter, 8));
-    CU_TRY(cudaMemcpyAsync(eng->d_tab8.p, plan.tab8.data(), plan.tab8.size(), cudaMemcpyHostToDevice, st));
+    int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
+    int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
+    CU_TRY(cudaMemcpyAsync(d_t8, plan.tab8.data(), nn, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_t32, plan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
     FastArgs F;
     F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
     F.npairs = (int64_t)db.n; F.sp = sp;
-    F.tab8 = (const int8_t *)eng->d_tab8.p;
+    F.tab8 = d_t8;
+    F.tab32 = d_t32;
     F.lut = (const uint8_t *)eng->d_lut.p;
     F.counter = (unsigned long long *)eng->d_counter.p;
     F.score = d_score; F.xend = d_xend; F.yend = d_yend;
@@ -476,7 +487,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   eng->last_launches = 0;
   eng->last_ms = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
-  if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN))
+  if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN && mode != SEQALIGN_MODE_SCORE_ONLY))
     return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
   eng->algo = algo; eng->mode = mode;
   eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);
@@ -506,24 +517,34 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   TRY(upload_tables(eng, bm, st));
   if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
 
-  if(mode == SEQALIGN_MODE_SCORE) {
+  if(mode == SEQALIGN_MODE_SCORE || mode == SEQALIGN_MODE_SCORE_ONLY) {
+    const bool ends = mode == SEQALIGN_MODE_SCORE;
     TRY(ensure_dev(eng, eng->d_score, n * 4));
     TRY(ensure_dev(eng, eng->d_xend, n * 4));
     TRY(ensure_dev(eng, eng->d_yend, n * 4));
-    TRY(run_score(eng, algo, db, bm, (int32_t *)eng->d_score.p, (int32_t *)eng->d_xend.p,
-                  (int32_t *)eng->d_yend.p, st));
+    TRY(run_score(eng, algo, db, bm, (int32_t *)eng->d_score.p, ends ? (int32_t *)eng->d_xend.p : nullptr,
+                  ends ? (int32_t *)eng->d_yend.p : nullptr, st));
     TRY(ensure_pin(eng, eng->h_res, n * 12));
     int32_t *hr = (int32_t *)eng->h_res.p;
     CU_TRY(cudaMemcpyAsync(hr, eng->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(hr + n, eng->d_xend.p, n * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(hr + 2 * n, eng->d_yend.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if(ends) {
+      CU_TRY(cudaMemcpyAsync(hr + n, eng->d_xend.p, n * 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(hr + 2 * n, eng->d_yend.p, n * 4, cudaMemcpyDeviceToHost, st));
+    }
     CU_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
     eng->last_ms = ms;
     memcpy(eng->score.data(), hr, n * 4);
-    memcpy(eng->xend.data(), hr + n, n * 4);
-    memcpy(eng->yend.data(), hr + 2 * n, n * 4);
+    if(ends) {
+      memcpy(eng->xend.data(), hr + n, n * 4);
+      memcpy(eng->yend.data(), hr + 2 * n, n * 4);
+    } else if(algo == SEQALIGN_NW) {
+      for(size_t i = 0; i < n; i++) {
+        eng->xend[i] = (int32_t)(h_off_a[i + 1] - h_off_a[i]);
+        eng->yend[i] = (int32_t)(h_off_b[i + 1] - h_off_b[i]);
+      }
+    }
   } else {
     TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
   }
@@ -617,7 +638,7 @@ int seqalign_batch_set_scoring(seqalign_batch_t *eng, const scoring_t *scoring)
   return 0;
 }
 
-void seqalign_batch_force_general(seqalign_batch_t *eng, int on) { if(eng) eng->force_general = on != 0; }
+void seqalign_batch_force_general(seqalign_batch_t *eng, int on) { if(eng) eng->force_mode = on; }
 
 int seqalign_batch_submit_packed(seqalign_batch_t *eng, int algo, int mode,
                                  const char *seq_a, const int64_t *off_a,

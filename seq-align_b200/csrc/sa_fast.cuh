@@ -45,7 +45,9 @@ struct FastArgs {
   const int64_t *off_a, *off_b;
   int64_t npairs;
   ScoreParams sp;
-  const int8_t *tab8;   /* [cb*ncodes + ca] = sub - open */
+  const int8_t *tab8;   /* [cb*ncodes + ca] = sub - open (int8 profile) */
+  const int32_t *tab32; /* same, int32 (small alphabets) */
+  int mul_one, mul_key; /* 1 and 32, as runtime values: see fast_score_kernel */
   const uint8_t *lut;
   unsigned long long *counter;
   int32_t *score, *xend, *yend;
@@ -58,6 +60,10 @@ struct FastPlan {
   bool is_sw = false;
   const char *name = "";
   std::vector<int8_t> tab8;
+  std::vector<int32_t> tab32;
+  int track = 0;
+  bool prof32 = false;
+  bool s16 = false;   /* two pairs per register (fast16_kernel) */
   size_t smem = 0;
   int a_stage = 0, b_stage = 0;
 };
@@ -85,14 +91,32 @@ __device__ __forceinline__ int sext_byte_dyn(unsigned w, int k)
   }
 }
 
-template <int G, int K, bool IS_SW>
+enum { TRACK_NONE = 0, TRACK_TREE = 1, TRACK_COLUMN = 2 };
+
+/* lane stride (in 32-bit words) of an int32 profile row: K, bumped by 4 when
+ * K/4 is even so that 128-bit loads of 8 consecutive lanes hit disjoint banks */
+__host__ __device__ constexpr int prof32_stride(int K) { return (K % 4 == 0 && (K / 4) % 2 == 0) ? K + 4 : K; }
+
+/*
+ * TRACK  how the SW best cell is kept (ignored for NW):
+ *   NONE    score only: running max of M (max3 tree over pairs of columns)
+ *   TREE    one packed key per lane, (M<<16 | 31-j<<11 | 2047-y): the max3
+ *           tree over a row picks the best column, one IMAD+max per row adds
+ *           the row.  Needs len_b <= 2047 and score < 2^15.
+ *   COLUMN  one key per column (M<<16 | 0xFFFF-y), len_b <= 65535.
+ * PROF32 int32 query profile (small alphabets): no PRMT per cell.
+ * mul_one / mul_key are the constants 1 and 32 passed as kernel arguments:
+ * a multiply-add with a runtime multiplier is a real IMAD (FMA pipe), which
+ * takes "H+open" and the key packing off the saturated ALU pipe.
+ */
+template <int G, int K, bool IS_SW, int TRACK, bool PROF32>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast_score_kernel(const FastArgs A)
 {
   constexpr int NG = 32 / G;              /* pairs per warp */
-  constexpr int KW = (K + 3) / 4;         /* profile words per lane */
-  constexpr int KPAD = KW * 4;
-  constexpr int PSTRIDE = 32 * KPAD;      /* bytes per profile row */
+  constexpr int KW = PROF32 ? K : (K + 3) / 4;            /* profile words per lane */
+  constexpr int KS = PROF32 ? prof32_stride(K) : KW;      /* lane stride in words */
+  constexpr int PSTRIDE = 32 * KS * 4;    /* bytes per profile row */
 
   unsigned char *dsm = SA_DYN_SMEM();
   const ScoreParams &sp = A.sp;
@@ -100,11 +124,13 @@ fast_score_kernel(const FastArgs A)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int grp = lane / G, lig = lane % G;
 
-  /* shared layout: [mbarriers][lut 256][tab8 n*n pad16][per-warp: profile | a stages | b stages] */
+  /* shared layout: [mbarriers][lut 256][table n*n (int8 or int32) pad16][per-warp: profile | a stages | b stages] */
   uint64_t *s_bar = (uint64_t *)dsm;                       /* FAST_WARPS*2 */
   uint8_t *s_lut = dsm + 64;
-  int8_t *s_tab = (int8_t *)(dsm + 64 + 256);
-  const int tab_bytes = (n * n + 15) & ~15;
+  int8_t *s_tab8 = (int8_t *)(dsm + 64 + 256);
+  int32_t *s_tab32 = (int32_t *)(dsm + 64 + 256);
+  const int tw = n + 1;   /* table row width: n codes + the padding code */
+  const int tab_bytes = ((PROF32 ? 4 : 1) * n * tw + 15) & ~15;
   const int warp_bytes = n * PSTRIDE + 2 * NG * (A.a_stage + A.b_stage);
   unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
   unsigned char *s_prof = wbase;
@@ -113,12 +139,14 @@ fast_score_kernel(const FastArgs A)
   uint64_t *bar = s_bar + wib * 2;
 
   for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
-  for(int i = threadIdx.x; i < n * n; i += blockDim.x) s_tab[i] = A.tab8[i];
+  if(PROF32) { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab32[i] = A.tab32[i]; }
+  else       { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab8[i] = A.tab8[i]; }
   if(lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   mbar_fence_init();
   __syncthreads();
 
   const int open = sp.open, ext = sp.ext, minv = sp.minv;
+  const int mul_one = A.mul_one, mul_key = A.mul_key;
   const int64_t nsets = (A.npairs + NG - 1) / NG;
 
   /* issue the bulk loads of set t into stage st (one lane per warp) */
@@ -183,27 +211,36 @@ fast_score_kernel(const FastArgs A)
 
     /* query profile of my K columns: row c holds sub'(a[x], c) */
     const int xf = lig * K + 1;
-    int acode[K];
+    {
+      int acode[K];
 #pragma unroll
-    for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : 0;
-    for(int c = 0; c < n; c++) {
-      const int8_t *trow = s_tab + c * n;
-      unsigned *dst = (unsigned *)(s_prof + c * PSTRIDE + lane * KPAD);
+      for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : n;   /* n = padding code */
+      for(int c = 0; c < n; c++) {
+        unsigned *dst = (unsigned *)(s_prof + c * PSTRIDE) + lane * KS;
+        if(PROF32) {
+          const int32_t *trow = s_tab32 + c * tw;
 #pragma unroll
-      for(int w = 0; w < KW; w++) {
-        unsigned word = 0;
+          for(int j = 0; j < K; j++) dst[j] = (unsigned)trow[acode[j]];
+        } else {
+          const int8_t *trow = s_tab8 + c * tw;
 #pragma unroll
-        for(int q = 0; q < 4; q++) {
-          const int j = 4 * w + q;
-          if(j < K) word |= (unsigned)(uint8_t)trow[acode[j]] << (8 * q);
+          for(int w = 0; w < KW; w++) {
+            unsigned word = 0;
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+              const int j = 4 * w + q;
+              if(j < K) word |= (unsigned)(uint8_t)trow[acode[j]] << (8 * q);
+            }
+            dst[w] = word;
+          }
         }
-        dst[w] = word;
       }
     }
     __syncwarp();
 
     /* borders (alignment.c:47-81), in H' = H+open form */
-    int hp[K], ga[K], best[K];
+    int hp[K], ga[K];
+    int colbest[TRACK == TRACK_COLUMN ? K : 1];
 #pragma unroll
     for(int j = 0; j < K; j++) {
       const int x = xf + j;
@@ -213,8 +250,9 @@ fast_score_kernel(const FastArgs A)
         hp[j] = addw(imax(gb0, minv), open);
         ga[j] = minv;
       }
-      best[j] = 0;
+      if constexpr(TRACK == TRACK_COLUMN) colbest[j] = 0;
     }
+    int best = 0;
     int hd; /* H'(xf-1, y-1) */
     if(IS_SW || xf == 1) hd = open;
     else hd = addw(imax(sp.no_start ? 0 : addw(sp.gap_open, (xf - 1) * ext), minv), open);
@@ -224,7 +262,7 @@ fast_score_kernel(const FastArgs A)
 #pragma unroll
     for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
     const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
-    const unsigned char *prow = s_prof + lane * KPAD;
+    const unsigned *prow = (const unsigned *)s_prof + lane * KS;
 
     for(int s = 0; s < nsteps; s++) {
       const int y = s - lig + 1;
@@ -242,18 +280,17 @@ fast_score_kernel(const FastArgs A)
       const int hl_in = hl;
       if(active) {
         const int c = rb[y - 1];
-        const unsigned *pw = (const unsigned *)(prow + c * PSTRIDE);
+        const unsigned *pw = prow + c * (PSTRIDE / 4);
         unsigned w[KW];
-        /* widest load the row layout allows: lane*KPAD is 16/8/4-byte
-         * aligned for KW%4==0 / KW%2==0 / odd KW, and those are exactly
-         * the widths that keep the 32 lanes on distinct banks */
-        if(KW % 4 == 0) {
+        /* widest load the row layout allows; the lane strides are chosen so
+         * that these loads are bank-conflict free across the warp */
+        if(KW % 4 == 0 && KS % 4 == 0) {
 #pragma unroll
           for(int q = 0; q < KW / 4; q++) {
             const uint4 v = ((const uint4 *)pw)[q];
             w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
           }
-        } else if(KW % 2 == 0) {
+        } else if(KW % 2 == 0 && KS % 2 == 0) {
 #pragma unroll
           for(int q = 0; q < KW / 2; q++) {
             const uint2 v = ((const uint2 *)pw)[q];
@@ -265,16 +302,26 @@ fast_score_kernel(const FastArgs A)
         }
         const int ykey = 0xffff - y;
         int d = hd;
+        int rowbest = (TRACK == TRACK_NONE) ? best : 0;
+        int kprev = 0;
 #pragma unroll
         for(int j = 0; j < K; j++) {
-          const int sub = sext_byte_dyn(w[j / 4], j & 3);
+          const int sub = PROF32 ? (int)w[j] : sext_byte_dyn(w[j / 4], j & 3);
           int m, h;
           if(IS_SW) {
             m = addmax(d, sub, 0);
             ga[j] = addmax_relu(ga[j], ext, hp[j]);
             gb = addmax_relu(gb, ext, hl);
             h = max3(m, ga[j], gb);
-            best[j] = imax(best[j], m * 65536 + ykey);
+            if constexpr(TRACK == TRACK_COLUMN) colbest[j] = imax(colbest[j], m * 65536 + ykey);
+            else {
+              /* padding columns need no mask: they score strictly below the
+               * real best (see fast_plan).  TREE packs the column index (IMAD) */
+              const int k = TRACK == TRACK_TREE ? m * mul_key + (31 - j) : m;
+              if(j & 1) rowbest = max3(rowbest, kprev, k);
+              else if(j == K - 1) rowbest = imax(rowbest, k);
+              kprev = k;
+            }
           } else {
             m = addmax(d, sub, minv);
             ga[j] = max3(addw(ga[j], ext), hp[j], minv);
@@ -282,9 +329,11 @@ fast_score_kernel(const FastArgs A)
             h = max3(m, ga[j], gb);
           }
           d = hp[j];
-          hl = addw(h, open);
+          hl = h * mul_one + open;   /* IMAD (FMA pipe) */
           hp[j] = hl;
         }
+        if(IS_SW && TRACK == TRACK_NONE) best = rowbest;
+        if(IS_SW && TRACK == TRACK_TREE) best = imax(best, rowbest * 2048 + (2047 - y));
         out_h = hl;
         out_gb = gb;
         hd = hl_in; /* next row's diagonal */
@@ -294,10 +343,17 @@ fast_score_kernel(const FastArgs A)
     /* results */
     if(IS_SW) {
       int bv = 0, bx = 0, by = 0;
+      if constexpr(TRACK == TRACK_COLUMN) {
 #pragma unroll
-      for(int j = 0; j < K; j++) {
-        const int v = best[j] >> 16;
-        if(xf + j <= la && v > bv) { bv = v; bx = xf + j; by = 0xffff - (best[j] & 0xffff); }
+        for(int j = 0; j < K; j++) {
+          const int v = colbest[j] >> 16;
+          if(xf + j <= la && v > bv) { bv = v; bx = xf + j; by = 0xffff - (colbest[j] & 0xffff); }
+        }
+      } else if(TRACK == TRACK_TREE) {
+        bv = best >> 16;
+        if(bv > 0) { bx = xf + 31 - ((best >> 11) & 31); by = 2047 - (best & 2047); }
+      } else {
+        bv = best;
       }
 #pragma unroll
       for(int o = G / 2; o > 0; o >>= 1) {
@@ -340,83 +396,381 @@ fast_score_kernel(const FastArgs A)
   }
 }
 
+/* ---------------------------------------------------------------------------
+ * fast16_kernel<G,K>: Smith-Waterman score-only, TWO pairs per lane group,
+ * packed in the low / high 16 bits of every register (VIADDMNMX.S16x2,
+ * VIMNMX3.S16x2): each DPX instruction advances two alignments.  Used when
+ * all pairs of the batch have the same shape and every score provably fits
+ * (min(len)*max_sub + |open| < 2^15), so widening back to int32 is exact.
+ *
+ * All stored values carry a bias B = -open (>= 0), which keeps both halves
+ * non-negative: H* = H+B, and the register copy H'* = H*+open.  Because the
+ * low half of H* is always >= B, adding the packed constant
+ * ((open-1)&0xffff)<<16 | (open&0xffff) with a plain 32-bit IMAD always
+ * carries out of the low half, and the "-1" in the high half absorbs it: the
+ * "+open" stays off the ALU pipe like in the int32 kernel.  GA/GB need no
+ * clamp at zero (they can never drop below open, and M >= 0 dominates the
+ * three-way max), M is clamped at B.
+ */
+template <int PAIR>
+__device__ __forceinline__ unsigned pack_sub2(unsigned wlo, unsigned whi)
+{
+#if defined(__CUDA_ARCH__)
+  unsigned r;
+  /* byte PAIR of wlo -> low half, byte PAIR of whi -> high half, both sign-extended */
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(wlo), "r"(whi),
+      "n"(PAIR | ((PAIR | 8) << 4) | ((4 + PAIR) << 8) | (((4 + PAIR) | 8) << 12)));
+  return r;
+#else
+  const int lo = (int8_t)(wlo >> (8 * PAIR)), hi = (int8_t)(whi >> (8 * PAIR));
+  return (unsigned)(unsigned short)lo | ((unsigned)(unsigned short)hi << 16);
+#endif
+}
+
+__device__ __forceinline__ unsigned pack_sub2_dyn(unsigned wlo, unsigned whi, int k)
+{
+  switch(k & 3) {
+    case 0: return pack_sub2<0>(wlo, whi);
+    case 1: return pack_sub2<1>(wlo, whi);
+    case 2: return pack_sub2<2>(wlo, whi);
+    default: return pack_sub2<3>(wlo, whi);
+  }
+}
+
+template <int G, int K>
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+fast16_kernel(const FastArgs A)
+{
+  constexpr int NG = 32 / G;              /* couples per warp */
+  constexpr int NP = 2 * NG;              /* pairs per warp set */
+  constexpr int KW = (K + 3) / 4;
+  constexpr int PSTRIDE = 32 * KW * 4;    /* bytes per profile row */
+
+  unsigned char *dsm = SA_DYN_SMEM();
+  const ScoreParams &sp = A.sp;
+  const int n = sp.ncodes, tw = n + 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int grp = lane / G, lig = lane % G;
+
+  uint64_t *s_bar = (uint64_t *)dsm;
+  uint8_t *s_lut = dsm + 64;
+  int8_t *s_tab8 = (int8_t *)(dsm + 64 + 256);
+  const int tab_bytes = (n * tw + 15) & ~15;
+  const int warp_bytes = 2 * n * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
+  unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
+  unsigned char *s_prof = wbase;                           /* [half][code][PSTRIDE] */
+  unsigned char *s_a = wbase + 2 * n * PSTRIDE;            /* [stage][pair][a_stage] */
+  unsigned char *s_b = s_a + 2 * NP * A.a_stage;
+  uint64_t *bar = s_bar + wib * 2;
+
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+  for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab8[i] = A.tab8[i];
+  if(lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  mbar_fence_init();
+  __syncthreads();
+
+  const int open = sp.open, ext = sp.ext;
+  const unsigned B = (unsigned)(-open);
+  const unsigned BB = B | (B << 16);
+  const unsigned EXT2 = ((unsigned)ext & 0xffffu) | ((unsigned)ext << 16);
+  const unsigned OPENC = (((unsigned)(open - 1) & 0xffffu) << 16) | ((unsigned)open & 0xffffu);
+  const unsigned mul_one = (unsigned)A.mul_one;
+  const int64_t nsets = (A.npairs + NP - 1) / NP;
+
+  auto issue = [&](int64_t t, int st) {
+    if(lane == 0) {
+      uint32_t bytes = 0;
+      for(int g = 0; g < NP; g++) {
+        const int64_t p = t * NP + g;
+        if(p >= A.npairs) break;
+        const int64_t oa = A.off_a[p], ob = A.off_b[p];
+        const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        if(ea > oa) bytes += (uint32_t)(((ea + 15) & ~(int64_t)15) - (oa & ~(int64_t)15));
+        if(eb > ob) bytes += (uint32_t)(((eb + 15) & ~(int64_t)15) - (ob & ~(int64_t)15));
+      }
+      mbar_expect_tx(&bar[st], bytes);
+      for(int g = 0; g < NP; g++) {
+        const int64_t p = t * NP + g;
+        if(p >= A.npairs) break;
+        const int64_t oa = A.off_a[p], ob = A.off_b[p];
+        const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        const int64_t a0 = oa & ~(int64_t)15, b0 = ob & ~(int64_t)15;
+        if(ea > oa)
+          bulk_g2s(s_a + (st * NP + g) * A.a_stage, A.seq_a + a0, (uint32_t)(((ea + 15) & ~(int64_t)15) - a0), &bar[st]);
+        if(eb > ob)
+          bulk_g2s(s_b + (st * NP + g) * A.b_stage, A.seq_b + b0, (uint32_t)(((eb + 15) & ~(int64_t)15) - b0), &bar[st]);
+      }
+    }
+  };
+  auto next_set = [&]() -> int64_t {
+    unsigned long long t = 0;
+    if(lane == 0) t = atomicAdd(A.counter, 1ull);
+    return (int64_t)__shfl_sync(FULL, t, 0);
+  };
+
+  int stage = 0;
+  unsigned phase0 = 0, phase1 = 0;
+  int64_t t = next_set();
+  if(t < nsets) issue(t, 0);
+
+  while(t < nsets) {
+    const int64_t tn = next_set();
+    if(tn < nsets) issue(tn, stage ^ 1);
+
+    /* this group's couple: pair plo in the low halves, phi in the high halves */
+    const int64_t plo = t * NP + 2 * grp, phi = plo + 1;
+    const bool have_lo = plo < A.npairs, have_hi = phi < A.npairs;
+    int la = 0, lb = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
+    if(have_lo) {
+      const int64_t oa = A.off_a[plo], ob = A.off_b[plo];
+      la = (int)(A.off_a[plo + 1] - oa); lb = (int)(A.off_b[plo + 1] - ob);   /* uniform batch: same for phi */
+      sha_lo = (int)(oa & 15); shb_lo = (int)(ob & 15);
+    }
+    if(have_hi) { sha_hi = (int)(A.off_a[phi] & 15); shb_hi = (int)(A.off_b[phi] & 15); }
+    mbar_wait(&bar[stage], stage ? phase1 : phase0);
+    if(stage) phase1 ^= 1; else phase0 ^= 1;
+
+    const int slot_lo = stage * NP + 2 * grp, slot_hi = have_hi ? slot_lo + 1 : slot_lo;
+    unsigned char *ra_lo = s_a + slot_lo * A.a_stage + sha_lo;
+    unsigned char *rb_lo = s_b + slot_lo * A.b_stage + shb_lo;
+    unsigned char *ra_hi = s_a + slot_hi * A.a_stage + (have_hi ? sha_hi : sha_lo);
+    unsigned char *rb_hi = s_b + slot_hi * A.b_stage + (have_hi ? shb_hi : shb_lo);
+
+    /* seq_b of both pairs: raw bytes -> codes, in place (a missing high pair aliases the low one) */
+    for(int i = lig; i < lb; i += G) {
+      const unsigned char c = s_lut[rb_lo[i]];
+      const unsigned char d = have_hi ? s_lut[rb_hi[i]] : c;
+      rb_lo[i] = c;
+      if(have_hi) rb_hi[i] = d;
+    }
+    __syncwarp();
+    const unsigned char *cb_hi = have_hi ? rb_hi : rb_lo;
+
+    /* query profiles of my K columns, one per half */
+    const int xf = lig * K + 1;
+#pragma unroll
+    for(int half = 0; half < 2; half++) {
+      const unsigned char *ra = half ? ra_hi : ra_lo;   /* seq_a stays raw in shared memory */
+      int acode[K];
+#pragma unroll
+      for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : n;
+      for(int c = 0; c < n; c++) {
+        const int8_t *trow = s_tab8 + c * tw;
+        unsigned *dst = (unsigned *)(s_prof + (half * n + c) * PSTRIDE) + lane * KW;
+#pragma unroll
+        for(int w = 0; w < KW; w++) {
+          unsigned word = 0;
+#pragma unroll
+          for(int q = 0; q < 4; q++) {
+            const int j = 4 * w + q;
+            if(j < K) word |= (unsigned)(uint8_t)trow[acode[j]] << (8 * q);
+          }
+          dst[w] = word;
+        }
+      }
+    }
+    __syncwarp();
+
+    /* borders, biased: H = 0 -> H'* = B + open = 0 ; GA = GB = 0 -> B */
+    unsigned hp[K], ga[K];
+#pragma unroll
+    for(int j = 0; j < K; j++) { hp[j] = 0; ga[j] = BB; }
+    unsigned best = BB, hd = 0, out_h = 0, out_gb = BB;
+
+    int maxlb = lb;
+#pragma unroll
+    for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
+    const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
+    const unsigned *prow_lo = (const unsigned *)s_prof + lane * KW;
+    const unsigned *prow_hi = prow_lo + n * (PSTRIDE / 4);
+
+    for(int s = 0; s < nsteps; s++) {
+      const int y = s - lig + 1;
+      const bool active = y >= 1 && y <= lb;
+      unsigned hl = __shfl_up_sync(FULL, out_h, 1);
+      unsigned gb = __shfl_up_sync(FULL, out_gb, 1);
+      if(lig == 0) { hl = 0; gb = BB; }     /* column 0 */
+      const unsigned hl_in = hl;
+      if(active) {
+        const unsigned *pl = prow_lo + rb_lo[y - 1] * (PSTRIDE / 4);
+        const unsigned *ph = prow_hi + cb_hi[y - 1] * (PSTRIDE / 4);
+        unsigned wl[KW], wh[KW];
+#pragma unroll
+        for(int q = 0; q < KW; q++) { wl[q] = pl[q]; wh[q] = ph[q]; }
+        unsigned d = hd, kprev = BB;
+#pragma unroll
+        for(int j = 0; j < K; j++) {
+          const unsigned sub = pack_sub2_dyn(wl[j / 4], wh[j / 4], j & 3);
+          const unsigned m = addmax_s16x2(d, sub, BB);
+          ga[j] = addmax_s16x2(ga[j], EXT2, hp[j]);
+          gb = addmax_s16x2(gb, EXT2, hl);
+          const unsigned h = max3_s16x2(m, ga[j], gb);
+          if(j & 1) best = max3_s16x2(best, kprev, m);
+          else if(j == K - 1) best = max3_s16x2(best, m, m);
+          kprev = m;
+          d = hp[j];
+          hl = h * mul_one + OPENC;   /* packed H* + open, see header */
+          hp[j] = hl;
+        }
+        out_h = hl;
+        out_gb = gb;
+        hd = hl_in;
+      }
+    }
+
+#pragma unroll
+    for(int o = G / 2; o > 0; o >>= 1) {
+      const unsigned v = __shfl_xor_sync(FULL, best, o);
+      best = max3_s16x2(best, v, v);
+    }
+    if(lig == 0) {
+      if(have_lo) {
+        A.score[plo] = (int)(best & 0xffffu) - (int)B;
+        if(A.xend) A.xend[plo] = 0;
+        if(A.yend) A.yend[plo] = 0;
+      }
+      if(have_hi) {
+        A.score[phi] = (int)(best >> 16) - (int)B;
+        if(A.xend) A.xend[phi] = 0;
+        if(A.yend) A.yend[phi] = 0;
+      }
+    }
+
+    fence_async_smem();
+    __syncwarp();
+    stage ^= 1;
+    t = tn;
+  }
+}
+
 /* ---- host side ---------------------------------------------------------- */
 
 struct FastShape { int G, K; };
 static const FastShape kFastShapes[] = {
     {8, 8}, {8, 12}, {8, 16}, {8, 20}, {16, 12}, {16, 16}, {32, 10}, {32, 12}, {32, 16}};
 
-inline size_t fast_smem_bytes(int G, int K, int ncodes, int a_stage, int b_stage)
+inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage, int b_stage)
 {
-  const int NG = 32 / G, KPAD = (K + 3) / 4 * 4;
-  const size_t warp_bytes = (size_t)ncodes * 32 * KPAD + 2 * (size_t)NG * (a_stage + b_stage);
-  return 64 + 256 + (((size_t)ncodes * ncodes + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
+  const int NG = 32 / G;
+  const int KS = prof32 ? prof32_stride(K) : (K + 3) / 4;
+  const size_t warp_bytes = (size_t)ncodes * 32 * KS * 4 + 2 * (size_t)NG * (a_stage + b_stage);
+  const size_t tab = (((size_t)(prof32 ? 4 : 1) * ncodes * (ncodes + 1)) + 15) & ~(size_t)15;
+  return 64 + 256 + tab + FAST_WARPS * warp_bytes;
 }
 
-/* can the fast kernel take this batch?  fills the plan if so */
+/* can the fast kernel take this batch?  fills the plan if so.
+ * want_ends: the caller needs the SW end cell (x_end, y_end) */
 inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
-                      int64_t max_la, int64_t max_lb, FastPlan *plan)
+                      int64_t max_la, int64_t max_lb, bool want_ends, bool uniform, FastPlan *plan)
 {
   if(sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
-  if(s->gap_open > 0) return false;                 /* needs open <= ext */
+  if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
   if(ft.any_unknown) return false;
   if(max_la < 1 || max_lb < 1 || max_la > 512 || max_lb > 65535) return false;
-  /* sub' = sub - open must fit int8 */
-  const long lo = (long)ft.min_sub - sp.open, hi = (long)ft.max_sub - sp.open;
-  if(lo < -127 || hi > 127) return false;
   for(size_t k = 0; k < ft.unknown.size(); k++) if(ft.unknown[k]) return false;
+  const long lo = (long)ft.min_sub - sp.open, hi = (long)ft.max_sub - sp.open;
+  if(lo < -(1L << 24) || hi > (1L << 24)) return false;
+  const long longest = (long)(max_la > max_lb ? max_la : max_lb), shortest = (long)(max_la < max_lb ? max_la : max_lb);
   if(sp.is_sw) {
-    /* packed (score,row) key: scores must stay below 2^15 */
-    const long cap = (long)(max_la < max_lb ? max_la : max_lb) * (ft.max_sub > 0 ? ft.max_sub : 0);
+    /* packed (score,position) keys: scores must stay below 2^15 */
+    const long cap = shortest * (ft.max_sub > 0 ? ft.max_sub : 0);
     if(cap >= 32768) return false;
   } else {
     /* sentinel arithmetic must not wrap (alignment.c:41) */
     const long room = labs((long)s->min_penalty);
     if(-(long)sp.open > room || -(long)sp.ext > room || -(long)ft.min_sub > room) return false;
     if(sp.ext > 0 || sp.open > 0) return false;
-    const long worst = (long)sp.gap_open + (long)(max_la > max_lb ? max_la : max_lb) * sp.ext;
+    const long worst = (long)sp.gap_open + longest * sp.ext;
     if(worst < -(1L << 30)) return false;
   }
   int G = 0, K = 0;
   for(const FastShape &sh : kFastShapes)
     if((int64_t)sh.G * sh.K >= max_la) { G = sh.G; K = sh.K; break; }
   if(!G) return false;
-  plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0;
+  const int n = ft.ncodes;
+  /* int32 profile when it stays small (DNA-sized alphabets); else int8, which
+   * needs sub' = sub - open to fit a signed byte */
+  bool prof32 = (size_t)n * 32 * prof32_stride(K) * 4 <= 16 * 1024;
+  const int padsub = ft.min_sub < -1 ? ft.min_sub : -1;
+  const bool fits8 = lo >= -127 && hi <= 127 && (long)padsub - sp.open >= -127 && (long)padsub - sp.open <= 127;
+  if(!prof32 && !fits8) return false;
+  /* packed 16-bit kernel: SW score only, one shape for the whole batch, and
+   * every biased value (score + |open|) inside int16 */
+  const bool s16 = sp.is_sw && !want_ends && uniform && fits8 &&
+                   shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open < 32000 && sp.open > -16000 &&
+                   ft.min_sub > -16000;
+  if(s16) prof32 = false;
+  plan->s16 = s16;
+  plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
+  plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
   plan->a_stage = (int)((G * K + 15 + 15) & ~15) + 16;
   plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16;
-  plan->smem = fast_smem_bytes(G, K, ft.ncodes, plan->a_stage, plan->b_stage);
+  plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage);
+  if(s16) {
+    const size_t warp_bytes = 2 * (size_t)n * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
+    plan->smem = 64 + 256 + (((size_t)n * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
+  }
   if(plan->smem > 200 * 1024) return false;
-  const int n = ft.ncodes;
-  plan->tab8.assign(((size_t)n * n + 15) & ~(size_t)15, 0);
-  for(int i = 0; i < n * n; i++) plan->tab8[i] = (int8_t)(ft.sub[i] - sp.open);
-  plan->name = sp.is_sw ? "fast_sw_score" : "fast_nw_score";
+  /* tables are n rows (code of seq_b) x n+1 columns (code of seq_a, last =
+   * padding).  A padding column scores strictly negative against everything,
+   * so (with open, ext <= 0) no cell in it can reach the best real score and
+   * the kernels need not mask it out of the running maximum. */
+  const int tw = n + 1;
+  plan->tab8.assign(((size_t)n * tw + 15) & ~(size_t)15, 0);
+  plan->tab32.assign((size_t)n * tw + 4, 0);
+  for(int cb = 0; cb < n; cb++)
+    for(int ca = 0; ca < tw; ca++) {
+      const int v = (ca < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
+      plan->tab32[(size_t)cb * tw + ca] = v;
+      if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
+    }
+  plan->name = !sp.is_sw ? "fast_nw_score" : s16 ? "fast16_sw_score"
+             : plan->track == TRACK_NONE ? "fast_sw_score" : plan->track == TRACK_TREE ? "fast_sw_score_end" : "fast_sw_score_endcol";
   return true;
 }
 
-template <int G, int K>
-int fast_launch_gk(const FastPlan &plan, const FastArgs &F, int grid, cudaStream_t st)
+/* persistent grid: exactly as many CTAs as are resident at once */
+template <class KF>
+int fast_grid(KF kfn, size_t smem, int num_sms, int64_t need)
 {
-  void (*kfn)(const FastArgs) = plan.is_sw ? fast_score_kernel<G, K, true> : fast_score_kernel<G, K, false>;
+  int per_sm = 1;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, FAST_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)num_sms * per_sm;
+  if(grid > need) grid = need;
+  return grid < 1 ? 1 : (int)grid;
+}
+
+template <int G, int K, bool P32>
+int fast_launch_gkp(const FastPlan &plan, const FastArgs &F, int num_sms, int64_t need, cudaStream_t st)
+{
+  void (*kfn)(const FastArgs);
+  if(!plan.is_sw) kfn = fast_score_kernel<G, K, false, TRACK_NONE, P32>;
+  else if(plan.track == TRACK_NONE) kfn = fast_score_kernel<G, K, true, TRACK_NONE, P32>;
+  else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32>;
+  else kfn = fast_score_kernel<G, K, true, TRACK_COLUMN, P32>;
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
-  SA_LAUNCH(kfn, grid, FAST_WARPS * 32, plan.smem, st, F);
+  SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F);
   return 0;
 }
 
 inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t smem_optin, cudaStream_t st)
 {
   F.a_stage = plan.a_stage; F.b_stage = plan.b_stage;
+  F.mul_one = 1; F.mul_key = 32;
   if(plan.smem > smem_optin) return -1;
-  /* persistent grid: as many CTAs per SM as shared memory allows (<= 4) */
-  int per_sm = (int)((smem_optin + 1024) / (plan.smem + 1024));
-  if(per_sm > 4) per_sm = 4;
-  if(per_sm < 1) per_sm = 1;
-  const int NG = 32 / plan.G;
-  int64_t nsets = (F.npairs + NG - 1) / NG;
-  int64_t grid = (int64_t)num_sms * per_sm;
+  const int NG = (plan.s16 ? 2 : 1) * (32 / plan.G);
+  const int64_t nsets = (F.npairs + NG - 1) / NG;
   const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
-  if(grid > need) grid = need;
-  if(grid < 1) grid = 1;
-#define SA_FAST_CASE(g, k) if(plan.G == g && plan.K == k) return fast_launch_gk<g, k>(plan, F, (int)grid, st)
+#define SA_FAST_CASE(g, k)                                                                    \
+  if(plan.G == g && plan.K == k && plan.s16) {                                                \
+    void (*kfn)(const FastArgs) = fast16_kernel<g, k>;                                        \
+    if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1; \
+    SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F); \
+    return 0;                                                                                 \
+  }                                                                                           \
+  if(plan.G == g && plan.K == k)                                                              \
+    return plan.prof32 ? fast_launch_gkp<g, k, true>(plan, F, num_sms, need, st)               \
+                       : fast_launch_gkp<g, k, false>(plan, F, num_sms, need, st)
   SA_FAST_CASE(8, 8); SA_FAST_CASE(8, 12); SA_FAST_CASE(8, 16); SA_FAST_CASE(8, 20);
   SA_FAST_CASE(16, 12); SA_FAST_CASE(16, 16);
   SA_FAST_CASE(32, 10); SA_FAST_CASE(32, 12); SA_FAST_CASE(32, 16);

@@ -46,7 +46,7 @@ struct ScoreParams {
 
 /* meta block written by scan_kernel, read back by the host (16 x u64) */
 enum { META_PRES_A = 0, META_PRES_B = 4, META_MAX_LA = 8, META_MAX_LB = 9,
-       META_CELLS = 10, META_MAX_CELLS = 11, META_WORDS = 16 };
+       META_CELLS = 10, META_MAX_CELLS = 11, META_MIN_LA = 12, META_MIN_LB = 13, META_WORDS = 16 };
 
 /* ---------------------------------------------------------------------------
  * scan_kernel: which byte values occur in seq_a / seq_b (256-bit sets), the
@@ -61,9 +61,10 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
             int64_t npairs, unsigned long long *__restrict__ meta)
 {
   __shared__ unsigned s_seen[2][256];
-  __shared__ unsigned long long s_red[4];
+  __shared__ unsigned long long s_red[6];
   for(int i = threadIdx.x; i < 512; i += blockDim.x) (&s_seen[0][0])[i] = 0;
   if(threadIdx.x < 4) s_red[threadIdx.x] = 0;
+  if(threadIdx.x >= 4 && threadIdx.x < 6) s_red[threadIdx.x] = ~0ull;
   __syncthreads();
 
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,12 +89,14 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
     for(int64_t i = nvec * 16 + tid; i < total; i += nthreads) s_seen[which][seq[i]] = 1;
   }
 
-  unsigned long long max_la = 0, max_lb = 0, cells = 0, max_cells = 0;
+  unsigned long long max_la = 0, max_lb = 0, cells = 0, max_cells = 0, min_la = ~0ull, min_lb = ~0ull;
   for(int64_t p = tid; p < npairs; p += nthreads) {
     unsigned long long la = (unsigned long long)(off_a[p + 1] - off_a[p]);
     unsigned long long lb = (unsigned long long)(off_b[p + 1] - off_b[p]);
     max_la = la > max_la ? la : max_la;
     max_lb = lb > max_lb ? lb : max_lb;
+    min_la = la < min_la ? la : min_la;
+    min_lb = lb < min_lb ? lb : min_lb;
     cells += la * lb;
     max_cells = la * lb > max_cells ? la * lb : max_cells;
   }
@@ -101,6 +104,8 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
   atomicMax(&s_red[1], max_lb);
   atomicAdd(&s_red[2], cells);
   atomicMax(&s_red[3], max_cells);
+  atomicMin(&s_red[4], min_la);
+  atomicMin(&s_red[5], min_lb);
   __syncthreads();
 
   if(threadIdx.x < 8) {
@@ -116,6 +121,8 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
     atomicMax(&meta[META_MAX_LB], s_red[1]);
     atomicAdd(&meta[META_CELLS], s_red[2]);
     atomicMax(&meta[META_MAX_CELLS], s_red[3]);
+    atomicMin(&meta[META_MIN_LA], s_red[4]);
+    atomicMin(&meta[META_MIN_LB], s_red[5]);
   }
 }
 

@@ -59,6 +59,35 @@ __host__ __device__ __forceinline__ int addmax_relu(int a, int b, int c)
 
 __host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 
+/* packed 2 x int16 DPX (VIADDMNMX.S16x2 / VIMNMX3.S16x2): two alignments per
+ * instruction when the scores fit 16 bits */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned addmax_s16x2(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2(a, b, c); }
+__device__ __forceinline__ unsigned max3_s16x2(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+#else
+__host__ __device__ inline unsigned addmax_s16x2(unsigned a, unsigned b, unsigned c)
+{
+  unsigned r = 0;
+  for(int h = 0; h < 2; h++) {
+    const int x = (short)(a >> (16 * h)), y = (short)(b >> (16 * h)), z = (short)(c >> (16 * h));
+    const int s = (short)(x + y);
+    r |= (unsigned)(unsigned short)(s > z ? s : z) << (16 * h);
+  }
+  return r;
+}
+__host__ __device__ inline unsigned max3_s16x2(unsigned a, unsigned b, unsigned c)
+{
+  unsigned r = 0;
+  for(int h = 0; h < 2; h++) {
+    int x = (short)(a >> (16 * h)), y = (short)(b >> (16 * h)), z = (short)(c >> (16 * h));
+    int m = x > y ? x : y;
+    m = m > z ? m : z;
+    r |= (unsigned)(unsigned short)m << (16 * h);
+  }
+  return r;
+}
+#endif
+
 /* ---- async bulk copy (TMA, 1-D) + mbarrier ------------------------------
  * cp.async.bulk moves a 16-byte-aligned span global -> shared without
  * touching registers and signals an mbarrier with the byte count

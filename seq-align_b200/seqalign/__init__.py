@@ -23,6 +23,7 @@ NW = 0
 SW = 1
 MODE_SCORE = 0
 MODE_ALIGN = 1
+MODE_SCORE_ONLY = 2
 
 ERR_CUDA = -1
 ERR_UNKNOWN_PAIR = -2
@@ -299,7 +300,8 @@ class BatchAligner:
         self._check(self._L.seqalign_batch_set_scoring(self._h, scoring.ptr))
 
     def force_general(self, on=True):
-        self._L.seqalign_batch_force_general(self._h, 1 if on else 0)
+        """0/False automatic, 1/True general kernel, 2 per-column end keys, 3 no end cell"""
+        self._L.seqalign_batch_force_general(self._h, int(on))
 
     def submit_packed(self, algo, mode, seq_a, off_a, seq_b, off_b):
         """Host arrays (numpy uint8 / int64, or anything exposing ctypes.data)."""

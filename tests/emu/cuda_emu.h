@@ -254,5 +254,7 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEve
 }
 template <class K>
 static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class K>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
 
 #endif

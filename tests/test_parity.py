@@ -54,7 +54,19 @@ def _score_check(engine, sc, algo, a, oa, b, ob, general):
         assert np.array_equal(s, es), np.nonzero(s != es)[0][:8]
         assert np.array_equal(x, np.diff(oa)) and np.array_equal(y, np.diff(ob))
     assert engine.last_launches >= 1
-    return engine.last_kernel
+    kernel = engine.last_kernel
+    if algo == SW and not general:
+        # the other two end-cell strategies of the specialised kernel
+        engine.force_general(2)
+        engine.submit_packed(algo, MODE_SCORE, a, oa, b, ob)
+        s2, x2, y2 = engine.ends()
+        assert np.array_equal(s2, es) and np.array_equal(x2, ex) and np.array_equal(y2, ey)
+        for mode in (3, 4):   # score only: packed 16-bit kernel if the batch qualifies / int32 only
+            engine.force_general(mode)
+            engine.submit_packed(algo, MODE_SCORE, a, oa, b, ob)
+            assert np.array_equal(engine.scores(), es), (mode, engine.last_kernel)
+        engine.force_general(0)
+    return kernel
 
 
 @pytest.mark.parametrize("algo", [SW, NW], ids=["sw", "nw"])
@@ -77,7 +89,11 @@ def test_headline_config_sample(engine, big):
     a, oa, b, ob = synthetic_batch(2, n, 150, 150)
     sc = scoring_from_spec(SPECS["sw_cli"])
     k = _score_check(engine, sc, SW, a, oa, b, ob, general=False)
-    assert k == "fast_sw_score"
+    assert k == "fast_sw_score_end"
+    engine.force_general(3)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast16_sw_score"
+    engine.force_general(0)
     # unrelated pairs too (throughput must not depend on the data; scores do)
     a, oa, b, ob = synthetic_batch(12, n // 2, 150, 150, related=False)
     _score_check(engine, sc, SW, a, oa, b, ob, general=False)
@@ -295,7 +311,7 @@ def test_full_size_invariants(engine, big):
     engine.force_general(False)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
     s, x, y = engine.ends()
-    assert engine.last_kernel == "fast_sw_score"
+    assert engine.last_kernel == "fast_sw_score_end"
     engine.force_general(True)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
     s2, x2, y2 = engine.ends()

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Kernel-time survey on the GPU box: headline shapes x kernel variants."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from helpers import *
+
+specs = scoring_specs()
+eng = seqalign.BatchAligner(0)
+rows = []
+
+def timeit(tag, name, algo, force, a, oa, b, ob, cells, reps=4, check=None):
+    sc = specs[name](); eng.set_scoring(sc); eng.force_general(force)
+    best = 1e9; e2e = 1e9
+    for r in range(reps):
+        t = time.time()
+        eng.submit_packed(algo, seqalign.MODE_SCORE, a, oa, b, ob)
+        e2e = min(e2e, time.time() - t)
+        best = min(best, eng.last_kernel_ms)
+    s = eng.scores()
+    ok = None if check is None else bool(np.array_equal(s, check))
+    res = dict(tag=tag, scoring=name, algo="SW" if algo else "NW", kernel=eng.last_kernel, kernel_ms=round(best, 4),
+               gcups_kernel=round(cells / best / 1e6, 1), e2e_ms=round(e2e * 1e3, 3), gcups_e2e=round(cells / e2e / 1e9, 1), same_scores=ok)
+    print(json.dumps(res), flush=True)
+    rows.append(res)
+    eng.force_general(0)
+    return s
+
+A, OA, B, OB = synthetic_batch(2, 100000, 150, 150)
+c = 100000 * 22500.0
+ref = timeit("dna150 auto(end,tree)", "sw_cli", seqalign.SW, 0, A, OA, B, OB, c)
+timeit("dna150 end,column", "sw_cli", seqalign.SW, 2, A, OA, B, OB, c, check=ref)
+timeit("dna150 score-only s16x2", "sw_cli", seqalign.SW, 3, A, OA, B, OB, c, check=ref)
+timeit("dna150 score-only int32", "sw_cli", seqalign.SW, 4, A, OA, B, OB, c, check=ref)
+timeit("dna150 general", "sw_cli", seqalign.SW, 1, A, OA, B, OB, c, reps=2, check=ref)
+timeit("dna150 nw", "nw_default", seqalign.NW, 0, A, OA, B, OB, c)
+timeit("dna150 libdefault sw", "nw_default", seqalign.SW, 0, A, OA, B, OB, c)
+PA, POA, PB, POB = synthetic_batch(4, 50000, 400, 400, kind="protein")
+c4 = 50000 * 160000.0
+ref = timeit("prot400 auto", "blosum62", seqalign.SW, 0, PA, POA, PB, POB, c4)
+timeit("prot400 score-only s16x2", "blosum62", seqalign.SW, 3, PA, POA, PB, POB, c4, check=ref)
+timeit("prot400 score-only int32", "blosum62", seqalign.SW, 4, PA, POA, PB, POB, c4, check=ref)
+for L in (64, 100, 128, 250, 300, 512):
+    n = int(2.0e9 / (L * L))
+    a, oa, b, ob = synthetic_batch(20 + L, n, L, L)
+    timeit("dna%d score-only" % L, "sw_cli", seqalign.SW, 3, a, oa, b, ob, n * L * L)
+# align mode
+sc = specs["sw_cli"](); eng.set_scoring(sc)
+n = 20000
+t = time.time(); eng.submit_packed(seqalign.SW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); dt = time.time() - t
+print(json.dumps(dict(tag="dna150 SW align 20k", e2e_ms=dt * 1e3, kernel_ms=eng.last_kernel_ms, gcups_kernel=n * 22500 / eng.last_kernel_ms / 1e6, kernel=eng.last_kernel)))
+sc = specs["nw_default"](); eng.set_scoring(sc)
+t = time.time(); eng.submit_packed(seqalign.NW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); dt = time.time() - t
+print(json.dumps(dict(tag="dna150 NW align 20k", e2e_ms=dt * 1e3, kernel_ms=eng.last_kernel_ms, gcups_kernel=n * 22500 / eng.last_kernel_ms / 1e6, kernel=eng.last_kernel)))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gpu_perf.json"), "w"), indent=1)
