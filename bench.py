@@ -173,18 +173,22 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def issue_peak_cells_per_clk_sm():
-    """measured issue-rate ceiling of the SW cell's instruction mix (tools/microbench.cu)"""
+def issue_peak_gcups(kernel_name):
+    """Measured issue-rate ceiling (Gcells/s, event-timed) of the instruction mix of the
+    kernel that ran, from tools/microbench.cu run on this GPU just now."""
+    want = "s16x2 mix" if kernel_name.startswith("fast16") else (
+        "int32 end-cell mix" if kernel_name.endswith("_end") else "int32 score-only mix")
     exe = os.path.join(ROOT, "bin", "microbench")
     try:
         out = subprocess.check_output([exe], text=True, timeout=60)
         for ln in out.splitlines():
             d = json.loads(ln)
-            if d.get("op", "").startswith("SW cell (9 ops"):
-                return d["lane_ops_per_clk_per_sm"] / 9.0, "live tools/microbench.cu"
+            if want in d.get("op", ""):
+                return d["cells_gcups"], "live tools/microbench.cu: " + d["op"]
     except Exception:
         pass
-    return 146.7 / 9.0, "recorded (profiles/microbench_r01.jsonl)"
+    recorded = {"s16x2 mix": 6900.0, "int32 end-cell mix": 3700.0, "int32 score-only mix": 3900.0}
+    return recorded[want], "recorded (profiles/microbench_r01b.jsonl): " + want
 
 
 def main():
@@ -305,9 +309,8 @@ def main():
         # algorithmic traffic, score mode: both sequences read once, score + end cell written
         alg_bytes = PAIRS * (LEN + LEN + 4)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        cpc, cpc_src = issue_peak_cells_per_clk_sm()
+        issue_peak, issue_src = issue_peak_gcups(kernel_name)
         f_mhz = clocks["sm_mhz"] or 1965.0
-        issue_peak = cpc * 148 * f_mhz * 1e6 / 1e9
         line = {
             "metric": "DP cell updates/s (GCUPS)", "value": value, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_ms / args.steps,
@@ -329,7 +332,7 @@ def main():
                                  "binding one is INT32/DPX issue, reported under 'issue'",
                          "issue": {"achieved_gcups": cells_step / (k_ms * 1e-3) / 1e9, "peak_gcups": issue_peak,
                                    "frac": cells_step / (k_ms * 1e-3) / 1e9 / issue_peak,
-                                   "cells_per_clk_per_sm_peak": cpc, "sm_mhz": f_mhz, "source": cpc_src}},
+                                   "sm_mhz": f_mhz, "source": issue_src}},
         }
         if world == 1 and not args.no_cpu_baseline:
             a, oa, b, ob = [t.numpy() for t in host[0]]

@@ -45,13 +45,23 @@ struct seqalign_batch {
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  enum { MAX_CHUNKS = 8 };
+  cudaEvent_t ev_copy[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {};
   std::string err;
   char unk_a = 0, unk_b = 0;
 
   bool have_scoring = false;
   scoring_t *scoring = nullptr;
   FlatTable ft;
+  unsigned scoring_version = 0;
+  /* what the device tables currently hold */
+  bool tables_valid = false;
+  unsigned tables_version = 0;
+  uint64_t tables_pres[8] = {};
+  std::vector<int32_t> dev_tab32;
+  std::vector<int8_t> dev_tab8;
   int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only */
 
   /* inputs on device */
@@ -186,21 +196,30 @@ int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
   return 0;
 }
 
-/* flatten scoring for this batch's alphabet and upload the tables */
+/* flatten scoring for this batch's alphabet and upload the tables; skipped
+ * when the device already holds the tables of this (scoring, alphabet) */
 int upload_tables(seqalign_batch *eng, const BatchMeta &bm, cudaStream_t st)
 {
+  uint64_t pres[8];
+  for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
+  if(eng->tables_valid && eng->tables_version == eng->scoring_version &&
+     memcmp(pres, eng->tables_pres, sizeof(pres)) == 0)
+    return 0;
   flatten_scoring(eng->scoring, bm.pres_a, bm.pres_b, &eng->ft);
   const FlatTable &ft = eng->ft;
   const size_t nn = (size_t)ft.ncodes * ft.ncodes;
   TRY(ensure_dev(eng, eng->d_sub, nn * 4));
   TRY(ensure_dev(eng, eng->d_forbid, nn));
   TRY(ensure_dev(eng, eng->d_lut, 256));
+  /* pageable sources: cudaMemcpyAsync returns once they are staged */
   CU_TRY(cudaMemcpyAsync(eng->d_sub.p, ft.sub.data(), nn * 4, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(eng->d_forbid.p, ft.forbid.data(), nn, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(eng->d_lut.p, ft.lut, 256, cudaMemcpyHostToDevice, st));
-  /* pageable sources: the copies above are staged before they return, but
-   * the vectors are rebuilt per batch, so make that explicit */
-  CU_TRY(cudaStreamSynchronize(st));
+  eng->tables_valid = true;
+  eng->tables_version = eng->scoring_version;
+  memcpy(eng->tables_pres, pres, sizeof(pres));
+  eng->dev_tab32.clear();
+  eng->dev_tab8.clear();
   return 0;
 }
 
@@ -286,8 +305,10 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
 
 /* score mode over a device-resident batch; results into d_score/d_xend/d_yend */
 int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta &bm,
-              int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st)
+              int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
+              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
+  if(!ev0) { ev0 = eng->ev0; ev1 = eng->ev1; }
   const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
   FastPlan plan;
   const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
@@ -299,9 +320,12 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     TRY(ensure_dev(eng, eng->d_counter, 8));
     int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
     int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
-    CU_TRY(cudaMemcpyAsync(d_t8, plan.tab8.data(), nn, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(d_t32, plan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    if(plan.tab32 != eng->dev_tab32 || plan.tab8 != eng->dev_tab8) {
+      CU_TRY(cudaMemcpyAsync(d_t8, plan.tab8.data(), nn, cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemcpyAsync(d_t32, plan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
+      eng->dev_tab32 = plan.tab32;
+      eng->dev_tab8 = plan.tab8;
+    }
     CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
     FastArgs F;
     F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
@@ -312,11 +336,11 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     F.counter = (unsigned long long *)eng->d_counter.p;
     F.score = d_score; F.xend = d_xend; F.yend = d_yend;
     F.max_lb = (int)bm.max_lb;
-    CU_TRY(cudaEventRecord(eng->ev0, st));
+    CU_TRY(cudaEventRecord(ev0, st));
     int r = fast_launch(plan, F, eng->num_sms, eng->smem_optin, st);
     if(r != 0) return fail(eng, SEQALIGN_ERR_CUDA, "fast kernel launch failed");
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(eng->ev1, st));
+    CU_TRY(cudaEventRecord(ev1, st));
     eng->last_launches++;
     eng->last_kernel = plan.name;
     return 0;
@@ -324,9 +348,9 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   GenArgs X;
   memset(&X, 0, sizeof(X));
   X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = nullptr;
-  CU_TRY(cudaEventRecord(eng->ev0, st));
+  CU_TRY(cudaEventRecord(ev0, st));
   TRY(launch_general<MODE_SCORE>(eng, db, sp, 0, (int64_t)db.n, bm, X, st));
-  CU_TRY(cudaEventRecord(eng->ev1, st));
+  CU_TRY(cudaEventRecord(ev1, st));
   eng->last_kernel = "general_score";
   return 0;
 }
@@ -503,38 +527,64 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
   TRY(ensure_dev(eng, eng->d_off_a, (n + 1) * 8));
   TRY(ensure_dev(eng, eng->d_off_b, (n + 1) * 8));
-  if(total_a) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, h_a, (size_t)total_a, cudaMemcpyHostToDevice, st));
-  if(total_b) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, h_b, (size_t)total_b, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-
-  DevBatch db;
-  db.a = (const uint8_t *)eng->d_seq_a.p; db.b = (const uint8_t *)eng->d_seq_b.p;
-  db.off_a = (const int64_t *)eng->d_off_a.p; db.off_b = (const int64_t *)eng->d_off_b.p;
-  db.n = n;
-  BatchMeta bm;
-  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a, total_b, st, &bm));
-  TRY(upload_tables(eng, bm, st));
-  if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
+  const uint8_t *d_a = (const uint8_t *)eng->d_seq_a.p, *d_b = (const uint8_t *)eng->d_seq_b.p;
+  const int64_t *d_oa = (const int64_t *)eng->d_off_a.p, *d_ob = (const int64_t *)eng->d_off_b.p;
 
   if(mode == SEQALIGN_MODE_SCORE || mode == SEQALIGN_MODE_SCORE_ONLY) {
+    /* Pipelined over chunks of pairs: the copy stream pushes chunk c+1 over
+     * PCIe while the compute stream scans and aligns chunk c.  Every chunk is
+     * a self-contained pass (own alphabet scan; tables are cached). */
     const bool ends = mode == SEQALIGN_MODE_SCORE;
+    cudaStream_t cs = eng->copy_stream;
     TRY(ensure_dev(eng, eng->d_score, n * 4));
     TRY(ensure_dev(eng, eng->d_xend, n * 4));
     TRY(ensure_dev(eng, eng->d_yend, n * 4));
-    TRY(run_score(eng, algo, db, bm, (int32_t *)eng->d_score.p, ends ? (int32_t *)eng->d_xend.p : nullptr,
-                  ends ? (int32_t *)eng->d_yend.p : nullptr, st));
     TRY(ensure_pin(eng, eng->h_res, n * 12));
     int32_t *hr = (int32_t *)eng->h_res.p;
-    CU_TRY(cudaMemcpyAsync(hr, eng->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
-    if(ends) {
-      CU_TRY(cudaMemcpyAsync(hr + n, eng->d_xend.p, n * 4, cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaMemcpyAsync(hr + 2 * n, eng->d_yend.p, n * 4, cudaMemcpyDeviceToHost, st));
+    int nchunks = (int)((total_a + total_b) / (8 << 20)) + 1;
+    if(nchunks > seqalign_batch::MAX_CHUNKS) nchunks = seqalign_batch::MAX_CHUNKS;
+    if((size_t)nchunks > n / 2048 + 1) nchunks = (int)(n / 2048 + 1);
+    const char *env = getenv("SEQALIGN_CHUNKS");
+    if(env && atoi(env) >= 1 && atoi(env) <= seqalign_batch::MAX_CHUNKS) nchunks = atoi(env);
+    if((size_t)nchunks > n) nchunks = (int)n;
+    CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    size_t bounds[seqalign_batch::MAX_CHUNKS + 1];
+    for(int c = 0; c <= nchunks; c++) bounds[c] = n * (size_t)c / (size_t)nchunks;
+    for(int c = 0; c < nchunks; c++) {
+      const int64_t a0 = h_off_a[bounds[c]], a1 = h_off_a[bounds[c + 1]];
+      const int64_t b0 = h_off_b[bounds[c]], b1 = h_off_b[bounds[c + 1]];
+      if(a1 > a0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_a.p + a0, h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
+      if(b1 > b0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_b.p + b0, h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+      CU_TRY(cudaEventRecord(eng->ev_copy[c], cs));
+    }
+    for(int c = 0; c < nchunks; c++) {
+      const size_t c0 = bounds[c], m = bounds[c + 1] - c0;
+      if(m == 0) continue;
+      CU_TRY(cudaStreamWaitEvent(st, eng->ev_copy[c], 0));
+      DevBatch db;
+      db.a = d_a; db.b = d_b; db.off_a = d_oa + c0; db.off_b = d_ob + c0; db.n = m;
+      BatchMeta bm;
+      TRY(scan_batch(eng, d_a + h_off_a[c0], d_b + h_off_b[c0], db.off_a, db.off_b, m,
+                     h_off_a[c0 + m] - h_off_a[c0], h_off_b[c0 + m] - h_off_b[c0], st, &bm));
+      TRY(upload_tables(eng, bm, st));
+      if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
+      int32_t *ds = (int32_t *)eng->d_score.p + c0, *dx = (int32_t *)eng->d_xend.p + c0, *dy = (int32_t *)eng->d_yend.p + c0;
+      TRY(run_score(eng, algo, db, bm, ds, ends ? dx : nullptr, ends ? dy : nullptr, st, eng->ev_k0[c], eng->ev_k1[c]));
+      CU_TRY(cudaMemcpyAsync(hr + c0, ds, m * 4, cudaMemcpyDeviceToHost, st));
+      if(ends) {
+        CU_TRY(cudaMemcpyAsync(hr + n + c0, dx, m * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(hr + 2 * n + c0, dy, m * 4, cudaMemcpyDeviceToHost, st));
+      }
     }
     CU_TRY(cudaStreamSynchronize(st));
-    float ms = 0;
-    CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
-    eng->last_ms = ms;
+    eng->last_ms = 0;
+    for(int c = 0; c < nchunks; c++) {
+      if(bounds[c + 1] == bounds[c]) continue;
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, eng->ev_k0[c], eng->ev_k1[c]));
+      eng->last_ms += ms;
+    }
     memcpy(eng->score.data(), hr, n * 4);
     if(ends) {
       memcpy(eng->xend.data(), hr + n, n * 4);
@@ -546,6 +596,16 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       }
     }
   } else {
+    if(total_a) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, h_a, (size_t)total_a, cudaMemcpyHostToDevice, st));
+    if(total_b) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, h_b, (size_t)total_b, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    DevBatch db;
+    db.a = d_a; db.b = d_b; db.off_a = d_oa; db.off_b = d_ob; db.n = n;
+    BatchMeta bm;
+    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a, total_b, st, &bm));
+    TRY(upload_tables(eng, bm, st));
+    if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
     TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
   }
   eng->n = n;
@@ -599,8 +659,13 @@ seqalign_batch_t *seqalign_batch_create(int device)
   eng->device = device;
   eng->num_sms = p.multiProcessorCount;
   eng->smem_optin = p.sharedMemPerBlockOptin;
-  if(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking) != cudaSuccess ||
-     cudaEventCreate(&eng->ev0) != cudaSuccess || cudaEventCreate(&eng->ev1) != cudaSuccess) {
+  bool ok = cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&eng->ev0) == cudaSuccess && cudaEventCreate(&eng->ev1) == cudaSuccess;
+  for(int i = 0; ok && i < seqalign_batch::MAX_CHUNKS; i++)
+    ok = cudaEventCreate(&eng->ev_copy[i]) == cudaSuccess && cudaEventCreate(&eng->ev_k0[i]) == cudaSuccess &&
+         cudaEventCreate(&eng->ev_k1[i]) == cudaSuccess;
+  if(!ok) {
     g_create_error = "cannot create stream/events";
     delete eng;
     return nullptr;
@@ -621,6 +686,12 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};
   for(PinBuf *b : h) b->release();
+  for(int i = 0; i < seqalign_batch::MAX_CHUNKS; i++) {
+    if(eng->ev_copy[i]) cudaEventDestroy(eng->ev_copy[i]);
+    if(eng->ev_k0[i]) cudaEventDestroy(eng->ev_k0[i]);
+    if(eng->ev_k1[i]) cudaEventDestroy(eng->ev_k1[i]);
+  }
+  if(eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   if(eng->ev0) cudaEventDestroy(eng->ev0);
   if(eng->ev1) cudaEventDestroy(eng->ev1);
   if(eng->stream) cudaStreamDestroy(eng->stream);
@@ -633,7 +704,10 @@ const char *seqalign_batch_error(const seqalign_batch_t *eng) { return eng ? eng
 int seqalign_batch_set_scoring(seqalign_batch_t *eng, const scoring_t *scoring)
 {
   if(!eng || !scoring) return SEQALIGN_ERR_ARG;
-  memcpy(eng->scoring, scoring, sizeof(scoring_t));
+  if(!eng->have_scoring || memcmp(eng->scoring, scoring, sizeof(scoring_t)) != 0) {
+    memcpy(eng->scoring, scoring, sizeof(scoring_t));
+    eng->scoring_version++;
+  }
   eng->have_scoring = true;
   return 0;
 }

@@ -72,9 +72,12 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
   for(int which = 0; which < 2; which++) {
     const uint8_t *seq = which ? seq_b : seq_a;
     const int64_t total = which ? total_b : total_a;
-    /* 16-byte vector body (base pointers are 16-byte aligned), scalar tail */
-    const int64_t nvec = total / 16;
-    const uint4 *v = (const uint4 *)seq;
+    /* scalar head up to 16-byte alignment, 16-byte vector body, scalar tail */
+    int64_t head = (int64_t)((16 - ((uintptr_t)seq & 15)) & 15);
+    if(head > total) head = total;
+    for(int64_t i = tid; i < head; i += nthreads) s_seen[which][seq[i]] = 1;
+    const int64_t nvec = (total - head) / 16;
+    const uint4 *v = (const uint4 *)(seq + head);
     for(int64_t i = tid; i < nvec; i += nthreads) {
       uint4 w = v[i];
       unsigned words[4] = {w.x, w.y, w.z, w.w};
@@ -86,7 +89,7 @@ scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
         s_seen[which][words[k] >> 24] = 1;
       }
     }
-    for(int64_t i = nvec * 16 + tid; i < total; i += nthreads) s_seen[which][seq[i]] = 1;
+    for(int64_t i = head + nvec * 16 + tid; i < total; i += nthreads) s_seen[which][seq[i]] = 1;
   }
 
   unsigned long long max_la = 0, max_lb = 0, cells = 0, max_cells = 0, min_la = ~0ull, min_lb = ~0ull;

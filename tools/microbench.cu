@@ -6,11 +6,13 @@
 #include <cuda_runtime.h>
 
 enum Op { IADD, IMAX, VIMAX3, VIADDMAX, VIADDMAX_RELU, IMAD, PRMT, SHFL, LDS32, CELL_SW, CELL_SW_KEY, VIMAX3_S16X2, VIADDMAX_S16X2_RELU, CELL_SW_S16 };
-static const char *names[] = {"IADD3", "IMNMX(max)", "VIMNMX3", "VIADDMNMX", "VIADDMNMX.RELU", "IMAD", "PRMT(sext)", "SHFL.UP", "LDS.32", "SW cell (7 ops, no key)", "SW cell (9 ops, packed key)", "VIMNMX3.S16x2", "VIADDMNMX.S16x2.RELU", "SW cell s16x2 (2 cells)"};
+static const char *names[] = {"IADD3", "IMNMX(max)", "VIMNMX3", "VIADDMNMX", "VIADDMNMX.RELU", "IMAD", "PRMT(sext)", "SHFL.UP", "LDS.32", "SW cell int32 score-only mix (fast_score_kernel)", "SW cell int32 end-cell mix (fast_score_kernel TREE)", "VIMNMX3.S16x2", "VIADDMNMX.S16x2.RELU", "SW cell s16x2 mix (fast16_kernel, 2 cells/op)"};
 static const int ops_per_iter[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 7 * 4, 9 * 4, 8, 8, 7 * 4};
+// DP cells advanced per loop iteration (0 = not a cell mix)
+static const int cells_per_iter[] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 0, 0, 8};
 
 template <int OP>
-__global__ void __launch_bounds__(256) bench(int iters, int seed, long long *cyc, int *sink)
+__global__ void __launch_bounds__(256) bench(int iters, int seed, int one, int one32, long long *cyc, int *sink)
 {
   __shared__ int sm[1024];
   for(int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * seed;
@@ -50,20 +52,22 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, long long *cyc
 #pragma unroll
       for(int k = 0; k < 8; k++) v[k] = sm[(v[k] + threadIdx.x) & 1023];
     } else if(OP == CELL_SW || OP == CELL_SW_KEY) {
-      // 4 cells of the fast SW recurrence chained left to right
-      int hl = v[0], gb = v[1], d = v[2];
+      // 4 cells of the int32 recurrence as the fast kernel issues them:
+      // 3 x VIADDMNMX + VIMNMX3 per cell, max3 tree over pairs of columns,
+      // H+open (and the key packing) as IMAD with a runtime multiplier
+      int hl = v[0], gb = v[1], d = v[2], kprev = 0;
 #pragma unroll
       for(int k = 0; k < 4; k++) {
-        int sub;
-        asm volatile("prmt.b32 %0, %1, %2, 0x9991;" : "=r"(sub) : "r"(w + k), "r"(0));
+        int sub = sm[(k + i) & 1023];
         int m = __viaddmax_s32(d, sub, 0);
         v[4 + k] = __viaddmax_s32_relu(v[4 + k], b, v[k]);
         gb = __viaddmax_s32_relu(gb, b, hl);
         int h = __vimax3_s32(m, v[4 + k], gb);
-        if(OP == CELL_SW_KEY) c = max(c, m * 65536 + i);
-        else c = max(c, m);
+        int key = OP == CELL_SW_KEY ? m * one32 + (31 - k) : m;
+        if(k & 1) c = __vimax3_s32(c, kprev, key);
+        kprev = key;
         d = v[k];
-        hl = h + a;
+        hl = h * one + a;
         v[k] = hl;
       }
       v[1] ^= gb;
@@ -74,21 +78,25 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, long long *cyc
 #pragma unroll
       for(int k = 0; k < 8; k++) v[k] = __viaddmax_s16x2_relu(v[k], b, v[(k + 3) & 7]);
     } else if(OP == CELL_SW_S16) {
-      unsigned hl = v[0], gb = v[1], d = v[2];
+      // 4 packed cell pairs as fast16_kernel issues them: PRMT combine,
+      // 3 x VIADDMNMX.S16x2, VIMNMX3.S16x2, max3 tree, packed add as IMAD
+      unsigned hl = v[0], gb = v[1], d = v[2], kprev = 0, cc = c;
 #pragma unroll
       for(int k = 0; k < 4; k++) {
         unsigned sub;
-        asm volatile("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(sub) : "r"(w + k), "r"(0));
-        unsigned m = __viaddmax_s16x2(d, sub, 0);
-        v[4 + k] = __viaddmax_s16x2_relu(v[4 + k], b, v[k]);
-        gb = __viaddmax_s16x2_relu(gb, b, hl);
+        asm volatile("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(sub) : "r"(w + k), "r"(w ^ (unsigned)i));
+        unsigned m = __viaddmax_s16x2(d, sub, 0x00020002u);
+        v[4 + k] = __viaddmax_s16x2(v[4 + k], b, v[k]);
+        gb = __viaddmax_s16x2(gb, b, hl);
         unsigned h = __vimax3_s16x2(m, v[4 + k], gb);
-        c = __vmaxs2(c, m);
+        if(k & 1) cc = __vimax3_s16x2(cc, kprev, m);
+        kprev = m;
         d = v[k];
-        hl = __vadd2(h, a);
+        hl = h * (unsigned)one + (unsigned)a;
         v[k] = hl;
       }
       v[1] ^= gb;
+      c = cc;
     }
   }
   long long t1 = clock64();
@@ -100,15 +108,15 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, long long *cyc
 }
 
 template <int OP>
-void run(int sms)
+void run(int sms, int clock_khz)
 {
   const int blocks = sms * 4, threads = 256, iters = 4096;
   long long *cyc; int *sink;
   cudaMalloc(&cyc, blocks * 8); cudaMalloc(&sink, 4);
-  bench<OP><<<blocks, threads>>>(16, 1, cyc, sink);
+  bench<OP><<<blocks, threads>>>(16, 1, 1, 32, cyc, sink);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  bench<OP><<<blocks, threads>>>(iters, 3, cyc, sink);
+  bench<OP><<<blocks, threads>>>(iters, 3, 1, 32, cyc, sink);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long *h = new long long[blocks];
@@ -116,8 +124,13 @@ void run(int sms)
   double avg = 0; for(int i = 0; i < blocks; i++) avg += h[i]; avg /= blocks;
   // 4 blocks x 256 threads resident per SM for the whole run
   const double lane_ops_per_sm = 4.0 * threads * (double)iters * ops_per_iter[OP];
-  printf("{\"op\": \"%s\", \"lane_ops_per_clk_per_sm\": %.1f, \"ms\": %.3f, \"gops\": %.1f}\n", names[OP],
-         lane_ops_per_sm / avg, ms, (double)blocks * threads * iters * ops_per_iter[OP] / ms / 1e6);
+  // event-timed rates (the clock64 figure is kept for reference only: blocks
+  // do not all start together, so it over-counts)
+  const double total_ops = (double)blocks * threads * iters * ops_per_iter[OP];
+  const double gops = total_ops / ms / 1e6;
+  const double cells_gcups = (double)blocks * threads * iters * cells_per_iter[OP] / ms / 1e6;
+  printf("{\"op\": \"%s\", \"gops\": %.1f, \"lane_ops_per_clk_per_sm_at_max_clock\": %.1f, \"cells_gcups\": %.1f, \"ms\": %.3f, \"clock64_lane_ops_per_clk_per_sm\": %.1f}\n",
+         names[OP], gops, gops * 1e9 / (sms * clock_khz * 1e3), cells_gcups, ms, lane_ops_per_sm / avg);
   cudaFree(cyc); cudaFree(sink); delete[] h;
 }
 
@@ -126,8 +139,9 @@ int main()
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, p.multiProcessorCount, p.clockRate);
   const int s = p.multiProcessorCount;
-  run<IADD>(s); run<IMAX>(s); run<VIMAX3>(s); run<VIADDMAX>(s); run<VIADDMAX_RELU>(s); run<IMAD>(s);
-  run<PRMT>(s); run<SHFL>(s); run<LDS32>(s); run<CELL_SW>(s); run<CELL_SW_KEY>(s);
-  run<VIMAX3_S16X2>(s); run<VIADDMAX_S16X2_RELU>(s); run<CELL_SW_S16>(s);
+#define run_(OP) run<OP>(s, p.clockRate)
+  run_(IADD); run_(IMAX); run_(VIMAX3); run_(VIADDMAX); run_(VIADDMAX_RELU); run_(IMAD);
+  run_(PRMT); run_(SHFL); run_(LDS32); run_(CELL_SW); run_(CELL_SW_KEY);
+  run_(VIMAX3_S16X2); run_(VIADDMAX_S16X2_RELU); run_(CELL_SW_S16);
   return 0;
 }
