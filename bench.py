@@ -217,6 +217,8 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line (NCCL otherwise announces its version there)
+        os.environ["NCCL_DEBUG"] = os.environ.get("SEQALIGN_NCCL_DEBUG", "WARN")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

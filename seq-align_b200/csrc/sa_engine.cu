@@ -286,18 +286,35 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
   A.forbid = (const uint8_t *)eng->d_forbid.p;
   A.lut = (const uint8_t *)eng->d_lut.p;
   A.table_in_smem = sp.ncodes <= SMEM_TABLE_MAX_CODES;
-  const int grid = general_grid(eng, (size_t)npairs);
+  /* wide pairs (>= 4 strips): a whole CTA per pair, warps pipelined over the
+   * column strips; otherwise a warp per pair */
+  const char *cenv = getenv("SEQALIGN_COOP");
+  const bool coop = cenv ? atoi(cenv) != 0 : bm.max_la > 3 * GSTRIP;
+  int grid;
+  if(coop) {
+    int64_t g = (int64_t)eng->num_sms * 2;
+    if(g > npairs) g = npairs;
+    grid = g < 1 ? 1 : (int)g;
+  } else {
+    grid = general_grid(eng, (size_t)npairs);
+  }
   A.bnd = nullptr; A.bnd_rows = 0;
   if(bm.max_la > GSTRIP) {
     A.bnd_rows = bm.max_lb + 1;
-    TRY(ensure_dev(eng, eng->d_bnd, (size_t)grid * GEN_WARPS * (size_t)A.bnd_rows * sizeof(int4)));
+    const size_t slots = (size_t)grid * (coop ? COOP_WARPS : GEN_WARPS);
+    TRY(ensure_dev(eng, eng->d_bnd, slots * (size_t)A.bnd_rows * sizeof(int4)));
     A.bnd = (int4 *)eng->d_bnd.p;
   }
   TRY(ensure_dev(eng, eng->d_counter, 8));
   CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
   A.counter = (unsigned long long *)eng->d_counter.p;
-  const size_t smem = general_smem_bytes(sp.ncodes, A.table_in_smem);
-  SA_LAUNCH(general_kernel<MODE>, grid, GEN_WARPS * 32, smem, st, A);
+  if(coop) {
+    const size_t smem = general_smem_bytes(sp.ncodes, A.table_in_smem, COOP_WARPS);
+    SA_LAUNCH(general_coop_kernel<MODE>, grid, COOP_WARPS * 32, smem, st, A);
+  } else {
+    const size_t smem = general_smem_bytes(sp.ncodes, A.table_in_smem);
+    SA_LAUNCH(general_kernel<MODE>, grid, GEN_WARPS * 32, smem, st, A);
+  }
   CU_TRY(cudaGetLastError());
   eng->last_launches++;
   return 0;

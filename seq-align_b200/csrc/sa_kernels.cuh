@@ -162,10 +162,31 @@ __host__ __device__ __forceinline__ bool hit_better(int v, int x, int y, int v2,
   return v > v2 || (v == v2 && (x < x2 || (x == x2 && y < y2)));
 }
 
+/* per-warp partial result of a pair (a CTA's warps are merged in shared memory) */
+struct PairPart { int bestV, bestX, bestY, has_fin, fm, fga, fgb; };
+
+__device__ __forceinline__ int4 ld_cg_int4(const int4 *p)
+{
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);   /* L2: the row may have been written by another warp of this CTA */
+#else
+  return *p;
+#endif
+}
+
+/*
+ * One pair, swept by W warps of a CTA (W = 1: a warp on its own).  Warp w
+ * takes the column strips w, w+W, ...; strip s reads the right edge of strip
+ * s-1 from the boundary slot (s-1)%W and writes its own into slot s%W.  With
+ * W > 1 the warps form a systolic pipeline: the consumer of a strip waits on
+ * a progress word in shared memory that the producer bumps every 32 rows.
+ */
 template <int MODE>
 __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
                              const int32_t *T, const uint8_t *F, const uint8_t *L,
-                             int4 *my_bnd, int4 *s_chunk)
+                             int4 *my_bnd, int4 *s_chunk,
+                             const int w, const int W, volatile unsigned long long *progress,
+                             PairPart *part)
 {
   const ScoreParams &sp = A.sp;
   const int64_t oa = A.off_a[p], ob = A.off_b[p];
@@ -181,7 +202,7 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
     dstride = dir_stride(la);
   }
 
-  if(MODE == MODE_MATS) {
+  if(MODE == MODE_MATS && w == 0) {
     /* borders: row 0 and column 0 (alignment.c:47-81) */
     for(int x = lane; x <= la; x += 32) {
       int m = minv, ga = minv, gb = sp.no_start ? 0 : addw(sp.gap_open, x * sp.ext);
@@ -196,14 +217,17 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
   }
 
   /* running best hit of this lane (SW) and the final cell (NW) */
-  int bestV = 0, bestX = 0, bestY = 0;
+  int bestV = 0, bestX = 0, bestY = 0, has_fin = 0;
   Cell3 fin = {0, 0, 0};
 
   const int nstrips = (la > 0 && lb > 0) ? (la + GSTRIP - 1) / GSTRIP : 0;
-  for(int strip = 0; strip < nstrips; strip++) {
+  for(int strip = w; strip < nstrips; strip += W) {
     const int x0 = strip * GSTRIP;
     const int xf = x0 + lane * GK + 1; /* my first column, 1-based */
     const bool more = strip + 1 < nstrips;
+    int4 *out_bnd = my_bnd + (int64_t)(strip % W) * A.bnd_rows;
+    const int4 *in_bnd = my_bnd + (int64_t)((strip + W - 1) % W) * A.bnd_rows;
+    const unsigned long long in_base = (unsigned long long)(strip - 1) * (unsigned long long)(lb + 1);
 
     int ac[GK], uM[GK], uGA[GK], uGB[GK], colV[GK], colY[GK];
 #pragma unroll
@@ -230,8 +254,14 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
         /* next 32 rows of the previous strip's right edge -> shared */
         __syncwarp();
         const int row = s + 1 + lane;
+        if(W > 1) {
+          /* wait until the producer strip has published these 32 rows */
+          const int need = s + 32 < lb ? s + 32 : lb;
+          while(progress[(strip + W - 1) % W] < in_base + (unsigned long long)need) SA_SPIN_HINT();
+          __threadfence_block();
+        }
         int4 v = make_int4(0, 0, 0, 0);
-        if(row <= lb) v = my_bnd[row];
+        if(row <= lb) v = W > 1 ? ld_cg_int4(&in_bnd[row]) : in_bnd[row];
         s_chunk[lane] = v;
         __syncwarp();
       }
@@ -343,7 +373,13 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
               }
           }
         }
-        if(more && lane == 31) my_bnd[y] = make_int4(out.m, out.ga, out.gb, 0);
+        if(more && lane == 31) {
+          out_bnd[y] = make_int4(out.m, out.ga, out.gb, 0);
+          if(W > 1 && ((y & 31) == 0 || y == lb)) {
+            __threadfence_block();
+            progress[strip % W] = (unsigned long long)strip * (unsigned long long)(lb + 1) + (unsigned long long)y;
+          }
+        }
         /* next row's diagonal predecessor is this row's left neighbour */
         dg = lf_in;
       }
@@ -362,31 +398,54 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
 #pragma unroll
       for(int j = 0; j < GK; j++)
         if(j == jf) { fin.m = uM[j]; fin.ga = uGA[j]; fin.gb = uGB[j]; }
+      has_fin = 1;
     }
     __syncwarp();
   }
 
-  /* ---- per-pair result ---- */
-  int score = 0, xe = 0, ye = 0, st = ST_M;
-  if(sp.is_sw && MODE != MODE_MATS) {
-    if(MODE == MODE_SCORE) {
+  /* ---- this warp's share of the result ---- */
+  if(MODE == MODE_SCORE && sp.is_sw) {
 #pragma unroll
-      for(int o = 16; o > 0; o >>= 1) {
-        const int v2 = __shfl_xor_sync(FULL, bestV, o);
-        const int x2 = __shfl_xor_sync(FULL, bestX, o);
-        const int y2 = __shfl_xor_sync(FULL, bestY, o);
-        if(hit_better(v2, x2, y2, bestV, bestX, bestY)) { bestV = v2; bestX = x2; bestY = y2; }
-      }
-      score = bestV; xe = bestX; ye = bestY;
+    for(int o = 16; o > 0; o >>= 1) {
+      const int v2 = __shfl_xor_sync(FULL, bestV, o);
+      const int x2 = __shfl_xor_sync(FULL, bestX, o);
+      const int y2 = __shfl_xor_sync(FULL, bestY, o);
+      if(hit_better(v2, x2, y2, bestV, bestX, bestY)) { bestV = v2; bestX = x2; bestY = y2; }
     }
-  } else if(MODE != MODE_MATS) {
-    /* final cell (la, lb): interior -> from the owning lane; else border */
-    if(nstrips > 0) {
-      const int x0 = (nstrips - 1) * GSTRIP;
-      const int lf_lane = (la - 1 - x0) / GK;
-      fin.m = __shfl_sync(FULL, fin.m, lf_lane);
-      fin.ga = __shfl_sync(FULL, fin.ga, lf_lane);
-      fin.gb = __shfl_sync(FULL, fin.gb, lf_lane);
+  }
+  {
+    /* the final cell (la, lb) lives in the lane that owns column la of the last strip */
+    const int x0 = nstrips > 0 ? (nstrips - 1) * GSTRIP : 0;
+    const int lf_lane = nstrips > 0 ? (la - 1 - x0) / GK : 0;
+    fin.m = __shfl_sync(FULL, fin.m, lf_lane);
+    fin.ga = __shfl_sync(FULL, fin.ga, lf_lane);
+    fin.gb = __shfl_sync(FULL, fin.gb, lf_lane);
+  }
+  part->bestV = bestV; part->bestX = bestX; part->bestY = bestY;
+  part->has_fin = has_fin; part->fm = fin.m; part->fga = fin.ga; part->fgb = fin.gb;
+}
+
+/* merge the warps' partial results and write the pair's outputs (one lane) */
+template <int MODE>
+__device__ void general_finish(const GenArgs &A, const int64_t p, const PairPart *parts, const int W)
+{
+  const ScoreParams &sp = A.sp;
+  if(MODE == MODE_MATS || (sp.is_sw && MODE == MODE_DIR)) return;
+  const int la = (int)(A.off_a[p + 1] - A.off_a[p]), lb = (int)(A.off_b[p + 1] - A.off_b[p]);
+  const int minv = sp.minv;
+  int score = 0, xe = 0, ye = 0, st = ST_M;
+  if(sp.is_sw) {
+    int bv = 0, bx = 0, by = 0;
+    for(int i = 0; i < W; i++)
+      if(hit_better(parts[i].bestV, parts[i].bestX, parts[i].bestY, bv, bx, by)) {
+        bv = parts[i].bestV; bx = parts[i].bestX; by = parts[i].bestY;
+      }
+    score = bv; xe = bx; ye = by;
+  } else {
+    Cell3 fin = {0, 0, 0};
+    if(la > 0 && lb > 0) {
+      for(int i = 0; i < W; i++)
+        if(parts[i].has_fin) { fin.m = parts[i].fm; fin.ga = parts[i].fga; fin.gb = parts[i].fgb; }
     } else if(la == 0 && lb == 0) {
       fin.m = fin.ga = fin.gb = 0;
     } else if(lb == 0) {
@@ -402,12 +461,10 @@ __device__ void general_pair(const GenArgs &A, const int64_t p, const int lane,
     if(fin.ga >= score) { score = fin.ga; st = ST_GA; }
     xe = la; ye = lb;
   }
-  if(lane == 0 && MODE != MODE_MATS && !(sp.is_sw && MODE == MODE_DIR)) {
-    A.score[p] = score;
-    if(A.xend) A.xend[p] = xe;
-    if(A.yend) A.yend[p] = ye;
-    if(A.state) A.state[p] = st;
-  }
+  A.score[p] = score;
+  if(A.xend) A.xend[p] = xe;
+  if(A.yend) A.yend[p] = ye;
+  if(A.state) A.state[p] = st;
 }
 
 template <int MODE>
@@ -437,13 +494,57 @@ general_kernel(const GenArgs A)
     if(lane == 0) t = atomicAdd(A.counter, 1ull);
     t = __shfl_sync(FULL, t, 0);
     if(t >= (unsigned long long)A.npairs) break;
-    general_pair<MODE>(A, A.pair0 + (int64_t)t, lane, T, F, s_lut, my_bnd, s_chunks + wib * 32);
+    PairPart part;
+    general_pair<MODE>(A, A.pair0 + (int64_t)t, lane, T, F, s_lut, my_bnd, s_chunks + wib * 32, 0, 1, nullptr, &part);
+    if(lane == 0) general_finish<MODE>(A, A.pair0 + (int64_t)t, &part, 1);
   }
 }
 
-inline size_t general_smem_bytes(int ncodes, bool table_in_smem)
+/* CTA-per-pair variant for wide pairs: COOP_WARPS warps sweep one pair as a
+ * systolic pipeline of column strips (see general_pair) */
+constexpr int COOP_WARPS = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(COOP_WARPS * 32)
+general_coop_kernel(const GenArgs A)
 {
-  size_t b = 256 + GEN_WARPS * 32 * sizeof(int4);
+  unsigned char *dsm = SA_DYN_SMEM();
+  const int n = A.sp.ncodes;
+  uint8_t *s_lut = dsm;
+  int4 *s_chunks = (int4 *)(dsm + 256);
+  int32_t *s_sub = (int32_t *)(dsm + 256 + COOP_WARPS * 32 * sizeof(int4));
+  uint8_t *s_forbid = (uint8_t *)(s_sub + (A.table_in_smem ? n * n : 0));
+  __shared__ unsigned long long s_progress[COOP_WARPS];
+  __shared__ unsigned long long s_next;
+  __shared__ PairPart s_parts[COOP_WARPS];
+
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+  if(A.table_in_smem)
+    for(int i = threadIdx.x; i < n * n; i += blockDim.x) { s_sub[i] = A.sub[i]; s_forbid[i] = A.forbid[i]; }
+  __syncthreads();
+
+  const int32_t *T = A.table_in_smem ? s_sub : A.sub;
+  const uint8_t *F = A.table_in_smem ? s_forbid : A.forbid;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int4 *cta_bnd = A.bnd + (int64_t)blockIdx.x * COOP_WARPS * A.bnd_rows;
+
+  for(;;) {
+    if(threadIdx.x == 0) s_next = atomicAdd(A.counter, 1ull);
+    if(threadIdx.x < COOP_WARPS) s_progress[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long t = s_next;
+    if(t >= (unsigned long long)A.npairs) break;
+    general_pair<MODE>(A, A.pair0 + (int64_t)t, lane, T, F, s_lut, cta_bnd, s_chunks + wib * 32,
+                       wib, COOP_WARPS, s_progress, &s_parts[wib]);
+    __syncthreads();
+    if(threadIdx.x == 0) general_finish<MODE>(A, A.pair0 + (int64_t)t, s_parts, COOP_WARPS);
+    __syncthreads();
+  }
+}
+
+inline size_t general_smem_bytes(int ncodes, bool table_in_smem, int warps = GEN_WARPS)
+{
+  size_t b = 256 + warps * 32 * sizeof(int4);
   if(table_in_smem) b += (size_t)ncodes * ncodes * 5;
   return b + 16;
 }

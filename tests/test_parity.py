@@ -124,6 +124,30 @@ def test_shapes(engine, big, shape):
             _score_check(engine, sc, algo, a, oa, b, ob, general=True)
 
 
+@pytest.mark.parametrize("shape", [(1100, 70), (2600, 40), (40, 2600)])
+def test_wide_pairs_cooperative(engine, big, shape):
+    """pairs of >= 4 strips are swept by a whole CTA (warps pipelined over the
+    column strips, more strips than warps): scores, tracebacks, matrices"""
+    la, lb = shape
+    if big:
+        la, lb = la * 2, lb * 4
+    a, oa, b, ob = synthetic_batch(la + lb, 3 if big else 2, la, lb)
+    sa = [a[i * la:(i + 1) * la].tobytes() for i in range(len(oa) - 1)]
+    sb = [b[i * lb:(i + 1) * lb].tobytes() for i in range(len(ob) - 1)]
+    for name in ("free_ends", "sw_cli", "nw_default"):
+        sc = scoring_from_spec(SPECS[name])
+        o = orc_from_scoring(sc)
+        for algo in (SW, NW):
+            _score_check(engine, sc, algo, a, oa, b, ob, general=True)
+            engine.submit(algo, MODE_ALIGN, sa, sb)
+            assert "general_dir" in engine.last_kernel
+            for i in range(len(sa)):
+                _check_alignment(engine.alignment(i), algo, o, sa[i], sb[i])
+        m, ga, gb = engine.fill_matrices(sa[0], sb[0], 0)
+        rc, em, ega, egb = orc_fill(o, sa[0], sb[0], 0)
+        assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb)
+
+
 def test_empty_inputs(engine):
     sc = scoring_from_spec(SPECS["nw_default"])
     engine.set_scoring(sc)
