@@ -399,3 +399,60 @@ def smith_waterman(a, b, scoring, max_hits=None):
     finally:
         L.alignment_free(res)
         L.smith_waterman_free(sw)
+
+
+class PipelinedAligner:
+    """Keeps `depth` batches in flight on one device: each worker thread owns an
+    engine (the C-ABI is one engine per host thread), so the PCIe copy of one
+    batch overlaps the DP kernel of another.  ctypes releases the GIL during
+    the calls.  `map_scores` yields score arrays in submission order."""
+
+    def __init__(self, device=0, scoring=None, depth=2):
+        from concurrent.futures import ThreadPoolExecutor
+        import queue
+        self._engines = queue.Queue()
+        self._all = [BatchAligner(device, scoring) for _ in range(depth)]
+        for e in self._all:
+            self._engines.put(e)
+        self._pool = ThreadPoolExecutor(max_workers=depth)
+        self.depth = depth
+
+    def _run(self, algo, mode, ptrs, n):
+        eng = self._engines.get()
+        try:
+            eng.submit_ptrs(algo, mode, *ptrs, n)
+            return eng.scores() if mode == MODE_SCORE_ONLY else eng.ends()
+        finally:
+            self._engines.put(eng)
+
+    def submit_ptrs(self, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n):
+        """asynchronous: returns a future whose result() is scores (MODE_SCORE_ONLY)
+        or (score, x_end, y_end)"""
+        return self._pool.submit(self._run, algo, mode, (ptr_a, off_a_ptr, ptr_b, off_b_ptr), n)
+
+    def submit_packed(self, algo, mode, seq_a, off_a, seq_b, off_b):
+        keep = (seq_a, off_a, seq_b, off_b)
+        fut = self.submit_ptrs(algo, mode, seq_a.ctypes.data, off_a.ctypes.data, seq_b.ctypes.data,
+                               off_b.ctypes.data, len(off_a) - 1)
+        fut._keep = keep
+        return fut
+
+    def map_scores(self, algo, batches, mode=MODE_SCORE_ONLY):
+        """batches: iterable of (seq_a, off_a, seq_b, off_b) numpy arrays"""
+        import collections
+        pending = collections.deque()
+        for b in batches:
+            pending.append(self.submit_packed(algo, mode, *b))
+            if len(pending) > self.depth:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+
+    @property
+    def engines(self):
+        return list(self._all)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for e in self._all:
+            e.close()

@@ -8,9 +8,9 @@
 
 namespace emu {
 
-Fiber *cur = nullptr;
-dim3 g_blockDim, g_gridDim;
-std::function<void()> g_entry;
+thread_local Fiber *cur = nullptr;
+thread_local dim3 g_blockDim, g_gridDim;
+thread_local std::function<void()> g_entry;
 
 static const size_t kStack = 512 * 1024;
 

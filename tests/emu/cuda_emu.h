@@ -36,7 +36,7 @@
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static
 
 using std::max;
@@ -88,9 +88,9 @@ struct Block {
   ucontext_t sched;
 };
 
-extern Fiber *cur;
-extern dim3 g_blockDim, g_gridDim;
-extern std::function<void()> g_entry;
+extern thread_local Fiber *cur;
+extern thread_local dim3 g_blockDim, g_gridDim;
+extern thread_local std::function<void()> g_entry;
 
 void yield();
 void block_barrier();

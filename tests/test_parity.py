@@ -377,3 +377,19 @@ def test_device_resident_api(engine, big):
                       ds.data_ptr(), dx.data_ptr(), dy.data_ptr())
     assert np.array_equal(ds.cpu().numpy(), s)
     assert np.array_equal(dx.cpu().numpy(), x) and np.array_equal(dy.cpu().numpy(), y)
+
+
+def test_pipelined_aligner(big):
+    """several batches in flight (one engine per worker thread), results in order"""
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    o = orc_from_scoring(sc)
+    pipe = seqalign.PipelinedAligner(0, sc, depth=3)
+    batches = [synthetic_batch(40 + k, 3000 if big else 5, 150 if big else 30, 150 if big else 30) for k in range(5)]
+    got = list(pipe.map_scores(SW, batches))
+    full = [pipe.submit_packed(SW, MODE_SCORE, *b) for b in batches]
+    for b, s, f in zip(batches, got, full):
+        es, ex, ey = orc_batch_sw(o, *b)
+        assert np.array_equal(s, es)
+        fs, fx, fy = f.result()
+        assert np.array_equal(fs, es) and np.array_equal(fx, ex) and np.array_equal(fy, ey)
+    pipe.close()
