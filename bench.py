@@ -345,7 +345,12 @@ def main():
                     "score_checksum_rank0": e2e_checksum},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
+                         # workload, from profiles/ncu_fast16_sw_r01_raw.csv (ncu --set full); not re-measured live
+                         "traffic": 31644160 if kernel_name == "fast16_sw_score" else None,
+                         "traffic_source": "profiles/ncu_fast16_sw_r01_raw.csv",
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "kernel": kernel_name, "kernel_ms": k_ms,
                          "kernel_gcups": cells_step / (k_ms * 1e-3) / 1e9,
                          "note": "score-only moves 0.0139 B/cell, so HBM is not the binding roof; the "
