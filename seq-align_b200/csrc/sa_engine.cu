@@ -392,12 +392,32 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
 
   eng->last_ms = 0;
   float ms = 0;
-  if(algo == SEQALIGN_SW) {
-    /* best cell first: the direction pass stores no scores */
+  /* specialised fill (score + end cell + traceback flags in one pass) when the
+   * scoring shape allows, else the general kernel (SW: best cell first, its
+   * direction pass stores no scores) */
+  FastPlan dplan;
+  const bool fast_dir = eng->force_mode != 1 &&
+                        fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, false, &dplan, true);
+  if(fast_dir && eng->force_mode == 2 && dplan.track == TRACK_TREE) dplan.track = TRACK_COLUMN;
+  if(algo == SEQALIGN_SW && !fast_dir) {
     TRY(run_score(eng, algo, db, bm, d_score, d_xend, d_yend, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
     eng->last_ms += ms;
+  }
+  int8_t *d_t8 = nullptr;
+  int32_t *d_t32 = nullptr;
+  if(fast_dir) {
+    const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+    TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
+    d_t8 = (int8_t *)eng->d_tab8.p;
+    d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
+    if(dplan.tab32 != eng->dev_tab32 || dplan.tab8 != eng->dev_tab8) {
+      CU_TRY(cudaMemcpyAsync(d_t8, dplan.tab8.data(), nn, cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemcpyAsync(d_t32, dplan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
+      eng->dev_tab32 = dplan.tab32;
+      eng->dev_tab8 = dplan.tab8;
+    }
   }
 
   size_t free_b = 0, total_b = 0;
@@ -446,14 +466,36 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     CU_TRY(cudaMemcpyAsync(eng->d_out_off.p, out_off.data(), m * 8, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));
 
-    GenArgs X;
-    memset(&X, 0, sizeof(X));
-    X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = d_state;
-    X.dir = (uint8_t *)eng->d_dir.p;
-    X.dir_off = (const int64_t *)eng->d_dir_off.p;
-    CU_TRY(cudaEventRecord(eng->ev0, st));
-    TRY(launch_general<MODE_DIR>(eng, db, sp, (int64_t)c0, (int64_t)m, bm, X, st));
-    CU_TRY(cudaEventRecord(eng->ev1, st));
+    if(fast_dir) {
+      TRY(ensure_dev(eng, eng->d_counter, 8));
+      CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+      FastArgs F;
+      memset(&F, 0, sizeof(F));
+      F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a + c0; F.off_b = db.off_b + c0;
+      F.npairs = (int64_t)m; F.sp = sp;
+      F.tab8 = d_t8; F.tab32 = d_t32;
+      F.lut = (const uint8_t *)eng->d_lut.p;
+      F.counter = (unsigned long long *)eng->d_counter.p;
+      F.score = d_score + c0; F.xend = d_xend + c0; F.yend = d_yend + c0;
+      F.max_lb = (int)bm.max_lb;
+      F.dir = (uint8_t *)eng->d_dir.p;
+      F.dir_off = (const int64_t *)eng->d_dir_off.p;
+      CU_TRY(cudaEventRecord(eng->ev0, st));
+      if(fast_launch(dplan, F, eng->num_sms, eng->smem_optin, st) != 0)
+        return fail(eng, SEQALIGN_ERR_CUDA, "fast dir kernel launch failed");
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaEventRecord(eng->ev1, st));
+      eng->last_launches++;
+    } else {
+      GenArgs X;
+      memset(&X, 0, sizeof(X));
+      X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = d_state;
+      X.dir = (uint8_t *)eng->d_dir.p;
+      X.dir_off = (const int64_t *)eng->d_dir_off.p;
+      CU_TRY(cudaEventRecord(eng->ev0, st));
+      TRY(launch_general<MODE_DIR>(eng, db, sp, (int64_t)c0, (int64_t)m, bm, X, st));
+      CU_TRY(cudaEventRecord(eng->ev1, st));
+    }
 
     WalkArgs W;
     memset(&W, 0, sizeof(W));
@@ -467,6 +509,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     int32_t *wk = (int32_t *)eng->d_walk.p;
     W.aln_start = wk; W.aln_len = wk + m; W.pos_a = wk + 2 * m; W.pos_b = wk + 3 * m;
     W.len_a = wk + 4 * m; W.len_b = wk + 5 * m; W.status = wk + 6 * m;
+    W.fmt = fast_dir ? 1 : 0;
     int wgrid = (int)((m + 127) / 128);
     if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
     SA_LAUNCH(walk_kernel, wgrid, 128, 0, st, W);
@@ -496,7 +539,8 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     }
     c0 = c1;
   }
-  eng->last_kernel = algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk";
+  eng->last_kernel = fast_dir ? (algo == SEQALIGN_SW ? "fast_sw_dir+walk" : "fast_nw_dir+walk")
+                              : (algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk");
 
   /* scores to host */
   eng->score.resize(n); eng->xend.resize(n); eng->yend.resize(n);

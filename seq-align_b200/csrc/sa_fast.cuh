@@ -47,6 +47,8 @@ struct FastArgs {
   ScoreParams sp;
   const int8_t *tab8;   /* [cb*ncodes + ca] = sub - open (int8 profile) */
   const int32_t *tab32; /* same, int32 (small alphabets) */
+  uint8_t *dir;         /* DIR kernels: traceback flag bytes, row-major per pair */
+  const int64_t *dir_off;
   int mul_one, mul_key; /* 1 and 32, as runtime values: see fast_score_kernel */
   const uint8_t *lut;
   unsigned long long *counter;
@@ -64,6 +66,7 @@ struct FastPlan {
   int track = 0;
   bool prof32 = false;
   bool s16 = false;   /* two pairs per register (fast16_kernel) */
+  bool dir = false;   /* also write traceback flag bytes */
   size_t smem = 0;
   int a_stage = 0, b_stage = 0;
 };
@@ -105,11 +108,21 @@ __host__ __device__ constexpr int prof32_stride(int K) { return (K % 4 == 0 && (
  *           the row.  Needs len_b <= 2047 and score < 2^15.
  *   COLUMN  one key per column (M<<16 | 0xFFFF-y), len_b <= 65535.
  * PROF32 int32 query profile (small alphabets): no PRMT per cell.
+ * DIR    also write one traceback byte per cell (align mode).  Unlike the
+ *        general kernel's resolved 2-bit codes these are five raw equality
+ *        flags (bit = 0 means "equal"), each one VIADDMNMX: min(a-b, 1) for
+ *        operands known to satisfy a >= b:
+ *          bit0  GA == H      bit1  GB == H       (of this cell)
+ *          bit2  GA == GA_up + ext                (gap_a was extended)
+ *          bit3  GB == GB_left + ext              (gap_b was extended)
+ *          bit4  GB == H_left + open              (gap_b could have been opened)
+ *        walk_kernel resolves them in the reference's priority order
+ *        (alignment.c:311-327): the choices depend only on these equalities.
  * mul_one / mul_key are the constants 1 and 32 passed as kernel arguments:
  * a multiply-add with a runtime multiplier is a real IMAD (FMA pipe), which
  * takes "H+open" and the key packing off the saturated ALU pipe.
  */
-template <int G, int K, bool IS_SW, int TRACK, bool PROF32>
+template <int G, int K, bool IS_SW, int TRACK, bool PROF32, bool DIR>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast_score_kernel(const FastArgs A)
 {
@@ -205,6 +218,9 @@ fast_score_kernel(const FastArgs A)
 
     unsigned char *ra = s_a + (stage * NG + grp) * A.a_stage + sha;
     unsigned char *rb = s_b + (stage * NG + grp) * A.b_stage + shb;
+    uint8_t *dirp = nullptr;
+    int dstride = 0;
+    if(DIR && have) { dirp = A.dir + A.dir_off[p]; dstride = (int)dir_stride(la); }
 
     /* seq_b: raw bytes -> codes, in place */
     for(int i = lig; i < lb; i += G) rb[i] = s_lut[rb[i]];
@@ -248,7 +264,9 @@ fast_score_kernel(const FastArgs A)
       else {
         const int gb0 = sp.no_start ? 0 : addw(sp.gap_open, x * ext);
         hp[j] = addw(imax(gb0, minv), open);
-        ga[j] = minv;
+        /* DIR subtracts neighbouring values: keep the "minus infinity" of the
+         * borders far from INT_MIN (no real value is below -2^28, see fast_plan) */
+        ga[j] = DIR ? -(1 << 29) : minv;
       }
       if constexpr(TRACK == TRACK_COLUMN) colbest[j] = 0;
     }
@@ -274,7 +292,7 @@ fast_score_kernel(const FastArgs A)
         if(IS_SW) { hl = open; gb = 0; }
         else {
           hl = addw(imax(sp.no_start ? 0 : addw(sp.gap_open, y * ext), minv), open);
-          gb = minv;
+          gb = DIR ? -(1 << 29) : minv;
         }
       }
       const int hl_in = hl;
@@ -304,10 +322,21 @@ fast_score_kernel(const FastArgs A)
         int d = hd;
         int rowbest = (TRACK == TRACK_NONE) ? best : 0;
         int kprev = 0;
+        unsigned dw[DIR ? (K + 3) / 4 : 1];
+        if constexpr(DIR) {
+#pragma unroll
+          for(int q = 0; q < (K + 3) / 4; q++) dw[q] = 0;
+        }
 #pragma unroll
         for(int j = 0; j < K; j++) {
           const int sub = PROF32 ? (int)w[j] : sext_byte_dyn(w[j / 4], j & 3);
           int m, h;
+          int uge = 0, lge = 0;
+          const int hleft = hl;
+          if constexpr(DIR) {
+            uge = ga[j] * mul_one + ext;   /* GA_up + ext, GB_left + ext (IMAD) */
+            lge = gb * mul_one + ext;
+          }
           if(IS_SW) {
             m = addmax(d, sub, 0);
             ga[j] = addmax_relu(ga[j], ext, hp[j]);
@@ -328,9 +357,23 @@ fast_score_kernel(const FastArgs A)
             gb = max3(addw(gb, ext), hl, minv);
             h = max3(m, ga[j], gb);
           }
+          if constexpr(DIR) {
+            /* five "not equal" bits, one VIADDMNMX each (a >= b holds for every pair) */
+            const int f = imin(h - ga[j], 1) + 2 * imin(h - gb, 1) + 4 * imin(ga[j] - uge, 1) +
+                          8 * imin(gb - lge, 1) + 16 * imin(gb - hleft, 1);
+            dw[j / 4] += (unsigned)f << (8 * (j & 3));
+          }
           d = hp[j];
           hl = h * mul_one + open;   /* IMAD (FMA pipe) */
           hp[j] = hl;
+        }
+        if constexpr(DIR) {
+          if(have) {
+            unsigned *drow = (unsigned *)(dirp + (int64_t)(y - 1) * dstride) + lig * (K / 4);
+#pragma unroll
+            for(int q = 0; q < K / 4; q++)
+              if(lig * K + 4 * q < dstride) drow[q] = dw[q];
+          }
         }
         if(IS_SW && TRACK == TRACK_NONE) best = rowbest;
         if(IS_SW && TRACK == TRACK_TREE) best = imax(best, rowbest * 2048 + (2047 - y));
@@ -661,7 +704,8 @@ inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage
 /* can the fast kernel take this batch?  fills the plan if so.
  * want_ends: the caller needs the SW end cell (x_end, y_end) */
 inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
-                      int64_t max_la, int64_t max_lb, bool want_ends, bool uniform, FastPlan *plan)
+                      int64_t max_la, int64_t max_lb, bool want_ends, bool uniform, FastPlan *plan,
+                      bool want_dir = false)
 {
   if(sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
   if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
@@ -682,10 +726,13 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
     if(sp.ext > 0 || sp.open > 0) return false;
     const long worst = (long)sp.gap_open + longest * sp.ext;
     if(worst < -(1L << 30)) return false;
+    if(want_dir && (worst + longest * (ft.min_sub < 0 ? ft.min_sub : 0) < -(1L << 28) ||
+                    shortest * (ft.max_sub > 0 ? ft.max_sub : 0) > (1L << 28)))
+      return false;
   }
   int G = 0, K = 0;
   for(const FastShape &sh : kFastShapes)
-    if((int64_t)sh.G * sh.K >= max_la) { G = sh.G; K = sh.K; break; }
+    if((int64_t)sh.G * sh.K >= max_la && (!want_dir || sh.K % 4 == 0)) { G = sh.G; K = sh.K; break; }
   if(!G) return false;
   const int n = ft.ncodes;
   /* int32 profile when it stays small (DNA-sized alphabets); else int8, which
@@ -696,11 +743,12 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   if(!prof32 && !fits8) return false;
   /* packed 16-bit kernel: SW score only, one shape for the whole batch, and
    * every biased value (score + |open|) inside int16 */
-  const bool s16 = sp.is_sw && !want_ends && uniform && fits8 &&
+  const bool s16 = sp.is_sw && !want_ends && !want_dir && uniform && fits8 &&
                    shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open < 32000 && sp.open > -16000 &&
                    ft.min_sub > -16000;
   if(s16) prof32 = false;
   plan->s16 = s16;
+  plan->dir = want_dir;
   plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
   plan->a_stage = (int)((G * K + 15 + 15) & ~15) + 16;
@@ -724,6 +772,10 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
       plan->tab32[(size_t)cb * tw + ca] = v;
       if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
     }
+  if(want_dir) {
+    plan->name = sp.is_sw ? "fast_sw_dir" : "fast_nw_dir";
+    return true;
+  }
   plan->name = !sp.is_sw ? "fast_nw_score" : s16 ? "fast16_sw_score"
              : plan->track == TRACK_NONE ? "fast_sw_score" : plan->track == TRACK_TREE ? "fast_sw_score_end" : "fast_sw_score_endcol";
   return true;
@@ -743,11 +795,19 @@ int fast_grid(KF kfn, size_t smem, int num_sms, int64_t need)
 template <int G, int K, bool P32>
 int fast_launch_gkp(const FastPlan &plan, const FastArgs &F, int num_sms, int64_t need, cudaStream_t st)
 {
-  void (*kfn)(const FastArgs);
-  if(!plan.is_sw) kfn = fast_score_kernel<G, K, false, TRACK_NONE, P32>;
-  else if(plan.track == TRACK_NONE) kfn = fast_score_kernel<G, K, true, TRACK_NONE, P32>;
-  else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32>;
-  else kfn = fast_score_kernel<G, K, true, TRACK_COLUMN, P32>;
+  void (*kfn)(const FastArgs) = nullptr;
+  if(plan.dir) {
+    if constexpr(K % 4 == 0) {
+      if(!plan.is_sw) kfn = fast_score_kernel<G, K, false, TRACK_NONE, P32, true>;
+      else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32, true>;
+      else kfn = fast_score_kernel<G, K, true, TRACK_COLUMN, P32, true>;
+    }
+  }
+  else if(!plan.is_sw) kfn = fast_score_kernel<G, K, false, TRACK_NONE, P32, false>;
+  else if(plan.track == TRACK_NONE) kfn = fast_score_kernel<G, K, true, TRACK_NONE, P32, false>;
+  else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32, false>;
+  else kfn = fast_score_kernel<G, K, true, TRACK_COLUMN, P32, false>;
+  if(!kfn) return -1;
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
   SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F);
   return 0;

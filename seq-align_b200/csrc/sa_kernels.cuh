@@ -572,6 +572,7 @@ struct WalkArgs {
   uint8_t *out_a, *out_b;
   const int64_t *out_off;      /* per pair (relative to pair0), la+lb each */
   int32_t *aln_start, *aln_len, *pos_a, *pos_b, *len_a, *len_b, *status; /* relative */
+  int fmt;                     /* 0: resolved 2-bit codes (general kernel), 1: equality flags (fast kernel) */
 };
 
 __global__ void __launch_bounds__(128)
@@ -591,13 +592,43 @@ walk_kernel(const WalkArgs A)
     int n = 0, status = WALK_OK;
     int x, y, st;
 
+    /* predecessor state when leaving cell (x,y) in state st */
+    auto next_state = [&](int x, int y, int st) -> int {
+      const unsigned f = dirp[(int64_t)(y - 1) * dstride + (x - 1)];
+      if(A.fmt == 0) return (f >> (2 * st)) & 3;
+      /* equality flags (bit clear = equal), resolved in the order GAP_A, GAP_B,
+       * MATCH of alignment.c:311-327.  A predecessor on the border ends the
+       * walk whatever its state, so it needs no flags. */
+      if(st == ST_M) {
+        if(x == 1 || y == 1) return ST_M;
+        const unsigned g = dirp[(int64_t)(y - 2) * dstride + (x - 2)];
+        return !(g & 1) ? ST_GA : !(g & 2) ? ST_GB : ST_M;
+      }
+      if(st == ST_GA) {
+        if(!(f & 4)) return ST_GA;
+        if(y == 1) return ST_M;
+        const unsigned g = dirp[(int64_t)(y - 2) * dstride + (x - 1)];
+        return !(g & 2) ? ST_GB : ST_M;
+      }
+      if(x == 1) return ST_M;
+      const unsigned g = dirp[(int64_t)(y - 1) * dstride + (x - 2)];
+      if(!(g & 1) && !(f & 16)) return ST_GA;
+      return !(f & 8) ? ST_GB : ST_M;
+    };
+
     if(!sp.is_sw) {
-      x = la; y = lb; st = A.state[p];
+      x = la; y = lb;
+      if(A.fmt == 0) st = A.state[p];
+      else if(la > 0 && lb > 0) {
+        /* end state GAP_A over GAP_B over MATCH on ties (needleman_wunsch.c:53-66) */
+        const unsigned f = dirp[(int64_t)(lb - 1) * dstride + (la - 1)];
+        st = !(f & 1) ? ST_GA : !(f & 2) ? ST_GB : ST_M;
+      } else st = ST_M;
       while(x > 0 && y > 0) {
         n++;
         ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
         rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
-        const int code = (dirp[(int64_t)(y - 1) * dstride + (x - 1)] >> (2 * st)) & 3;
+        const int code = next_state(x, y, st);
         if(code == ST_FAIL) { status = WALK_FAIL; break; }
         if(st == ST_M) { x--; y--; } else if(st == ST_GA) y--; else x--;
         st = code;
@@ -616,7 +647,7 @@ walk_kernel(const WalkArgs A)
         n++;
         ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
         rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
-        const int code = (dirp[(int64_t)(y - 1) * dstride + (x - 1)] >> (2 * st)) & 3;
+        const int code = next_state(x, y, st);
         if(code == ST_FAIL) { status = WALK_FAIL; break; }
         /* the penalty the reference subtracts implicitly: it continues
          * with the predecessor's stored value (alignment.c:311-327) */
@@ -634,6 +665,7 @@ walk_kernel(const WalkArgs A)
           x--;
         }
         cs = (int)((unsigned)cs - (unsigned)pen);
+        if(x == 0 || y == 0) cs = 0;   /* the SW borders are all zero: the hit starts here */
         st = code;
       }
       A.pos_a[r] = x; A.pos_b[r] = y; A.len_a[r] = xe - x; A.len_b[r] = ye - y;

@@ -58,6 +58,7 @@ __host__ __device__ __forceinline__ int addmax_relu(int a, int b, int c)
 #endif
 
 __host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 
 /* packed 2 x int16 DPX (VIADDMNMX.S16x2 / VIMNMX3.S16x2): two alignments per
  * instruction when the scores fit 16 bits */

@@ -191,10 +191,16 @@ def test_alignments_ragged(engine, big, name, algo):
     sc = scoring_from_spec(SPECS[name])
     o = orc_from_scoring(sc)
     engine.set_scoring(sc)
-    engine.force_general(False)
-    engine.submit(algo, MODE_ALIGN, sa, sb)
-    for i, (a, b) in enumerate(zip(sa, sb)):
-        _check_alignment(engine.alignment(i), algo, o, a, b)
+    kernels = set()
+    for mode in (0, 1, 2):   # specialised fill (flag bytes), general fill (2-bit codes), per-column end keys
+        engine.force_general(mode)
+        engine.submit(algo, MODE_ALIGN, sa, sb)
+        kernels.add(engine.last_kernel)
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            _check_alignment(engine.alignment(i), algo, o, a, b)
+    engine.force_general(0)
+    if name in ("sw_cli", "nw_default", "blosum62", "wild_n", "mutations"):
+        assert any(k.startswith("fast_") for k in kernels) and any("general_dir" in k for k in kernels), kernels
 
 
 def test_alignments_wide_and_waves(engine, big, monkeypatch):
