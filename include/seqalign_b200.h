@@ -109,13 +109,20 @@ int seqalign_batch_alignment(seqalign_batch_t *eng, size_t i, alignment_t *out);
 
 /* Device-resident variant (score mode): all pointers are device memory on
  * the engine's device, stream is a cudaStream_t (NULL = engine's own).
- * d_x_end/d_y_end may be NULL.  Asynchronous w.r.t. the host except for one
- * 64-byte readback that sizes the alphabet. */
+ * d_x_end/d_y_end may be NULL (score only: lets the engine use its packed
+ * 16-bit kernel).  Returns when the results are in d_score.  Sequence
+ * buffers must be readable up to the next 16-byte boundary past their end
+ * (the kernels stage them with 16-byte bulk copies). */
 int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
                               const void *d_seq_a, const void *d_off_a,
                               const void *d_seq_b, const void *d_off_b,
                               size_t n, void *d_score, void *d_x_end,
                               void *d_y_end, void *stream);
+
+/* seqalign_batch_run_device launches speculatively with the previous run's
+ * plan (same scoring, algorithm and outputs) and verifies against this
+ * batch's scan afterwards; these count how often the guess held / was redone. */
+void seqalign_batch_speculation_stats(const seqalign_batch_t *eng, int *hits, int *misses);
 
 /* Materialise mode, one pair: the literal aligner_align() contract
  * (reference src/alignment.c:28-168).  match/gap_a/gap_b are host arrays of

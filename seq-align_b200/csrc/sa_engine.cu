@@ -62,6 +62,16 @@ struct seqalign_batch {
   uint64_t tables_pres[8] = {};
   std::vector<int32_t> dev_tab32;
   std::vector<int8_t> dev_tab8;
+  /* plan of the last device-resident run, reused speculatively by the next one */
+  struct {
+    bool valid = false;
+    unsigned version = 0;
+    int algo = 0;
+    bool want_ends = false;
+    FastPlan plan;
+    int64_t max_lb = 0;
+  } spec;
+  int spec_hits = 0, spec_misses = 0;
   int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only */
 
   /* inputs on device */
@@ -166,24 +176,32 @@ struct BatchMeta {
   int64_t max_la, max_lb, cells, max_cells, min_la, min_lb;
 };
 
-/* scan the device-resident batch: alphabet, longest sequences, cell count */
-int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
-               const int64_t *d_off_a, const int64_t *d_off_b, size_t n,
-               int64_t total_a, int64_t total_b, cudaStream_t st, BatchMeta *bm)
+/* scan the device-resident pairs [0,n) of (off_a, off_b): alphabet, longest
+ * sequences, cell count.  d_a/d_b are the buffers the offsets index into;
+ * approx_bytes only sizes the grid.  scan_launch is asynchronous,
+ * scan_collect waits for it and decodes the meta block. */
+int scan_launch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
+                const int64_t *d_off_a, const int64_t *d_off_b, size_t n,
+                int64_t approx_bytes, cudaStream_t st)
 {
   TRY(ensure_dev(eng, eng->d_meta, META_WORDS * 8));
   TRY(ensure_pin(eng, eng->h_meta, META_WORDS * 8));
   CU_TRY(cudaMemsetAsync(eng->d_meta.p, 0, META_WORDS * 8, st));
   CU_TRY(cudaMemsetAsync((unsigned long long *)eng->d_meta.p + META_MIN_LA, 0xff, 16, st));
-  int64_t work = (total_a + total_b) / 16 + (int64_t)n;
+  int64_t work = approx_bytes / 16 + (int64_t)n;
   int grid = (int)((work + 255) / 256);
   if(grid > eng->num_sms * 8) grid = eng->num_sms * 8;
   if(grid < 1) grid = 1;
-  SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, total_a, d_b, total_b, d_off_a, d_off_b,
+  SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, d_b, d_off_a, d_off_b,
             (int64_t)n, (unsigned long long *)eng->d_meta.p);
   CU_TRY(cudaGetLastError());
   eng->last_launches++;
   CU_TRY(cudaMemcpyAsync(eng->h_meta.p, eng->d_meta.p, META_WORDS * 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int scan_collect(seqalign_batch *eng, size_t n, cudaStream_t st, BatchMeta *bm)
+{
   CU_TRY(cudaStreamSynchronize(st));
   const uint64_t *m = (const uint64_t *)eng->h_meta.p;
   for(int i = 0; i < 4; i++) { bm->pres_a[i] = m[META_PRES_A + i]; bm->pres_b[i] = m[META_PRES_B + i]; }
@@ -196,6 +214,14 @@ int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
   return 0;
 }
 
+int scan_batch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
+               const int64_t *d_off_a, const int64_t *d_off_b, size_t n,
+               int64_t approx_bytes, cudaStream_t st, BatchMeta *bm)
+{
+  TRY(scan_launch(eng, d_a, d_b, d_off_a, d_off_b, n, approx_bytes, st));
+  return scan_collect(eng, n, st, bm);
+}
+
 /* flatten scoring for this batch's alphabet and upload the tables; skipped
  * when the device already holds the tables of this (scoring, alphabet) */
 int upload_tables(seqalign_batch *eng, const BatchMeta &bm, cudaStream_t st)
@@ -205,6 +231,7 @@ int upload_tables(seqalign_batch *eng, const BatchMeta &bm, cudaStream_t st)
   if(eng->tables_valid && eng->tables_version == eng->scoring_version &&
      memcmp(pres, eng->tables_pres, sizeof(pres)) == 0)
     return 0;
+  eng->spec.valid = false;   /* codes are about to change under any cached plan */
   flatten_scoring(eng->scoring, bm.pres_a, bm.pres_b, &eng->ft);
   const FlatTable &ft = eng->ft;
   const size_t nn = (size_t)ft.ncodes * ft.ncodes;
@@ -321,11 +348,41 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
 }
 
 /* score mode over a device-resident batch; results into d_score/d_xend/d_yend */
+/* launch the specialised score kernel of `plan` (tables must be on the device) */
+int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScoreParams &sp, const DevBatch &db,
+                      int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
+                      cudaEvent_t ev0, cudaEvent_t ev1)
+{
+  const size_t nn = (size_t)sp.ncodes * (sp.ncodes + 1);
+  int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
+  int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
+  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+  FastArgs F;
+  memset(&F, 0, sizeof(F));
+  F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
+  F.npairs = (int64_t)db.n; F.sp = sp;
+  F.tab8 = d_t8;
+  F.tab32 = d_t32;
+  F.lut = (const uint8_t *)eng->d_lut.p;
+  F.counter = (unsigned long long *)eng->d_counter.p;
+  F.score = d_score; F.xend = d_xend; F.yend = d_yend;
+  F.max_lb = (int)max_lb;
+  CU_TRY(cudaEventRecord(ev0, st));
+  int r = fast_launch(plan, F, eng->num_sms, eng->smem_optin, st);
+  if(r != 0) return fail(eng, SEQALIGN_ERR_CUDA, "fast kernel launch failed");
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(ev1, st));
+  eng->last_launches++;
+  eng->last_kernel = plan.name;
+  return 0;
+}
+
 int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta &bm,
               int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
-              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
+              cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, FastPlan *plan_out = nullptr)
 {
   if(!ev0) { ev0 = eng->ev0; ev1 = eng->ev1; }
+  if(plan_out) plan_out->G = 0;
   const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
   FastPlan plan;
   const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
@@ -343,23 +400,8 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       eng->dev_tab32 = plan.tab32;
       eng->dev_tab8 = plan.tab8;
     }
-    CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
-    FastArgs F;
-    F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
-    F.npairs = (int64_t)db.n; F.sp = sp;
-    F.tab8 = d_t8;
-    F.tab32 = d_t32;
-    F.lut = (const uint8_t *)eng->d_lut.p;
-    F.counter = (unsigned long long *)eng->d_counter.p;
-    F.score = d_score; F.xend = d_xend; F.yend = d_yend;
-    F.max_lb = (int)bm.max_lb;
-    CU_TRY(cudaEventRecord(ev0, st));
-    int r = fast_launch(plan, F, eng->num_sms, eng->smem_optin, st);
-    if(r != 0) return fail(eng, SEQALIGN_ERR_CUDA, "fast kernel launch failed");
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(ev1, st));
-    eng->last_launches++;
-    eng->last_kernel = plan.name;
+    TRY(launch_fast_score(eng, plan, sp, db, bm.max_lb, d_score, d_xend, d_yend, st, ev0, ev1));
+    if(plan_out) *plan_out = plan;
     return 0;
   }
   GenArgs X;
@@ -626,8 +668,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       DevBatch db;
       db.a = d_a; db.b = d_b; db.off_a = d_oa + c0; db.off_b = d_ob + c0; db.n = m;
       BatchMeta bm;
-      TRY(scan_batch(eng, d_a + h_off_a[c0], d_b + h_off_b[c0], db.off_a, db.off_b, m,
-                     h_off_a[c0 + m] - h_off_a[c0], h_off_b[c0 + m] - h_off_b[c0], st, &bm));
+      TRY(scan_batch(eng, d_a, d_b, db.off_a, db.off_b, m,
+                     h_off_a[c0 + m] - h_off_a[c0] + h_off_b[c0 + m] - h_off_b[c0], st, &bm));
       TRY(upload_tables(eng, bm, st));
       if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
       int32_t *ds = (int32_t *)eng->d_score.p + c0, *dx = (int32_t *)eng->d_xend.p + c0, *dy = (int32_t *)eng->d_yend.p + c0;
@@ -664,7 +706,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     DevBatch db;
     db.a = d_a; db.b = d_b; db.off_a = d_oa; db.off_b = d_ob; db.n = n;
     BatchMeta bm;
-    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a, total_b, st, &bm));
+    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a + total_b, st, &bm));
     TRY(upload_tables(eng, bm, st));
     if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
     TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
@@ -868,19 +910,59 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
   if(n == 0) return 0;
   CU_TRY(cudaSetDevice(eng->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : eng->stream;
-  /* totals: last offsets */
-  int64_t tot[2];
-  CU_TRY(cudaMemcpyAsync(&tot[0], (const int64_t *)d_off_a + n, 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(&tot[1], (const int64_t *)d_off_b + n, 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
   DevBatch db;
   db.a = (const uint8_t *)d_seq_a; db.b = (const uint8_t *)d_seq_b;
   db.off_a = (const int64_t *)d_off_a; db.off_b = (const int64_t *)d_off_b;
   db.n = n;
+  const bool want_ends = (d_x_end != nullptr || d_y_end != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
+  const int64_t approx_bytes = (int64_t)n * 256;
   BatchMeta bm;
-  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, tot[0], tot[1], st, &bm));
+  float ms = 0;
+
+  /* Speculative path: batches of a stream usually share alphabet and shape
+   * with their predecessor, so launch the DP kernel right away with the
+   * previous plan and tables while the scan of THIS batch runs next to it;
+   * the scan result is checked afterwards and the batch is redone the slow
+   * way if the guess was wrong (the kernels turn pairs that do not fit the
+   * plan into empty ones, so a wrong guess is harmless). */
+  if(eng->spec.valid && eng->spec.version == eng->scoring_version && eng->spec.algo == algo &&
+     eng->spec.want_ends == want_ends && eng->tables_valid && eng->tables_version == eng->scoring_version &&
+     eng->spec.plan.tab32 == eng->dev_tab32 && eng->spec.plan.tab8 == eng->dev_tab8 &&
+     eng->force_mode == 0 && !getenv("SEQALIGN_NO_SPECULATION")) {
+    const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
+    TRY(launch_fast_score(eng, eng->spec.plan, sp, db, eng->spec.max_lb, (int32_t *)d_score,
+                          (int32_t *)d_x_end, (int32_t *)d_y_end, st, eng->ev0, eng->ev1));
+    TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, approx_bytes, st));
+    TRY(scan_collect(eng, n, st, &bm));
+    uint64_t pres[8];
+    bool subset = true;
+    for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
+    for(int i = 0; i < 8; i++) subset = subset && (pres[i] & ~eng->tables_pres[i]) == 0;
+    FastPlan now;
+    const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
+    const FastPlan &old = eng->spec.plan;
+    if(subset && bm.max_lb <= eng->spec.max_lb &&
+       fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &now) &&
+       now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) &&
+       (old.track != TRACK_TREE || bm.max_lb <= 2047)) {
+      /* (a larger shape than needed, or int32 where 16 bits would do, is still exact) */
+      CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+      eng->last_ms = ms;
+      eng->spec_hits++;
+      return 0;
+    }
+    eng->spec_misses++;
+    eng->spec.valid = false;
+    eng->last_launches = 0;
+  } else {
+    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, approx_bytes, st, &bm));
+  }
+
   TRY(upload_tables(eng, bm, st));
   if(eng->ft.any_unknown) {
+    int64_t tot[2];
+    CU_TRY(cudaMemcpy(&tot[0], (const int64_t *)d_off_a + n, 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&tot[1], (const int64_t *)d_off_b + n, 8, cudaMemcpyDeviceToHost));
     std::vector<char> ha((size_t)tot[0] + 1), hb((size_t)tot[1] + 1);
     std::vector<int64_t> oa(n + 1), ob(n + 1);
     CU_TRY(cudaMemcpy(ha.data(), d_seq_a, (size_t)tot[0], cudaMemcpyDeviceToHost));
@@ -889,11 +971,22 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
     CU_TRY(cudaMemcpy(ob.data(), d_off_b, (n + 1) * 8, cudaMemcpyDeviceToHost));
     TRY(check_unknown_pairs(eng, ha.data(), oa.data(), hb.data(), ob.data(), n));
   }
-  TRY(run_score(eng, algo, db, bm, (int32_t *)d_score, (int32_t *)d_x_end, (int32_t *)d_y_end, st));
+  FastPlan used;
+  TRY(run_score(eng, algo, db, bm, (int32_t *)d_score, (int32_t *)d_x_end, (int32_t *)d_y_end, st,
+                nullptr, nullptr, &used));
   CU_TRY(cudaStreamSynchronize(st));
-  float ms = 0;
   CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   eng->last_ms = ms;
+  if(used.G != 0 && !eng->ft.any_unknown) {
+    eng->spec.valid = true;
+    eng->spec.version = eng->scoring_version;
+    eng->spec.algo = algo;
+    eng->spec.want_ends = want_ends;
+    eng->spec.plan = used;
+    eng->spec.max_lb = bm.max_lb;
+  } else {
+    eng->spec.valid = false;
+  }
   return 0;
 }
 
@@ -923,7 +1016,7 @@ int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_
   db.off_a = (const int64_t *)eng->d_off_a.p; db.off_b = (const int64_t *)eng->d_off_b.p;
   db.n = 1;
   BatchMeta bm;
-  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, 1, off_a[1], off_b[1], st, &bm));
+  TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, 1, off_a[1] + off_b[1], st, &bm));
   TRY(upload_tables(eng, bm, st));
   if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, seq_a, off_a, seq_b, off_b, 1));
 
@@ -951,6 +1044,13 @@ int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_
   eng->last_ms = ms;
   eng->last_kernel = "general_mats";
   return 0;
+}
+
+void seqalign_batch_speculation_stats(const seqalign_batch_t *eng, int *hits, int *misses)
+{
+  if(!eng) return;
+  if(hits) *hits = eng->spec_hits;
+  if(misses) *misses = eng->spec_misses;
 }
 
 void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b)

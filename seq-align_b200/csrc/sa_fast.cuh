@@ -171,6 +171,7 @@ fast_score_kernel(const FastArgs A)
         if(p >= A.npairs) break;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        if(ea - oa > G * K || eb - ob > A.max_lb) continue;   /* does not fit the plan: skipped, see below */
         if(ea > oa) bytes += (uint32_t)(((ea + 15) & ~(int64_t)15) - (oa & ~(int64_t)15));
         if(eb > ob) bytes += (uint32_t)(((eb + 15) & ~(int64_t)15) - (ob & ~(int64_t)15));
       }
@@ -180,6 +181,7 @@ fast_score_kernel(const FastArgs A)
         if(p >= A.npairs) break;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        if(ea - oa > G * K || eb - ob > A.max_lb) continue;
         const int64_t a0 = oa & ~(int64_t)15, b0 = ob & ~(int64_t)15;
         if(ea > oa)
           bulk_g2s(s_a + (st * NG + g) * A.a_stage, A.seq_a + a0, (uint32_t)(((ea + 15) & ~(int64_t)15) - a0), &bar[st]);
@@ -212,6 +214,10 @@ fast_score_kernel(const FastArgs A)
       const int64_t oa = A.off_a[p], ob = A.off_b[p];
       la = (int)(A.off_a[p + 1] - oa); lb = (int)(A.off_b[p + 1] - ob);
       sha = (int)(oa & 15); shb = (int)(ob & 15);
+      /* a pair larger than the launch was planned for (only possible when the
+       * engine launched speculatively with the previous batch's plan) is
+       * treated as empty; the engine notices from the scan and reruns */
+      if(la > G * K || lb > A.max_lb) { la = 0; lb = 0; }
     }
     mbar_wait(&bar[stage], stage ? phase1 : phase0);
     if(stage) phase1 ^= 1; else phase0 ^= 1;
@@ -528,6 +534,7 @@ fast16_kernel(const FastArgs A)
         if(p >= A.npairs) break;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        if(ea - oa > G * K || eb - ob > A.max_lb) continue;   /* does not fit the plan: skipped, see below */
         if(ea > oa) bytes += (uint32_t)(((ea + 15) & ~(int64_t)15) - (oa & ~(int64_t)15));
         if(eb > ob) bytes += (uint32_t)(((eb + 15) & ~(int64_t)15) - (ob & ~(int64_t)15));
       }
@@ -537,6 +544,7 @@ fast16_kernel(const FastArgs A)
         if(p >= A.npairs) break;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
+        if(ea - oa > G * K || eb - ob > A.max_lb) continue;
         const int64_t a0 = oa & ~(int64_t)15, b0 = ob & ~(int64_t)15;
         if(ea > oa)
           bulk_g2s(s_a + (st * NP + g) * A.a_stage, A.seq_a + a0, (uint32_t)(((ea + 15) & ~(int64_t)15) - a0), &bar[st]);
@@ -569,6 +577,12 @@ fast16_kernel(const FastArgs A)
       la = (int)(A.off_a[plo + 1] - oa); lb = (int)(A.off_b[plo + 1] - ob);   /* uniform batch: same for phi */
       sha_lo = (int)(oa & 15); shb_lo = (int)(ob & 15);
     }
+    if(have_hi) {
+      /* speculative launches only: shapes the plan did not foresee become empty pairs */
+      const int la_hi = (int)(A.off_a[phi + 1] - A.off_a[phi]), lb_hi = (int)(A.off_b[phi + 1] - A.off_b[phi]);
+      if(la_hi != la || lb_hi != lb) { la = 0; lb = 0; }
+    }
+    if(la > G * K || lb > A.max_lb) { la = 0; lb = 0; }
     if(have_hi) { sha_hi = (int)(A.off_a[phi] & 15); shb_hi = (int)(A.off_b[phi] & 15); }
     mbar_wait(&bar[stage], stage ? phase1 : phase0);
     if(stage) phase1 ^= 1; else phase0 ^= 1;

@@ -55,11 +55,13 @@ enum { META_PRES_A = 0, META_PRES_B = 4, META_MAX_LA = 8, META_MAX_LB = 9,
  * HBM-bound streaming read.
  */
 __global__ void __launch_bounds__(256)
-scan_kernel(const uint8_t *__restrict__ seq_a, int64_t total_a,
-            const uint8_t *__restrict__ seq_b, int64_t total_b,
+scan_kernel(const uint8_t *__restrict__ seq_a_base, const uint8_t *__restrict__ seq_b_base,
             const int64_t *__restrict__ off_a, const int64_t *__restrict__ off_b,
             int64_t npairs, unsigned long long *__restrict__ meta)
 {
+  /* the pairs' bytes are seq_*_base[off[0] .. off[npairs]) */
+  const uint8_t *seq_a = seq_a_base + off_a[0], *seq_b = seq_b_base + off_b[0];
+  const int64_t total_a = off_a[npairs] - off_a[0], total_b = off_b[npairs] - off_b[0];
   __shared__ unsigned s_seen[2][256];
   __shared__ unsigned long long s_red[6];
   for(int i = threadIdx.x; i < 512; i += blockDim.x) (&s_seen[0][0])[i] = 0;

@@ -140,6 +140,7 @@ def load():
     L.seqalign_batch_last_kernel.restype = ctypes.c_char_p
     L.seqalign_batch_last_kernel.argtypes = [vp]
     L.seqalign_batch_force_general.argtypes = [vp, ctypes.c_int]
+    L.seqalign_batch_speculation_stats.argtypes = [vp, vp, vp]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -354,6 +355,11 @@ class BatchAligner:
                                                     m.ctypes.data, ga.ctypes.data, gb.ctypes.data))
         shape = (len(b) + 1, len(a) + 1)
         return m.reshape(shape), ga.reshape(shape), gb.reshape(shape)
+
+    def speculation_stats(self):
+        h, m = ctypes.c_int(), ctypes.c_int()
+        self._L.seqalign_batch_speculation_stats(self._h, ctypes.byref(h), ctypes.byref(m))
+        return h.value, m.value
 
     @property
     def last_kernel_ms(self):

@@ -364,25 +364,55 @@ def test_full_size_invariants(engine, big):
     assert np.array_equal(s[idx], es) and np.array_equal(x[idx], ex) and np.array_equal(y[idx], ey)
 
 
-def test_device_resident_api(engine, big):
-    """seqalign_batch_run_device: inputs and outputs stay in HBM"""
-    if not big:
-        pytest.skip("needs torch CUDA tensors")
-    import torch
-    a, oa, b, ob = synthetic_batch(9, 3000, 150, 150)
+def _device_arrays(big, arrays):
+    """CUDA copies of numpy arrays (GPU) / the arrays themselves (the emulator's
+    device memory is host memory); returns (keepalive, pointers)"""
+    if big:
+        import torch
+        ts = [torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0") for a in arrays]
+        torch.cuda.synchronize()
+        return ts, [t.data_ptr() for t in ts]
+    # pad: the kernels stage sequences with 16-byte bulk copies
+    ts = [np.concatenate([a, np.zeros(32, dtype=a.dtype)]) for a in arrays]
+    return ts, [t.ctypes.data for t in ts]
+
+
+def _device_result(big, t, n):
+    return t.cpu().numpy()[:n] if big else t[:n]
+
+
+def test_device_resident_api(big):
+    """seqalign_batch_run_device: inputs and outputs stay in device memory.  A stream of
+    batches exercises the speculative launch (previous plan reused, verified against the
+    scan afterwards): hits, and misses on a new alphabet, a new shape, ragged lengths."""
     sc = scoring_from_spec(SPECS["sw_cli"])
-    engine.set_scoring(sc)
-    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
-    s, x, y = engine.ends()
-    dev = torch.device("cuda:0")
-    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
-    toa, tob = torch.from_numpy(oa).to(dev), torch.from_numpy(ob).to(dev)
-    ds, dx, dy = (torch.zeros(3000, dtype=torch.int32, device=dev) for _ in range(3))
-    torch.cuda.synchronize()
-    engine.run_device(SW, ta.data_ptr(), toa.data_ptr(), tb.data_ptr(), tob.data_ptr(), 3000,
-                      ds.data_ptr(), dx.data_ptr(), dy.data_ptr())
-    assert np.array_equal(ds.cpu().numpy(), s)
-    assert np.array_equal(dx.cpu().numpy(), x) and np.array_equal(dy.cpu().numpy(), y)
+    o = orc_from_scoring(sc)
+    eng = seqalign.BatchAligner(0, sc)
+    n, L = (3000, 150) if big else (6, 30)
+    ragged = seqalign.pack(ragged_batch(3, n, L + 20, L + 20)[0]) + seqalign.pack(ragged_batch(3, n, L + 20, L + 20)[1])
+    withn = ragged_batch(8, n, L, L, alphabet=b"ACGTN")
+    batches = [
+        synthetic_batch(9, n, L, L), synthetic_batch(10, n, L, L), synthetic_batch(11, n, L, L),   # miss, hit, hit
+        seqalign.pack(withn[0]) + seqalign.pack(withn[1]),                                          # new alphabet + ragged
+        synthetic_batch(12, n, L, L),                                                              # back to uniform
+        synthetic_batch(13, n, L + 40, L + 33),                                                     # larger shape
+        synthetic_batch(14, n, L, L), synthetic_batch(15, n, L - 7, L - 3),                         # smaller shape: hit
+        ragged,
+    ]
+    for want_ends in (False, True):
+        for k, (a, oa, b, ob) in enumerate(batches):
+            m = len(oa) - 1
+            es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+            out = [np.zeros(m, dtype=np.int32) for _ in range(3)]
+            keep, (pa, poa, pb, pob, ps, px, py) = _device_arrays(big, [a, oa, b, ob] + out)
+            eng.run_device(SW, pa, poa, pb, pob, m, ps, px if want_ends else 0, py if want_ends else 0)
+            assert np.array_equal(_device_result(big, keep[4], m), es), (want_ends, k, eng.last_kernel)
+            if want_ends:
+                assert np.array_equal(_device_result(big, keep[5], m), ex)
+                assert np.array_equal(_device_result(big, keep[6], m), ey)
+    hits, misses = eng.speculation_stats()
+    assert hits >= 6 and misses >= 4, (hits, misses)
+    eng.close()
 
 
 def test_pipelined_aligner(big):
