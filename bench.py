@@ -217,9 +217,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    # stdout carries exactly one JSON line: everything else that libraries print there
+    # (NCCL announces its version on stdout) is sent to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL otherwise announces its version there)
-        os.environ["NCCL_DEBUG"] = os.environ.get("SEQALIGN_NCCL_DEBUG", "WARN")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -377,7 +380,9 @@ def main():
                 g, sec, s = cpu_port_gcups(a, oa, b, ob, 2000)
                 line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": 1, "kind": "port",
                                         "sample": "oracle C restatement on 2000 pairs of one step, 1 thread, %.1f s" % sec}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

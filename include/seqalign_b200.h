@@ -37,6 +37,8 @@ typedef struct seqalign_batch seqalign_batch_t;
 /* what a submit computes */
 #define SEQALIGN_MODE_SCORE 0 /* score (+ best SW cell): fill only           */
 #define SEQALIGN_MODE_ALIGN 1 /* + traceback: gapped strings, pos/len fields */
+#define SEQALIGN_MODE_HITS 3  /* SW: every local hit in the reference's order,
+                                 up to the limits of seqalign_batch_set_hit_limits */
 #define SEQALIGN_MODE_SCORE_ONLY 2 /* scores only (x_end/y_end = 0): lets the
                                       engine use its packed 16-bit SW kernel   */
 
@@ -106,6 +108,20 @@ size_t seqalign_batch_size(const seqalign_batch_t *eng);
  * Returns 1 if an alignment was written, 0 if the SW pair has no hit,
  * negative on error. */
 int seqalign_batch_alignment(seqalign_batch_t *eng, size_t i, alignment_t *out);
+
+/* MODE_HITS (Smith-Waterman): the whole hit iteration of
+ * smith_waterman_align2 + repeated smith_waterman_fetch on a fresh aligner
+ * (reference src/smith_waterman.c:152-161, 165-277) runs on the device:
+ * candidates with match score >= min_score (and > 0) sorted by score desc,
+ * x asc, y asc; walked back in that order through a visited mask; a walk that
+ * meets a marked cell is dropped.  At most max_hits hits per pair are kept
+ * (the reference's CLI stops the same way: src/tools/sw_cmdline.c:214-217).
+ * Defaults: max_hits 8, min_score 1.  Available for the scoring shapes of the
+ * specialised kernel (SEQALIGN_ERR_ARG otherwise). */
+int seqalign_batch_set_hit_limits(seqalign_batch_t *eng, size_t max_hits, int32_t min_score);
+size_t seqalign_batch_hit_count(const seqalign_batch_t *eng, size_t i);
+/* hit h of pair i into a reference alignment_t (all fields); 1 if written */
+int seqalign_batch_hit(seqalign_batch_t *eng, size_t i, size_t h, alignment_t *out);
 
 /* Device-resident variant (score mode): all pointers are device memory on
  * the engine's device, stream is a cudaStream_t (NULL = engine's own).

@@ -20,6 +20,7 @@
 #include "sa_flatten.h"
 #include "sa_kernels.cuh"
 #include "sa_fast.cuh"
+#include "sa_hits.cuh"
 
 using namespace sa;
 
@@ -82,6 +83,8 @@ struct seqalign_batch {
   DevBuf d_score, d_xend, d_yend, d_state;
   /* align-mode wave buffers */
   DevBuf d_dir, d_dir_off, d_out_a, d_out_b, d_out_off, d_walk;
+  /* multi-hit mode */
+  DevBuf d_m16, d_keys0, d_keys1, d_mask, d_ncand, d_which, d_nhits, d_rec;
   /* materialise mode */
   DevBuf d_mats;
   PinBuf h_in_a, h_in_b, h_off_a, h_off_b, h_meta, h_res, h_walk, h_str_a, h_str_b;
@@ -93,6 +96,12 @@ struct seqalign_batch {
   std::vector<int64_t> res_off;          /* n+1, into res_a/res_b */
   std::vector<char> res_a, res_b;        /* right-aligned strings per pair */
   std::vector<int32_t> aln_start, aln_len, pos_a, pos_b, len_a, len_b, status;
+  /* multi-hit results */
+  int32_t hit_min_score = 1, hit_max = 8;
+  std::vector<int32_t> nhits, hit_rec;       /* n, n*max*8 */
+  std::vector<int64_t> hit_off;              /* n+1: string offsets (per pair: max * (la+lb)) */
+  std::vector<char> hit_a, hit_b;
+  int32_t hit_max_used = 0;
 
   double last_ms = 0;
   int last_launches = 0;
@@ -606,6 +615,163 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   return 0;
 }
 
+/* multi-hit mode (SW): fill with flags + int16 match scores, candidate sort,
+ * masked walks, all on the device; waves bounded by memory */
+int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
+             const int64_t *h_off_a, const int64_t *h_off_b, cudaStream_t st)
+{
+  const size_t n = db.n;
+  const ScoreParams sp = make_params(eng->scoring, 1, eng->ft.ncodes);
+  FastPlan plan;
+  if(eng->force_mode == 1 ||
+     !fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, false, &plan, true) || bm.max_lb > 65535)
+    return fail(eng, SEQALIGN_ERR_ARG,
+                "device multi-hit needs the specialised kernel (affine gaps with gap_open <= 0, no gap/mismatch "
+                "restrictions, len_a <= 512, small scores); use smith_waterman_fetch() for this input");
+  plan.hits = true;
+  plan.track = TRACK_NONE;
+  const int maxh = eng->hit_max;
+  eng->hit_max_used = maxh;
+  const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+  TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
+  int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
+  int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
+  if(plan.tab32 != eng->dev_tab32 || plan.tab8 != eng->dev_tab8) {
+    CU_TRY(cudaMemcpyAsync(d_t8, plan.tab8.data(), nn, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_t32, plan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
+    eng->dev_tab32 = plan.tab32;
+    eng->dev_tab8 = plan.tab8;
+  }
+  TRY(ensure_dev(eng, eng->d_score, n * 4));
+  TRY(ensure_dev(eng, eng->d_counter, 8));
+
+  eng->nhits.assign(n, 0);
+  eng->hit_rec.assign(n * (size_t)maxh * 8, 0);
+  eng->hit_off.assign(n + 1, 0);
+  for(size_t i = 0; i < n; i++)
+    eng->hit_off[i + 1] = eng->hit_off[i] + (int64_t)maxh * ((h_off_a[i + 1] - h_off_a[i]) + (h_off_b[i + 1] - h_off_b[i]));
+  eng->hit_a.resize((size_t)eng->hit_off[n] + 1);
+  eng->hit_b.resize((size_t)eng->hit_off[n] + 1);
+
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  int64_t budget = (int64_t)(free_b / 2);
+  const char *env = getenv("SEQALIGN_DIR_BUDGET");
+  if(env) budget = atoll(env);
+  eng->last_ms = 0;
+
+  std::vector<int64_t> dir_off, out_off;
+  size_t c0 = 0;
+  while(c0 < n) {
+    size_t c1 = c0;
+    int64_t cells = 0;
+    dir_off.clear(); out_off.clear();
+    while(c1 < n) {
+      const int64_t la = h_off_a[c1 + 1] - h_off_a[c1], lb = h_off_b[c1 + 1] - h_off_b[c1];
+      const int64_t need = (dir_stride((int)la) * lb + 31) & ~(int64_t)31;   /* whole mask words per pair */
+      /* per cell: flags 1 + scores 2 + two key buffers 16 + mask 1/8 */
+      if(c1 > c0 && (cells + need) * 20 > budget) break;
+      dir_off.push_back(cells);
+      out_off.push_back(eng->hit_off[c1] - eng->hit_off[c0]);
+      cells += need;
+      c1++;
+    }
+    const size_t m = c1 - c0;
+    const int64_t obytes = eng->hit_off[c1] - eng->hit_off[c0];
+    TRY(ensure_dev(eng, eng->d_dir, (size_t)cells + 64));
+    TRY(ensure_dev(eng, eng->d_m16, (size_t)cells * 2 + 64));
+    TRY(ensure_dev(eng, eng->d_keys0, (size_t)cells * 8 + 64));
+    TRY(ensure_dev(eng, eng->d_keys1, (size_t)cells * 8 + 64));
+    TRY(ensure_dev(eng, eng->d_mask, (size_t)cells / 8 + 64));
+    TRY(ensure_dev(eng, eng->d_dir_off, m * 8));
+    TRY(ensure_dev(eng, eng->d_out_off, m * 8));
+    TRY(ensure_dev(eng, eng->d_ncand, m * 4));
+    TRY(ensure_dev(eng, eng->d_which, m * 4));
+    TRY(ensure_dev(eng, eng->d_nhits, m * 4));
+    TRY(ensure_dev(eng, eng->d_rec, m * (size_t)maxh * 32));
+    TRY(ensure_dev(eng, eng->d_out_a, (size_t)obytes + 16));
+    TRY(ensure_dev(eng, eng->d_out_b, (size_t)obytes + 16));
+    TRY(ensure_pin(eng, eng->h_walk, m * 4 + m * (size_t)maxh * 32));
+    TRY(ensure_pin(eng, eng->h_str_a, (size_t)obytes + 16));
+    TRY(ensure_pin(eng, eng->h_str_b, (size_t)obytes + 16));
+    CU_TRY(cudaMemcpyAsync(eng->d_dir_off.p, dir_off.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(eng->d_out_off.p, out_off.data(), m * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(eng->d_mask.p, 0, (size_t)cells / 8 + 64, st));
+    CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+
+    FastArgs F;
+    memset(&F, 0, sizeof(F));
+    F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a + c0; F.off_b = db.off_b + c0;
+    F.npairs = (int64_t)m; F.sp = sp;
+    F.tab8 = d_t8; F.tab32 = d_t32;
+    F.lut = (const uint8_t *)eng->d_lut.p;
+    F.counter = (unsigned long long *)eng->d_counter.p;
+    F.score = (int32_t *)eng->d_score.p + c0;
+    F.max_lb = (int)bm.max_lb;
+    F.dir = (uint8_t *)eng->d_dir.p;
+    F.dir_off = (const int64_t *)eng->d_dir_off.p;
+    F.m16 = (int16_t *)eng->d_m16.p;
+    CU_TRY(cudaEventRecord(eng->ev0, st));
+    if(fast_launch(plan, F, eng->num_sms, eng->smem_optin, st) != 0)
+      return fail(eng, SEQALIGN_ERR_CUDA, "fast hits kernel launch failed");
+    CU_TRY(cudaGetLastError());
+    eng->last_launches++;
+
+    HitsArgs H;
+    memset(&H, 0, sizeof(H));
+    H.seq_a = db.a; H.seq_b = db.b; H.off_a = db.off_a + c0; H.off_b = db.off_b + c0;
+    H.npairs = (int64_t)m; H.sp = sp;
+    H.sub = (const int32_t *)eng->d_sub.p; H.lut = (const uint8_t *)eng->d_lut.p;
+    H.dir = (const uint8_t *)eng->d_dir.p; H.m16 = (const int16_t *)eng->d_m16.p;
+    H.dir_off = (const int64_t *)eng->d_dir_off.p;
+    H.keys0 = (unsigned long long *)eng->d_keys0.p; H.keys1 = (unsigned long long *)eng->d_keys1.p;
+    H.ncand = (int32_t *)eng->d_ncand.p; H.which = (int32_t *)eng->d_which.p;
+    H.mask = (unsigned *)eng->d_mask.p;
+    H.min_score = eng->hit_min_score; H.max_hits = maxh;
+    H.nhits = (int32_t *)eng->d_nhits.p; H.rec = (int32_t *)eng->d_rec.p;
+    H.out_a = (uint8_t *)eng->d_out_a.p; H.out_b = (uint8_t *)eng->d_out_b.p;
+    H.out_off = (const int64_t *)eng->d_out_off.p;
+    H.counter = (unsigned long long *)eng->d_counter.p;
+    CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+    int sgrid = (int)((m + HITS_WARPS - 1) / HITS_WARPS);
+    if(sgrid > eng->num_sms * 3) sgrid = eng->num_sms * 3;
+    SA_LAUNCH(hits_sort_kernel, sgrid, HITS_WARPS * 32, 0, st, H);
+    CU_TRY(cudaGetLastError());
+    int wgrid = (int)((m + 127) / 128);
+    if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
+    SA_LAUNCH(hits_walk_kernel, wgrid, 128, 0, st, H);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(eng->ev1, st));
+    eng->last_launches += 2;
+
+    int32_t *hw = (int32_t *)eng->h_walk.p;
+    CU_TRY(cudaMemcpyAsync(hw, eng->d_nhits.p, m * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(hw + m, eng->d_rec.p, m * (size_t)maxh * 32, cudaMemcpyDeviceToHost, st));
+    if(obytes > 0) {
+      CU_TRY(cudaMemcpyAsync(eng->h_str_a.p, eng->d_out_a.p, (size_t)obytes, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaMemcpyAsync(eng->h_str_b.p, eng->d_out_b.p, (size_t)obytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+    eng->last_ms += ms;
+    memcpy(&eng->nhits[c0], hw, m * 4);
+    memcpy(&eng->hit_rec[c0 * (size_t)maxh * 8], hw + m, m * (size_t)maxh * 32);
+    if(obytes > 0) {
+      memcpy(&eng->hit_a[(size_t)eng->hit_off[c0]], eng->h_str_a.p, (size_t)obytes);
+      memcpy(&eng->hit_b[(size_t)eng->hit_off[c0]], eng->h_str_b.p, (size_t)obytes);
+    }
+    c0 = c1;
+  }
+  /* scores: best hit of each pair */
+  for(size_t i = 0; i < n; i++) {
+    eng->score[i] = eng->nhits[i] > 0 ? eng->hit_rec[i * (size_t)maxh * 8] : 0;
+    eng->xend[i] = eng->yend[i] = 0;
+  }
+  eng->last_kernel = "fast_sw_hits+sort+walk";
+  return 0;
+}
+
 int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
                   const char *h_b, const int64_t *h_off_b, size_t n)
 {
@@ -614,7 +780,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   eng->last_launches = 0;
   eng->last_ms = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
-  if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN && mode != SEQALIGN_MODE_SCORE_ONLY))
+  if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN && mode != SEQALIGN_MODE_SCORE_ONLY &&
+      mode != SEQALIGN_MODE_HITS) || (mode == SEQALIGN_MODE_HITS && algo != SEQALIGN_SW))
     return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
   eng->algo = algo; eng->mode = mode;
   eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);
@@ -709,7 +876,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a + total_b, st, &bm));
     TRY(upload_tables(eng, bm, st));
     if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
-    TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
+    if(mode == SEQALIGN_MODE_HITS) TRY(run_hits(eng, db, bm, h_off_a, h_off_b, st));
+    else TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
   }
   eng->n = n;
   return 0;
@@ -784,7 +952,8 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
   DevBuf *d[] = {&eng->d_seq_a, &eng->d_seq_b, &eng->d_off_a, &eng->d_off_b, &eng->d_meta, &eng->d_counter,
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
                  &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
-                 &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats};
+                 &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats, &eng->d_m16, &eng->d_keys0,
+                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec};
   for(DevBuf *b : d) b->release();
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};
@@ -1049,6 +1218,46 @@ int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_
   eng->last_ms = ms;
   eng->last_kernel = "general_mats";
   return 0;
+}
+
+int seqalign_batch_set_hit_limits(seqalign_batch_t *eng, size_t max_hits, int32_t min_score)
+{
+  if(!eng || max_hits < 1 || max_hits > 4096) return SEQALIGN_ERR_ARG;
+  eng->hit_max = (int32_t)max_hits;
+  eng->hit_min_score = min_score;
+  return 0;
+}
+
+size_t seqalign_batch_hit_count(const seqalign_batch_t *eng, size_t i)
+{
+  if(!eng || eng->mode != SEQALIGN_MODE_HITS || i >= eng->n) return 0;
+  return (size_t)eng->nhits[i];
+}
+
+int seqalign_batch_hit(seqalign_batch_t *eng, size_t i, size_t h, alignment_t *out)
+{
+  if(!eng || !out) return SEQALIGN_ERR_ARG;
+  if(eng->mode != SEQALIGN_MODE_HITS || i >= eng->n) return fail(eng, SEQALIGN_ERR_ARG, "no hits for this index");
+  if(h >= (size_t)eng->nhits[i]) return 0;
+  const int32_t *r = &eng->hit_rec[(i * (size_t)eng->hit_max_used + h) * 8];
+  const size_t len = (size_t)r[5];
+  if(out->capacity < len + 1) {
+    size_t cap = ROUNDUP2POW(len + 1);
+    out->result_a = (char *)realloc(out->result_a, cap);
+    out->result_b = (char *)realloc(out->result_b, cap);
+    out->capacity = cap;
+    if(!out->result_a || !out->result_b) return fail(eng, SEQALIGN_ERR_NOMEM, "Out of memory");
+  }
+  const size_t per = (size_t)(eng->hit_off[i + 1] - eng->hit_off[i]) / (size_t)eng->hit_max_used;
+  const size_t base = (size_t)eng->hit_off[i] + h * per + (size_t)r[6];
+  memcpy(out->result_a, &eng->hit_a[base], len);
+  memcpy(out->result_b, &eng->hit_b[base], len);
+  out->result_a[len] = out->result_b[len] = '\0';
+  out->length = len;
+  out->score = r[0];
+  out->pos_a = (size_t)r[1]; out->pos_b = (size_t)r[2];
+  out->len_a = (size_t)r[3]; out->len_b = (size_t)r[4];
+  return 1;
 }
 
 void seqalign_batch_speculation_stats(const seqalign_batch_t *eng, int *hits, int *misses)

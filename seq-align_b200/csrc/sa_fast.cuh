@@ -49,6 +49,7 @@ struct FastArgs {
   const int32_t *tab32; /* same, int32 (small alphabets) */
   uint8_t *dir;         /* DIR kernels: traceback flag bytes, row-major per pair */
   const int64_t *dir_off;
+  int16_t *m16;         /* HITS kernels: match scores, same layout/offsets (in elements) */
   int mul_one, mul_key; /* 1 and 32, as runtime values: see fast_score_kernel */
   const uint8_t *lut;
   unsigned long long *counter;
@@ -67,6 +68,7 @@ struct FastPlan {
   bool prof32 = false;
   bool s16 = false;   /* two pairs per register (fast16_kernel) */
   bool dir = false;   /* also write traceback flag bytes */
+  bool hits = false;  /* ... and int16 match scores (multi-hit stage) */
   size_t smem = 0;
   int a_stage = 0, b_stage = 0;
 };
@@ -118,11 +120,13 @@ __host__ __device__ constexpr int prof32_stride(int K) { return (K % 4 == 0 && (
  *          bit4  GB == H_left + open              (gap_b could have been opened)
  *        walk_kernel resolves them in the reference's priority order
  *        (alignment.c:311-327): the choices depend only on these equalities.
+ * HITS   (with DIR) also store every cell's match score as int16, the input
+ *        of the multi-hit stage (candidate sort + masked walks, sa_hits.cuh).
  * mul_one / mul_key are the constants 1 and 32 passed as kernel arguments:
  * a multiply-add with a runtime multiplier is a real IMAD (FMA pipe), which
  * takes "H+open" and the key packing off the saturated ALU pipe.
  */
-template <int G, int K, bool IS_SW, int TRACK, bool PROF32, bool DIR>
+template <int G, int K, bool IS_SW, int TRACK, bool PROF32, bool DIR, bool HITS = false>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast_score_kernel(const FastArgs A)
 {
@@ -329,9 +333,14 @@ fast_score_kernel(const FastArgs A)
         int rowbest = (TRACK == TRACK_NONE) ? best : 0;
         int kprev = 0;
         unsigned dw[DIR ? (K + 3) / 4 : 1];
+        unsigned mw[HITS ? (K + 1) / 2 : 1];
         if constexpr(DIR) {
 #pragma unroll
           for(int q = 0; q < (K + 3) / 4; q++) dw[q] = 0;
+        }
+        if constexpr(HITS) {
+#pragma unroll
+          for(int q = 0; q < (K + 1) / 2; q++) mw[q] = 0;
         }
 #pragma unroll
         for(int j = 0; j < K; j++) {
@@ -369,6 +378,7 @@ fast_score_kernel(const FastArgs A)
                           8 * imin(gb - lge, 1) + 16 * imin(gb - hleft, 1);
             dw[j / 4] += (unsigned)f << (8 * (j & 3));
           }
+          if constexpr(HITS) mw[j / 2] += (unsigned)m << (16 * (j & 1));   /* 0 <= m < 2^15 */
           d = hp[j];
           hl = h * mul_one + open;   /* IMAD (FMA pipe) */
           hp[j] = hl;
@@ -379,6 +389,12 @@ fast_score_kernel(const FastArgs A)
 #pragma unroll
             for(int q = 0; q < K / 4; q++)
               if(lig * K + 4 * q < dstride) drow[q] = dw[q];
+            if constexpr(HITS) {
+              unsigned *mrow = (unsigned *)(A.m16 + A.dir_off[p] + (int64_t)(y - 1) * dstride) + lig * (K / 2);
+#pragma unroll
+              for(int q = 0; q < K / 2; q++)
+                if(lig * K + 2 * q < dstride) mrow[q] = mw[q];
+            }
           }
         }
         if(IS_SW && TRACK == TRACK_NONE) best = rowbest;
@@ -810,7 +826,10 @@ template <int G, int K, bool P32>
 int fast_launch_gkp(const FastPlan &plan, const FastArgs &F, int num_sms, int64_t need, cudaStream_t st)
 {
   void (*kfn)(const FastArgs) = nullptr;
-  if(plan.dir) {
+  if(plan.dir && plan.hits) {
+    if constexpr(K % 4 == 0) kfn = fast_score_kernel<G, K, true, TRACK_NONE, P32, true, true>;
+  }
+  else if(plan.dir) {
     if constexpr(K % 4 == 0) {
       if(!plan.is_sw) kfn = fast_score_kernel<G, K, false, TRACK_NONE, P32, true>;
       else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32, true>;

@@ -24,6 +24,7 @@ SW = 1
 MODE_SCORE = 0
 MODE_ALIGN = 1
 MODE_SCORE_ONLY = 2
+MODE_HITS = 3
 
 ERR_CUDA = -1
 ERR_UNKNOWN_PAIR = -2
@@ -141,6 +142,10 @@ def load():
     L.seqalign_batch_last_kernel.argtypes = [vp]
     L.seqalign_batch_force_general.argtypes = [vp, ctypes.c_int]
     L.seqalign_batch_speculation_stats.argtypes = [vp, vp, vp]
+    L.seqalign_batch_set_hit_limits.argtypes = [vp, sz, ctypes.c_int32]
+    L.seqalign_batch_hit_count.restype = sz
+    L.seqalign_batch_hit_count.argtypes = [vp, sz]
+    L.seqalign_batch_hit.argtypes = [vp, sz, sz, vp]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -339,6 +344,17 @@ class BatchAligner:
         """Alignment of pair i (None for an SW pair without a hit)."""
         rc = self._check(self._L.seqalign_batch_alignment(self._h, i, self._res))
         return Alignment(self._res.contents) if rc == 1 else None
+
+    def set_hit_limits(self, max_hits=8, min_score=1):
+        self._check(self._L.seqalign_batch_set_hit_limits(self._h, max_hits, min_score))
+
+    def hits(self, i):
+        """all hits of pair i of the last MODE_HITS submit, in the reference's order"""
+        out = []
+        for h in range(self._L.seqalign_batch_hit_count(self._h, i)):
+            self._check(self._L.seqalign_batch_hit(self._h, i, h, self._res))
+            out.append(Alignment(self._res.contents))
+        return out
 
     def run_device(self, algo, d_seq_a, d_off_a, d_seq_b, d_off_b, n, d_score, d_xend=0, d_yend=0, stream=0):
         """Device pointers (ints); results stay on the device."""

@@ -166,6 +166,16 @@ static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32)
   return emu_shfl(v, emu::cur->lane ^ m);
 }
 static inline unsigned __ballot_sync(unsigned, int pred) { return emu::warp_ballot(pred); }
+template <class T>
+static inline unsigned __match_any_sync(unsigned, T v)
+{
+  unsigned m = 0;
+  for(int src = 0; src < 32; src++) {
+    T o = emu_shfl(v, src);
+    if(o == v) m |= 1u << src;
+  }
+  return m;
+}
 static inline int __any_sync(unsigned, int pred) { return emu::warp_ballot(pred) != 0; }
 static inline int __all_sync(unsigned, int pred) { return emu::warp_ballot(!pred) == 0; }
 static inline unsigned __activemask() { return 0xffffffffu; }

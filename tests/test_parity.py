@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import seqalign
-from seqalign import NW, SW, MODE_SCORE, MODE_ALIGN
+from seqalign import NW, SW, MODE_SCORE, MODE_ALIGN, MODE_HITS
 from helpers import (ROOT, SPECS, orc_batch_nw, orc_batch_sw, orc_fill, orc_from_scoring, orc_nw,
                      orc_sw_hits, ragged_batch, scoring_from_spec, synthetic_batch)
 
@@ -429,3 +429,61 @@ def test_pipelined_aligner(big):
         fs, fx, fy = f.result()
         assert np.array_equal(fs, es) and np.array_equal(fx, ex) and np.array_equal(fy, ey)
     pipe.close()
+
+
+def _hit_tuple(h):
+    return (h.score, h.result_a, h.result_b, h.pos_a, h.pos_b, h.len_a, h.len_b)
+
+
+@pytest.mark.parametrize("name", ["sw_cli", "nw_default", "linear_gap", "wild_n", "mutations", "blosum62", "pam30"])
+def test_multi_hit_on_device(engine, big, name):
+    """MODE_HITS: candidate sort + masked walks on the device vs the oracle's restatement of
+    smith_waterman_align2 + fetch loop (fresh mask), for several hit limits"""
+    n, maxlen = (150, 160) if big else (8, 36)
+    sa, sb = ragged_batch(4100 + _h(name) % 100, n, maxlen, maxlen, alphabet=_alphabet(name), min_len=1)
+    # self-similar pairs: many equal-score candidates and colliding walks (the lcs use case)
+    sa += [b"abcabcdabcdexabcd".upper() if name not in PROTEIN_SPECS else b"ARNDARNDCQARNDCQE", sa[0]]
+    sb += [sa[-2], sa[0]]
+    sc = scoring_from_spec(SPECS[name])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    for max_hits, min_score in ((1, 1), (5, 1), (40, 1), (6, 4)):
+        engine.set_hit_limits(max_hits, min_score)
+        engine.submit(SW, MODE_HITS, sa, sb)
+        assert "hits" in engine.last_kernel
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            nref, ref = orc_sw_hits(o, a, b, max_hits)
+            ref = [h for h in ref if h["score"] >= min_score]
+            got = engine.hits(i)
+            assert [_hit_tuple(h) for h in got] == [
+                (h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"], h["len_a"], h["len_b"]) for h in ref], (
+                name, max_hits, min_score, a, b)
+    engine.set_hit_limits(8, 1)
+
+
+def test_multi_hit_golden(engine):
+    """the reference's own hit lists (tests/golden/reference_vectors.json, up to six hits per pair)"""
+    engine.set_hit_limits(6, 1)
+    by_spec = {}
+    for c in GOLD["cases"]:
+        by_spec.setdefault(c["spec"], []).append(c)
+    checked = 0
+    for spec, cs in by_spec.items():
+        sc = scoring_from_spec(GOLD["specs"][spec])
+        engine.set_scoring(sc)
+        cs = [c for c in cs if len(c["a"]) <= 512 and len(c["a"]) > 0 and len(c["b"]) > 0]
+        try:
+            engine.submit(SW, MODE_HITS, [c["a"].encode() for c in cs], [c["b"].encode() for c in cs])
+        except seqalign.SeqAlignError as e:
+            assert e.code == seqalign.ERR_ARG   # scoring shapes only the general kernel handles
+            continue
+        for i, c in enumerate(cs):
+            got = [(h.score, h.result_a.decode(), h.result_b.decode(), h.pos_a, h.pos_b, h.len_a, h.len_b)
+                   for h in engine.hits(i)]
+            exp = [(e["score"], e["result_a"], e["result_b"], e["pos_a"], e["pos_b"], e["len_a"], e["len_b"])
+                   for e in c["sw"]]
+            assert got == exp, c
+            checked += 1
+    assert checked > 100
+    engine.set_hit_limits(8, 1)
