@@ -34,8 +34,8 @@
 namespace sa {
 
 constexpr int HITS_WARPS = 4;
-constexpr int HITS_BINS = 4096;          /* counters per warp (shared memory) */
-constexpr int HITS_DIGIT_BITS = 12;
+constexpr int HITS_BINS = 2048;          /* counters per warp (shared memory: 4 x 8 KB) */
+constexpr int HITS_DIGIT_BITS = 11;
 
 struct HitsArgs {
   const uint8_t *seq_a, *seq_b;
