@@ -21,6 +21,7 @@
 #include "sa_kernels.cuh"
 #include "sa_fast.cuh"
 #include "sa_hits.cuh"
+#include "sa_long.cuh"
 
 using namespace sa;
 
@@ -78,7 +79,7 @@ struct seqalign_batch {
   /* inputs on device */
   DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
   /* scratch */
-  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd;
+  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd, d_lbnd;
   /* score-mode results */
   DevBuf d_score, d_xend, d_yend, d_state;
   /* align-mode wave buffers */
@@ -386,6 +387,57 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
   return 0;
 }
 
+/* upload the profile tables of a specialised plan unless the device holds them */
+int upload_plan_tables(seqalign_batch *eng, const std::vector<int8_t> &tab8, const std::vector<int32_t> &tab32,
+                       int8_t **d_t8_out, int32_t **d_t32_out, cudaStream_t st)
+{
+  const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+  TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
+  int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
+  int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
+  if(tab32 != eng->dev_tab32 || tab8 != eng->dev_tab8) {
+    CU_TRY(cudaMemcpyAsync(d_t8, tab8.data(), nn, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_t32, tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
+    eng->dev_tab32 = tab32;
+    eng->dev_tab8 = tab8;
+  }
+  *d_t8_out = d_t8; *d_t32_out = d_t32;
+  return 0;
+}
+
+/* wide-pair kernel over the device-resident pairs [c0, c0+m) of db; results
+ * into d_score/d_xend/d_yend (absolute pair index); dir/dir_off (relative to
+ * c0) only for plans with traceback flags */
+int launch_long(seqalign_batch *eng, const LongPlan &plan, const ScoreParams &sp, const DevBatch &db,
+                size_t c0, size_t m, int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend,
+                uint8_t *d_dir, const int64_t *d_dir_off, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
+{
+  int8_t *d_t8 = nullptr;
+  int32_t *d_t32 = nullptr;
+  TRY(upload_plan_tables(eng, plan.tab8, plan.tab32, &d_t8, &d_t32, st));
+  const int grid = long_grid(plan, eng->num_sms, (int64_t)m);
+  LongArgs L;
+  memset(&L, 0, sizeof(L));
+  L.bnd_rows = (max_lb + 1 + 3) & ~(int64_t)3;
+  TRY(ensure_dev(eng, eng->d_lbnd, (size_t)grid * 2 * LONG_WARPS * (size_t)L.bnd_rows * sizeof(int2)));
+  L.bnd = (int2 *)eng->d_lbnd.p;
+  L.seq_a = db.a; L.seq_b = db.b; L.off_a = db.off_a + c0; L.off_b = db.off_b + c0;
+  L.npairs = (int64_t)m; L.sp = sp;
+  L.tab8 = d_t8; L.tab32 = d_t32;
+  L.lut = (const uint8_t *)eng->d_lut.p;
+  L.dir = d_dir; L.dir_off = d_dir_off;
+  L.score = d_score + c0;
+  L.xend = d_xend ? d_xend + c0 : nullptr;
+  L.yend = d_yend ? d_yend + c0 : nullptr;
+  CU_TRY(cudaEventRecord(ev0, st));
+  if(long_launch(plan, L, grid, st) != 0) return fail(eng, SEQALIGN_ERR_CUDA, "wide-pair kernel launch failed");
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(ev1, st));
+  eng->last_launches++;
+  eng->last_kernel = plan.name;
+  return 0;
+}
+
 int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta &bm,
               int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, FastPlan *plan_out = nullptr)
@@ -413,6 +465,9 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     if(plan_out) *plan_out = plan;
     return 0;
   }
+  LongPlan lplan;
+  if(eng->force_mode != 1 && long_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, false, &lplan))
+    return launch_long(eng, lplan, sp, db, 0, db.n, bm.max_lb, d_score, d_xend, d_yend, nullptr, nullptr, st, ev0, ev1);
   GenArgs X;
   memset(&X, 0, sizeof(X));
   X.score = d_score; X.xend = d_xend; X.yend = d_yend; X.state = nullptr;
@@ -450,6 +505,10 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   const bool fast_dir = eng->force_mode != 1 &&
                         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, false, &dplan, true);
   if(fast_dir && eng->force_mode == 2 && dplan.track == TRACK_TREE) dplan.track = TRACK_COLUMN;
+  /* wide pairs / free end gaps (NW): the strip-pipelined kernel, same flag bytes */
+  LongPlan lplan;
+  const bool long_dir = !fast_dir && eng->force_mode != 1 &&
+                        long_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, &lplan);
   if(algo == SEQALIGN_SW && !fast_dir) {
     TRY(run_score(eng, algo, db, bm, d_score, d_xend, d_yend, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -537,6 +596,9 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       CU_TRY(cudaGetLastError());
       CU_TRY(cudaEventRecord(eng->ev1, st));
       eng->last_launches++;
+    } else if(long_dir) {
+      TRY(launch_long(eng, lplan, sp, db, c0, m, bm.max_lb, d_score, d_xend, d_yend, (uint8_t *)eng->d_dir.p,
+                      (const int64_t *)eng->d_dir_off.p, st, eng->ev0, eng->ev1));
     } else {
       GenArgs X;
       memset(&X, 0, sizeof(X));
@@ -560,7 +622,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     int32_t *wk = (int32_t *)eng->d_walk.p;
     W.aln_start = wk; W.aln_len = wk + m; W.pos_a = wk + 2 * m; W.pos_b = wk + 3 * m;
     W.len_a = wk + 4 * m; W.len_b = wk + 5 * m; W.status = wk + 6 * m;
-    W.fmt = fast_dir ? 1 : 0;
+    W.fmt = (fast_dir || long_dir) ? 1 : 0;
     int wgrid = (int)((m + 127) / 128);
     if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
     SA_LAUNCH(walk_kernel, wgrid, 128, 0, st, W);
@@ -591,7 +653,8 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     c0 = c1;
   }
   eng->last_kernel = fast_dir ? (algo == SEQALIGN_SW ? "fast_sw_dir+walk" : "fast_nw_dir+walk")
-                              : (algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk");
+                     : long_dir ? "long_nw_dir+walk"
+                                : (algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk");
 
   /* scores to host */
   eng->score.resize(n); eng->xend.resize(n); eng->yend.resize(n);
@@ -953,7 +1016,7 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
                  &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
                  &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats, &eng->d_m16, &eng->d_keys0,
-                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec};
+                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd};
   for(DevBuf *b : d) b->release();
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};

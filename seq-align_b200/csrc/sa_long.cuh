@@ -1,0 +1,440 @@
+/*
+ * sa_long.cuh -- sm_100a kernels of the batch alignment engine (part 4):
+ * the specialised fill for WIDE pairs (len_a beyond one warp-wide strip, up
+ * to any length) and for Needleman-Wunsch with free end gaps.  This is the
+ * kernel behind BASELINE config 3 (NW 10k x 10k, --freestartgap
+ * --freeendgap, score + traceback).
+ *
+ * Same recurrence as alignment_fill_matrices (reference
+ * src/alignment.c:89-167) in the H' = max(M,GA,GB)+open form of sa_fast.cuh
+ * (one VIADDMNMX per matrix, H'+open on the FMA pipe, query profile in
+ * shared memory).  What is new here is the work shape:
+ *
+ *   * a pair is cut into column strips of 32*K columns; a strip is swept top
+ *     to bottom by one warp as an anti-diagonal wavefront (lane = K columns);
+ *   * the LONG_WARPS warps of a CTA take the strips of the CTA's pairs in one
+ *     continuous round-robin sequence (strip g of that sequence belongs to
+ *     warp g % LONG_WARPS) -- a systolic pipeline that does not drain between
+ *     pairs: while the last strips of one pair finish, the first strips of
+ *     the next pair are already running;
+ *   * the right edge of a strip (H', GB per row, 8 bytes) goes through a
+ *     per-CTA boundary buffer in global memory (L2 resident), the consumer
+ *     follows the producer's progress word in shared memory 32 rows at a
+ *     time;
+ *   * seq_b is streamed 32 rows at a time into a 64-entry ring per warp, so
+ *     no sequence has to fit shared memory.
+ *
+ * Free end gaps (scoring->no_end_gap_penalty, alignment.c:122-155): in the
+ * last column gap_a costs nothing, in the last row gap_b costs nothing.
+ * Only the strip holding column len_a and the row len_b of every strip run
+ * the "generic" row body that selects the penalties per column / per row;
+ * everything else runs the lean body.
+ *
+ * Traceback flags are the five equality bits of sa_fast.cuh (same byte
+ * layout, same walk): they are computed with the penalties that applied to
+ * the cell, so alignment_reverse_move's zeroed penalties in the last column /
+ * row (alignment.c:265-268) need nothing extra in the walk.
+ */
+#ifndef SA_LONG_CUH
+#define SA_LONG_CUH
+
+#include <vector>
+#include "sa_platform.h"
+#include "sa_flatten.h"
+#include "sa_kernels.cuh"
+#include "sa_fast.cuh"
+
+namespace sa {
+
+constexpr int LONG_WARPS = 8;
+constexpr int LONG_NEG = -(1 << 29);   /* "minus infinity" of the NW borders: far from INT_MIN, below every real value */
+
+struct LongArgs {
+  const uint8_t *seq_a, *seq_b;
+  const int64_t *off_a, *off_b;   /* of the launch's first pair */
+  int64_t npairs;
+  ScoreParams sp;
+  const int8_t *tab8;             /* [cb*(n+1) + ca] = sub - open, last column = padding code */
+  const int32_t *tab32;
+  const uint8_t *lut;
+  int2 *bnd;                      /* [grid][2][LONG_WARPS][bnd_rows] strip edges */
+  int64_t bnd_rows;
+  uint8_t *dir;                   /* DIR: traceback flag bytes, row-major per pair */
+  const int64_t *dir_off;
+  int32_t *score, *xend, *yend;   /* per pair of the launch */
+  int mul_one;
+};
+
+struct LongPlan {
+  int K = 0;
+  bool is_sw = false, prof32 = false, dir = false, noend = false;
+  const char *name = "";
+  std::vector<int8_t> tab8;
+  std::vector<int32_t> tab32;
+  size_t smem = 0;
+};
+
+/* one row of a lane's K columns.  GEN: penalties selected per column (bit j
+ * of lastmask = this is column len_a) and per row (lastrow), for free end
+ * gaps; otherwise the lean body. */
+template <int K, bool IS_SW, bool PROF32, bool DIR, bool GEN>
+__device__ __forceinline__ void long_row(int (&hp)[K], int (&ga)[K], int &hl, int &gb, int d,
+                                         const unsigned *w, unsigned *dw,
+                                         const int open, const int ext, const int mul_one,
+                                         const unsigned lastmask, const bool lastrow)
+{
+#pragma unroll
+  for(int j = 0; j < K; j++) {
+    const int sub = PROF32 ? (int)w[j] : sext_byte_dyn(w[j / 4], j & 3);
+    int eA = ext, eB = ext, hup = hp[j], hlf = hl;
+    if(GEN) {
+      if((lastmask >> j) & 1) { eA = 0; hup = hp[j] - open; }   /* gap_a is free in column len_a */
+      if(lastrow) { eB = 0; hlf = hl - open; }                   /* gap_b is free in row len_b */
+    }
+    int uge = 0, lge = 0;
+    if(DIR) {
+      uge = ga[j] * mul_one + eA;   /* GA_up + ext, GB_left + ext (IMAD, FMA pipe) */
+      lge = gb * mul_one + eB;
+    }
+    int m, h;
+    if(IS_SW) {
+      m = addmax(d, sub, 0);
+      ga[j] = addmax_relu(ga[j], eA, hup);
+      gb = addmax_relu(gb, eB, hlf);
+    } else {
+      /* no clamp at "min": every operand is a real value or LONG_NEG + one
+       * penalty, which never wins a max (see long_plan) */
+      m = d * mul_one + sub;
+      ga[j] = addmax(ga[j], eA, hup);
+      gb = addmax(gb, eB, hlf);
+    }
+    h = max3(m, ga[j], gb);
+    if(DIR) {
+      /* five "not equal" bits (sa_fast.cuh), a >= b holds for every pair */
+      const int f = imin(h - ga[j], 1) + 2 * imin(h - gb, 1) + 4 * imin(ga[j] - uge, 1) +
+                    8 * imin(gb - lge, 1) + 16 * imin(gb - hlf, 1);
+      dw[j / 4] += (unsigned)f << (8 * (j & 3));
+    }
+    d = hp[j];
+    hl = h * mul_one + open;
+    hp[j] = hl;
+  }
+}
+
+template <int K, bool IS_SW, bool PROF32, bool DIR, bool NOEND>
+__global__ void __launch_bounds__(LONG_WARPS * 32, 2)
+long_kernel(const LongArgs A)
+{
+  constexpr int W = LONG_WARPS;
+  constexpr int STRIP = 32 * K;
+  constexpr int KW = PROF32 ? K : (K + 3) / 4;
+  constexpr int KS = PROF32 ? prof32_stride(K) : KW;
+  constexpr int PSTRIDE = 32 * KS * 4;
+  static_assert(K % 4 == 0, "flag bytes are stored as whole words");
+
+  unsigned char *dsm = SA_DYN_SMEM();
+  const ScoreParams &sp = A.sp;
+  const int n = sp.ncodes, tw = n + 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+
+  /* shared: [lut 256][table][per warp: profile | b ring 64 | edge chunk 32 x int2] */
+  uint8_t *s_lut = dsm;
+  int8_t *s_tab8 = (int8_t *)(dsm + 256);
+  int32_t *s_tab32 = (int32_t *)(dsm + 256);
+  const int tab_bytes = ((PROF32 ? 4 : 1) * n * tw + 15) & ~15;
+  const int warp_bytes = n * PSTRIDE + 64 + 32 * 8;
+  unsigned char *wbase = dsm + 256 + tab_bytes + wib * warp_bytes;
+  unsigned char *s_prof = wbase;
+  uint8_t *s_bring = wbase + n * PSTRIDE;
+  int2 *s_chunk = (int2 *)(s_bring + 64);
+  __shared__ volatile unsigned long long s_progress[W];   /* producer warp -> (strip << 32 | rows published) */
+  __shared__ volatile unsigned s_fin[W];                   /* warp -> strips finished (index of the last one + 1) */
+
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+  if(PROF32) { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab32[i] = A.tab32[i]; }
+  else       { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab8[i] = A.tab8[i]; }
+  if(threadIdx.x < W) { s_progress[threadIdx.x] = 0; s_fin[threadIdx.x] = 0; }
+  __syncthreads();
+
+  const int open = sp.open, ext = sp.ext;
+  const int mul_one = A.mul_one;
+  int2 *cta_bnd = A.bnd + (int64_t)blockIdx.x * 2 * W * A.bnd_rows;
+  const unsigned *prow = (const unsigned *)s_prof + lane * KS;
+
+  unsigned gs_base = 0;   /* position of this pair's strip 0 in the CTA's strip sequence */
+  for(int64_t p = blockIdx.x; p < A.npairs; p += gridDim.x) {
+    const int64_t oa = A.off_a[p], ob = A.off_b[p];
+    const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
+    const uint8_t *pa = A.seq_a + oa, *pb = A.seq_b + ob;
+    const int nstrips = (la > 0 && lb > 0) ? (la + STRIP - 1) / STRIP : 0;
+    if(nstrips == 0) {
+      if(wib == 0 && lane == 0) {
+        int sc = 0;
+        if(!IS_SW && (la > 0 || lb > 0)) sc = sp.no_start ? 0 : addw(sp.gap_open, (la > 0 ? la : lb) * ext);
+        A.score[p] = sc;
+        if(A.xend) A.xend[p] = IS_SW ? 0 : la;
+        if(A.yend) A.yend[p] = IS_SW ? 0 : lb;
+      }
+      continue;
+    }
+    uint8_t *dirp = nullptr;
+    int dstride = 0;
+    if(DIR) { dirp = A.dir + A.dir_off[p]; dstride = (int)dir_stride(la); }
+
+    for(int s = (int)((wib + W - gs_base % W) % W); s < nstrips; s += W) {
+      const unsigned gs = gs_base + (unsigned)s;
+      const int x0 = s * STRIP;
+      const int xf = x0 + lane * K + 1;   /* my first column, 1-based */
+      const bool more = s + 1 < nstrips;
+      int2 *out_bnd = cta_bnd + (int64_t)(((gs / W) & 1) * W + wib) * A.bnd_rows;
+      const int2 *in_bnd = cta_bnd + (int64_t)((((gs - 1) / W) & 1) * W + (wib + W - 1) % W) * A.bnd_rows;
+      const unsigned long long in_base = (unsigned long long)(gs - 1) << 32;
+      /* my edge slot was last used two rounds ago; its reader must be done */
+      if(more && gs >= 2 * W)
+        while(s_fin[(wib + 1) % W] < gs - 2 * W + 2) SA_SPIN_HINT();
+
+      /* query profile of my K columns: row c holds sub'(a[x], c) */
+      unsigned lastmask = 0;
+      {
+        int acode[K];
+#pragma unroll
+        for(int j = 0; j < K; j++) {
+          acode[j] = (xf + j <= la) ? s_lut[pa[xf + j - 1]] : n;   /* n = padding code */
+          if(NOEND && xf + j == la) lastmask |= 1u << j;
+        }
+        for(int c = 0; c < n; c++) {
+          unsigned *dst = (unsigned *)(s_prof + c * PSTRIDE) + lane * KS;
+          if(PROF32) {
+            const int32_t *trow = s_tab32 + c * tw;
+#pragma unroll
+            for(int j = 0; j < K; j++) dst[j] = (unsigned)trow[acode[j]];
+          } else {
+            const int8_t *trow = s_tab8 + c * tw;
+#pragma unroll
+            for(int q = 0; q < KW; q++) {
+              unsigned word = 0;
+#pragma unroll
+              for(int b4 = 0; b4 < 4; b4++) {
+                const int j = 4 * q + b4;
+                if(j < K) word |= (unsigned)(uint8_t)trow[acode[j]] << (8 * b4);
+              }
+              dst[q] = word;
+            }
+          }
+        }
+      }
+
+      /* row 0 (alignment.c:47-69) in H' form */
+      int hp[K], ga[K];
+#pragma unroll
+      for(int j = 0; j < K; j++) {
+        if(IS_SW) { hp[j] = open; ga[j] = 0; }
+        else {
+          hp[j] = (sp.no_start ? 0 : sp.gap_open + (xf + j) * ext) + open;
+          ga[j] = LONG_NEG;
+        }
+      }
+      int hd;   /* H'(xf-1, y-1) */
+      if(IS_SW || xf == 1) hd = open;
+      else hd = (sp.no_start ? 0 : sp.gap_open + (xf - 1) * ext) + open;
+
+      int out_h = 0, out_gb = 0;
+      const int nsteps = lb + 31;
+      for(int st = 0; st < nsteps; st++) {
+        const int y = st - lane + 1;
+        const bool active = y >= 1 && y <= lb;
+
+        if((st & 31) == 0) {
+          /* next 32 rows: seq_b codes into the ring, the left strip's edge into the chunk */
+          __syncwarp();
+          const int row = st + 1 + lane;
+          if(row <= lb) s_bring[(row - 1) & 63] = s_lut[pb[row - 1]];
+          if(x0 > 0) {
+            const unsigned long long need = in_base + (unsigned long long)(st + 32 < lb ? st + 32 : lb);
+            while(s_progress[(wib + W - 1) % W] < need) SA_SPIN_HINT();
+            __threadfence_block();
+            int2 v = make_int2(0, 0);
+            if(row <= lb) {
+#if defined(__CUDA_ARCH__)
+              v = __ldcg(&in_bnd[row]);   /* L2: written by another warp of this CTA */
+#else
+              v = in_bnd[row];
+#endif
+            }
+            s_chunk[lane] = v;
+          }
+          __syncwarp();
+        }
+
+        /* left neighbour (xf-1, y) */
+        int hl = __shfl_up_sync(FULL, out_h, 1);
+        int gb = __shfl_up_sync(FULL, out_gb, 1);
+        if(lane == 0) {
+          if(x0 == 0) {
+            /* column 0 (alignment.c:55-56, 72-80) */
+            if(IS_SW) { hl = open; gb = 0; }
+            else { hl = (sp.no_start ? 0 : sp.gap_open + y * ext) + open; gb = LONG_NEG; }
+          } else {
+            const int2 v = s_chunk[st & 31];
+            hl = v.x; gb = v.y;
+          }
+        }
+        const int hl_in = hl;
+
+        if(active) {
+          const int c = s_bring[(y - 1) & 63];
+          const unsigned *pw = prow + c * (PSTRIDE / 4);
+          unsigned w[KW];
+          if(KW % 4 == 0 && KS % 4 == 0) {
+#pragma unroll
+            for(int q = 0; q < KW / 4; q++) {
+              const uint4 v = ((const uint4 *)pw)[q];
+              w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for(int q = 0; q < KW; q++) w[q] = pw[q];
+          }
+          unsigned dw[DIR ? K / 4 : 1];
+          if(DIR) {
+#pragma unroll
+            for(int q = 0; q < K / 4; q++) dw[q] = 0;
+          }
+          if(NOEND && (!more || y == lb))
+            long_row<K, IS_SW, PROF32, DIR, true>(hp, ga, hl, gb, hd, w, dw, open, ext, mul_one, lastmask, y == lb);
+          else
+            long_row<K, IS_SW, PROF32, DIR, false>(hp, ga, hl, gb, hd, w, dw, open, ext, mul_one, 0u, false);
+          if(DIR) {
+            /* the row stride is a multiple of 16: a lane's 16 bytes are inside or outside as a whole */
+            unsigned *drow = (unsigned *)(dirp + (int64_t)(y - 1) * dstride + (xf - 1));
+            if(K == 16) {
+              if(xf - 1 < dstride) *(uint4 *)drow = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+            } else {
+#pragma unroll
+              for(int q = 0; q < K / 4; q++)
+                if(xf - 1 + 4 * q < dstride) drow[q] = dw[q];
+            }
+          }
+          if(more && lane == 31) {
+            out_bnd[y] = make_int2(hl, gb);
+            if((y & 31) == 0 || y == lb) {
+              __threadfence_block();
+              s_progress[wib] = ((unsigned long long)gs << 32) | (unsigned long long)y;
+            }
+          }
+          out_h = hl;
+          out_gb = gb;
+          hd = hl_in;   /* next row's diagonal */
+        }
+      }
+
+      if(!more) {
+        /* the final cell (len_a, len_b) is in this strip */
+        const int jf = (la - 1 - x0) % K, lf = (la - 1 - x0) / K;
+        if(lane == lf) {
+          int v = 0;
+#pragma unroll
+          for(int j = 0; j < K; j++) if(j == jf) v = hp[j];
+          if(!IS_SW) {
+            A.score[p] = v - open;
+            if(A.xend) A.xend[p] = la;
+            if(A.yend) A.yend[p] = lb;
+          }
+        }
+      }
+      __syncwarp();
+      if(lane == 0) s_fin[wib] = gs + 1;
+    }
+    gs_base += (unsigned)nstrips;
+  }
+}
+
+/* ---- host side ---------------------------------------------------------- */
+
+inline size_t long_smem_bytes(int K, int ncodes, bool prof32)
+{
+  const int KS = prof32 ? prof32_stride(K) : (K + 3) / 4;
+  const size_t warp_bytes = (size_t)ncodes * 32 * KS * 4 + 64 + 32 * 8;
+  const size_t tab = (((size_t)(prof32 ? 4 : 1) * ncodes * (ncodes + 1)) + 15) & ~(size_t)15;
+  return 256 + tab + LONG_WARPS * warp_bytes;
+}
+
+/* can the wide-pair kernel take this batch?  Needleman-Wunsch with affine
+ * gaps (gap_open, gap_extend <= 0), optional free start / end gaps, no gap or
+ * mismatch restrictions, values far from the int32 limits. */
+inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
+                      int64_t max_la, int64_t max_lb, bool want_dir, LongPlan *plan)
+{
+  if(sp.is_sw) return false;
+  if(sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
+  if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
+  if(ft.any_unknown) return false;
+  for(size_t k = 0; k < ft.unknown.size(); k++) if(ft.unknown[k]) return false;
+  if(max_la < 1 || max_lb < 1 || max_la > (1 << 24) || max_lb > (1 << 24)) return false;
+  const long lo = (long)ft.min_sub - sp.open, hi = (long)ft.max_sub - sp.open;
+  if(lo < -(1L << 20) || hi > (1L << 20)) return false;
+  /* every real value stays inside (-2^28, 2^28): no clamp at the reference's
+   * "min" (alignment.c:41) can ever bind, and LONG_NEG + penalty never wins */
+  const long longest = (long)(max_la > max_lb ? max_la : max_lb);
+  const long step = -(long)sp.open - (long)sp.ext - (ft.min_sub < 0 ? ft.min_sub : 0) + (ft.max_sub > 0 ? ft.max_sub : 0) + 1;
+  if(step > (1L << 20) || 2 * longest * step + 2 * labs((long)sp.gap_open) > (1L << 28)) return false;
+  const long room = labs((long)s->min_penalty);
+  if(-(long)sp.open > room || -(long)sp.ext > room || -(long)ft.min_sub > room) return false;
+
+  const int K = 16, n = ft.ncodes;
+  bool prof32 = (size_t)n * 32 * prof32_stride(K) * 4 <= 13 * 1024;
+  const int padsub = ft.min_sub < -1 ? ft.min_sub : -1;
+  const bool fits8 = lo >= -127 && hi <= 127 && (long)padsub - sp.open >= -127 && (long)padsub - sp.open <= 127;
+  if(!prof32 && !fits8) return false;
+  plan->K = K; plan->is_sw = false; plan->prof32 = prof32; plan->dir = want_dir; plan->noend = sp.no_end != 0;
+  plan->smem = long_smem_bytes(K, n, prof32);
+  if(plan->smem > 100 * 1024) return false;
+  const int tw = n + 1;
+  plan->tab8.assign(((size_t)n * tw + 15) & ~(size_t)15, 0);
+  plan->tab32.assign((size_t)n * tw + 4, 0);
+  for(int cb = 0; cb < n; cb++)
+    for(int ca = 0; ca < tw; ca++) {
+      const int v = (ca < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
+      plan->tab32[(size_t)cb * tw + ca] = v;
+      if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
+    }
+  plan->name = want_dir ? "long_nw_dir" : "long_nw_score";
+  return true;
+}
+
+template <int K, bool P32, bool DIR, bool NOEND>
+int long_launch_one(const LongPlan &plan, const LongArgs &L, int grid, cudaStream_t st)
+{
+  void (*kfn)(const LongArgs) = long_kernel<K, false, P32, DIR, NOEND>;
+  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
+  SA_LAUNCH(kfn, grid, LONG_WARPS * 32, plan.smem, st, L);
+  return 0;
+}
+
+/* CTAs resident at once for this plan (the grid of a launch; the caller
+ * sizes the boundary buffer with it) */
+inline int long_grid(const LongPlan &plan, int num_sms, int64_t npairs)
+{
+  int64_t g = (int64_t)num_sms * 2;
+  if(plan.smem > 110 * 1024) g = num_sms;
+  if(g > npairs) g = npairs;
+  return g < 1 ? 1 : (int)g;
+}
+
+inline int long_launch(const LongPlan &plan, LongArgs L, int grid, cudaStream_t st)
+{
+  L.mul_one = 1;
+#define SA_LONG_CASE(P32_, DIR_, NOEND_)                                          \
+  if(plan.prof32 == P32_ && plan.dir == DIR_ && plan.noend == NOEND_)             \
+    return long_launch_one<16, P32_, DIR_, NOEND_>(plan, L, grid, st)
+  SA_LONG_CASE(true, true, true);   SA_LONG_CASE(true, true, false);
+  SA_LONG_CASE(true, false, true);  SA_LONG_CASE(true, false, false);
+  SA_LONG_CASE(false, true, true);  SA_LONG_CASE(false, true, false);
+  SA_LONG_CASE(false, false, true); SA_LONG_CASE(false, false, false);
+#undef SA_LONG_CASE
+  return -1;
+}
+
+} // namespace sa
+
+#endif

@@ -148,6 +148,45 @@ def test_wide_pairs_cooperative(engine, big, shape):
         assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb)
 
 
+@pytest.mark.parametrize("case", ["ragged_wide", "many_strips", "short_free_ends", "protein_wide"])
+def test_wide_pairs_strip_pipeline(engine, big, case):
+    """NW beyond one strip / with free end gaps: the strip-pipelined kernel
+    (sa_long.cuh).  Ragged widths (strips of several pairs interleave in a
+    CTA), more than 2 x LONG_WARPS strips (edge slots are reused), the
+    last-column / last-row rules of free end gaps; scores and strings."""
+    alphabet = b"ACGT"
+    names = ("free_ends", "nw_default", "free_end", "free_start", "linear_gap")
+    if case == "ragged_wide":
+        sa, sb = ragged_batch(8, 40 if big else 8, 3000 if big else 1300, 700 if big else 24, min_len=1)
+    elif case == "many_strips":
+        sa, sb = ragged_batch(9, 6 if big else 3, 512 * 19, 300 if big else 12, min_len=5)
+        sa[0] = (sa[0] * 40)[:512 * 18 + 7]
+    elif case == "short_free_ends":
+        sa, sb = ragged_batch(7, 300 if big else 24, 200 if big else 60, 200 if big else 60)
+        names = ("free_ends", "free_end")
+    else:
+        alphabet = b"ARNDCQEGHILKMFPSTWYVBZX"
+        sa, sb = ragged_batch(10, 20 if big else 5, 2000 if big else 700, 500 if big else 30, alphabet=alphabet, min_len=1)
+        names = ("blosum62", "pam30")
+    a, oa = seqalign.pack(sa)
+    b, ob = seqalign.pack(sb)
+    engine.force_general(0)
+    for name in names:
+        sc = scoring_from_spec(SPECS[name])
+        o = orc_from_scoring(sc)
+        engine.set_scoring(sc)
+        engine.submit_packed(NW, MODE_SCORE, a, oa, b, ob)
+        assert engine.last_kernel == "long_nw_score", engine.last_kernel
+        es = orc_batch_nw(o, a, oa, b, ob)
+        s = engine.scores()
+        assert np.array_equal(s, es), (name, np.nonzero(s != es)[0][:8])
+        engine.submit_packed(NW, MODE_ALIGN, a, oa, b, ob)
+        assert engine.last_kernel == "long_nw_dir+walk", engine.last_kernel
+        assert np.array_equal(engine.scores(), es)
+        for i in range(len(sa)):
+            _check_alignment(engine.alignment(i), NW, o, sa[i], sb[i])
+
+
 def test_empty_inputs(engine):
     sc = scoring_from_spec(SPECS["nw_default"])
     engine.set_scoring(sc)
