@@ -157,6 +157,7 @@ void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b);
  * engine's stream) and launch count of the DP kernels of the last
  * submit/run, and the name of the kernel variant that ran. */
 double seqalign_batch_last_kernel_ms(const seqalign_batch_t *eng);
+double seqalign_batch_last_walk_ms(const seqalign_batch_t *eng);   /* traceback walk kernels of an align-mode submit */
 int seqalign_batch_last_launches(const seqalign_batch_t *eng);
 const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng);
 

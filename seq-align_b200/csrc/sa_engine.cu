@@ -104,7 +104,7 @@ struct seqalign_batch {
   std::vector<char> hit_a, hit_b;
   int32_t hit_max_used = 0;
 
-  double last_ms = 0;
+  double last_ms = 0, last_walk_ms = 0;
   int last_launches = 0;
   const char *last_kernel = "none";
 };
@@ -497,6 +497,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   int32_t *d_yend = (int32_t *)eng->d_yend.p, *d_state = (int32_t *)eng->d_state.p;
 
   eng->last_ms = 0;
+  eng->last_walk_ms = 0;
   float ms = 0;
   /* specialised fill (score + end cell + traceback flags in one pass) when the
    * scoring shape allows, else the general kernel (SW: best cell first, its
@@ -535,7 +536,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   int64_t budget = (int64_t)(free_b / 2);
   const char *env = getenv("SEQALIGN_DIR_BUDGET");
   if(env) budget = atoll(env);
-  if(budget > ((int64_t)48 << 30)) budget = (int64_t)48 << 30;
+  if(budget > ((int64_t)64 << 30)) budget = (int64_t)64 << 30;
 
   eng->res_off.assign(n + 1, 0);
   for(size_t i = 0; i < n; i++)
@@ -560,6 +561,17 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       out_off.push_back(eng->res_off[c1] - eng->res_off[c0]);
       dbytes += need;
       c1++;
+    }
+    if(long_dir && c1 < n) {
+      /* the strip pipeline streams pairs through its resident CTAs: a wave of
+       * a whole number of pairs per CTA leaves no CTA idle at the end */
+      const size_t g = (size_t)long_grid(lplan, eng->num_sms, (int64_t)n);
+      if(c1 - c0 > g) {
+        c1 = c0 + (c1 - c0) / g * g;
+        dir_off.resize(c1 - c0); out_off.resize(c1 - c0);
+        const int64_t la = h_off_a[c1] - h_off_a[c1 - 1], lb = h_off_b[c1] - h_off_b[c1 - 1];
+        dbytes = dir_off.back() + dir_bytes(la, lb);
+      }
     }
     const size_t m = c1 - c0;
     const int64_t obytes = eng->res_off[c1] - eng->res_off[c0];
@@ -623,10 +635,21 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     W.aln_start = wk; W.aln_len = wk + m; W.pos_a = wk + 2 * m; W.pos_b = wk + 3 * m;
     W.len_a = wk + 4 * m; W.len_b = wk + 5 * m; W.status = wk + 6 * m;
     W.fmt = (fast_dir || long_dir) ? 1 : 0;
-    int wgrid = (int)((m + 127) / 128);
-    if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
-    SA_LAUNCH(walk_kernel, wgrid, 128, 0, st, W);
+    /* long walks: a warp per pair with a shared-memory window over the flag
+     * bytes; many short ones: a thread per pair */
+    const char *wenv = getenv("SEQALIGN_WALK");
+    const bool tiled = wenv ? strcmp(wenv, "tiled") == 0 : bm.cells / (int64_t)n >= (1 << 20);
+    if(tiled) {
+      int wgrid = (int)((m + WT_WARPS - 1) / WT_WARPS);
+      if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;
+      SA_LAUNCH(walk_tiled_kernel, wgrid, WT_WARPS * 32, 0, st, W);
+    } else {
+      int wgrid = (int)((m + 127) / 128);
+      if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
+      SA_LAUNCH(walk_kernel, wgrid, 128, 0, st, W);
+    }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(eng->ev_k1[0], st));
     eng->last_launches++;
 
     CU_TRY(cudaMemcpyAsync(eng->h_walk.p, eng->d_walk.p, m * 4 * 7, cudaMemcpyDeviceToHost, st));
@@ -637,6 +660,8 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
     eng->last_ms += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev1, eng->ev_k1[0]));
+    eng->last_walk_ms += ms;
 
     const int32_t *hw = (const int32_t *)eng->h_walk.p;
     memcpy(&eng->aln_start[c0], hw, m * 4);
@@ -1338,6 +1363,7 @@ void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b)
 }
 
 double seqalign_batch_last_kernel_ms(const seqalign_batch_t *eng) { return eng ? eng->last_ms : 0; }
+double seqalign_batch_last_walk_ms(const seqalign_batch_t *eng) { return eng ? eng->last_walk_ms : 0; }
 int seqalign_batch_last_launches(const seqalign_batch_t *eng) { return eng ? eng->last_launches : 0; }
 const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng) { return eng ? eng->last_kernel : "none"; }
 

@@ -577,104 +577,162 @@ struct WalkArgs {
   int fmt;                     /* 0: resolved 2-bit codes (general kernel), 1: equality flags (fast kernel) */
 };
 
-__global__ void __launch_bounds__(128)
-walk_kernel(const WalkArgs A)
+/* the walk of one pair; get(cx, cy) returns the flag byte of cell (cx+1, cy+1);
+ * only the `writer` thread stores results (the tiled kernel runs the walk
+ * warp-uniformly so that all lanes can refill the window together) */
+template <class Get>
+__device__ __forceinline__ void walk_pair(const WalkArgs &A, const int64_t r, Get get, const bool writer)
 {
   const ScoreParams &sp = A.sp;
-  for(int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.npairs;
-      r += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = A.pair0 + r;
-    const int64_t oa = A.off_a[p], ob = A.off_b[p];
-    const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
-    const uint8_t *a = A.seq_a + oa, *b = A.seq_b + ob;
-    const uint8_t *dirp = A.dir + A.dir_off[r];
-    const int64_t dstride = dir_stride(la);
-    uint8_t *ra = A.out_a + A.out_off[r], *rb = A.out_b + A.out_off[r];
-    const int cap = la + lb;
-    int n = 0, status = WALK_OK;
-    int x, y, st;
+  const int64_t p = A.pair0 + r;
+  const int64_t oa = A.off_a[p], ob = A.off_b[p];
+  const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
+  const uint8_t *a = A.seq_a + oa, *b = A.seq_b + ob;
+  uint8_t *ra = A.out_a + A.out_off[r], *rb = A.out_b + A.out_off[r];
+  const int cap = la + lb;
+  int n = 0, status = WALK_OK;
+  int x, y, st;
 
-    /* predecessor state when leaving cell (x,y) in state st */
-    auto next_state = [&](int x, int y, int st) -> int {
-      const unsigned f = dirp[(int64_t)(y - 1) * dstride + (x - 1)];
-      if(A.fmt == 0) return (f >> (2 * st)) & 3;
-      /* equality flags (bit clear = equal), resolved in the order GAP_A, GAP_B,
-       * MATCH of alignment.c:311-327.  A predecessor on the border ends the
-       * walk whatever its state, so it needs no flags. */
-      if(st == ST_M) {
-        if(x == 1 || y == 1) return ST_M;
-        const unsigned g = dirp[(int64_t)(y - 2) * dstride + (x - 2)];
-        return !(g & 1) ? ST_GA : !(g & 2) ? ST_GB : ST_M;
-      }
-      if(st == ST_GA) {
-        if(!(f & 4)) return ST_GA;
-        if(y == 1) return ST_M;
-        const unsigned g = dirp[(int64_t)(y - 2) * dstride + (x - 1)];
-        return !(g & 2) ? ST_GB : ST_M;
-      }
-      if(x == 1) return ST_M;
-      const unsigned g = dirp[(int64_t)(y - 1) * dstride + (x - 2)];
-      if(!(g & 1) && !(f & 16)) return ST_GA;
-      return !(f & 8) ? ST_GB : ST_M;
-    };
-
-    if(!sp.is_sw) {
-      x = la; y = lb;
-      if(A.fmt == 0) st = A.state[p];
-      else if(la > 0 && lb > 0) {
-        /* end state GAP_A over GAP_B over MATCH on ties (needleman_wunsch.c:53-66) */
-        const unsigned f = dirp[(int64_t)(lb - 1) * dstride + (la - 1)];
-        st = !(f & 1) ? ST_GA : !(f & 2) ? ST_GB : ST_M;
-      } else st = ST_M;
-      while(x > 0 && y > 0) {
-        n++;
-        ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
-        rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
-        const int code = next_state(x, y, st);
-        if(code == ST_FAIL) { status = WALK_FAIL; break; }
-        if(st == ST_M) { x--; y--; } else if(st == ST_GA) y--; else x--;
-        st = code;
-      }
-      if(status == WALK_OK) {
-        for(; y > 0; y--) { n++; ra[cap - n] = '-'; rb[cap - n] = b[y - 1]; }
-        for(; x > 0; x--) { n++; ra[cap - n] = a[x - 1]; rb[cap - n] = '-'; }
-      }
-      A.pos_a[r] = 0; A.pos_b[r] = 0; A.len_a[r] = la; A.len_b[r] = lb;
-    } else {
-      const int xe = A.xend[p], ye = A.yend[p];
-      int cs = A.score[p];
-      x = xe; y = ye; st = ST_M;
-      if(cs <= 0) status = WALK_NOHIT;
-      while(cs > 0) {
-        n++;
-        ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
-        rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
-        const int code = next_state(x, y, st);
-        if(code == ST_FAIL) { status = WALK_FAIL; break; }
-        /* the penalty the reference subtracts implicitly: it continues
-         * with the predecessor's stored value (alignment.c:311-327) */
-        int pen;
-        if(st == ST_M) {
-          pen = A.sub[A.lut[b[y - 1]] * sp.ncodes + A.lut[a[x - 1]]];
-          x--; y--;
-        } else if(st == ST_GA) {
-          const bool fr = sp.no_end && x == la;
-          pen = fr ? 0 : (code == ST_GA ? sp.ext : sp.open);
-          y--;
-        } else {
-          const bool fr = sp.no_end && y == lb;
-          pen = fr ? 0 : (code == ST_GB ? sp.ext : sp.open);
-          x--;
-        }
-        cs = (int)((unsigned)cs - (unsigned)pen);
-        if(x == 0 || y == 0) cs = 0;   /* the SW borders are all zero: the hit starts here */
-        st = code;
-      }
-      A.pos_a[r] = x; A.pos_b[r] = y; A.len_a[r] = xe - x; A.len_b[r] = ye - y;
+  /* predecessor state when leaving cell (x,y) in state st */
+  auto next_state = [&](int x, int y, int st) -> int {
+    const unsigned f = get(x - 1, y - 1);
+    if(A.fmt == 0) return (f >> (2 * st)) & 3;
+    /* equality flags (bit clear = equal), resolved in the order GAP_A, GAP_B,
+     * MATCH of alignment.c:311-327.  A predecessor on the border ends the
+     * walk whatever its state, so it needs no flags. */
+    if(st == ST_M) {
+      if(x == 1 || y == 1) return ST_M;
+      const unsigned g = get(x - 2, y - 2);
+      return !(g & 1) ? ST_GA : !(g & 2) ? ST_GB : ST_M;
     }
+    if(st == ST_GA) {
+      if(!(f & 4)) return ST_GA;
+      if(y == 1) return ST_M;
+      const unsigned g = get(x - 1, y - 2);
+      return !(g & 2) ? ST_GB : ST_M;
+    }
+    if(x == 1) return ST_M;
+    const unsigned g = get(x - 2, y - 1);
+    if(!(g & 1) && !(f & 16)) return ST_GA;
+    return !(f & 8) ? ST_GB : ST_M;
+  };
+
+  if(!sp.is_sw) {
+    x = la; y = lb;
+    if(A.fmt == 0) st = A.state[p];
+    else if(la > 0 && lb > 0) {
+      /* end state GAP_A over GAP_B over MATCH on ties (needleman_wunsch.c:53-66) */
+      const unsigned f = get(la - 1, lb - 1);
+      st = !(f & 1) ? ST_GA : !(f & 2) ? ST_GB : ST_M;
+    } else st = ST_M;
+    while(x > 0 && y > 0) {
+      n++;
+      if(writer) {
+        ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
+        rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
+      }
+      const int code = next_state(x, y, st);
+      if(code == ST_FAIL) { status = WALK_FAIL; break; }
+      if(st == ST_M) { x--; y--; } else if(st == ST_GA) y--; else x--;
+      st = code;
+    }
+    if(status == WALK_OK) {
+      for(; y > 0; y--) { n++; if(writer) { ra[cap - n] = '-'; rb[cap - n] = b[y - 1]; } }
+      for(; x > 0; x--) { n++; if(writer) { ra[cap - n] = a[x - 1]; rb[cap - n] = '-'; } }
+    }
+    if(writer) { A.pos_a[r] = 0; A.pos_b[r] = 0; A.len_a[r] = la; A.len_b[r] = lb; }
+  } else {
+    const int xe = A.xend[p], ye = A.yend[p];
+    int cs = A.score[p];
+    x = xe; y = ye; st = ST_M;
+    if(cs <= 0) status = WALK_NOHIT;
+    while(cs > 0) {
+      n++;
+      if(writer) {
+        ra[cap - n] = st == ST_GA ? '-' : a[x - 1];
+        rb[cap - n] = st == ST_GB ? '-' : b[y - 1];
+      }
+      const int code = next_state(x, y, st);
+      if(code == ST_FAIL) { status = WALK_FAIL; break; }
+      /* the penalty the reference subtracts implicitly: it continues
+       * with the predecessor's stored value (alignment.c:311-327) */
+      int pen;
+      if(st == ST_M) {
+        pen = A.sub[A.lut[b[y - 1]] * sp.ncodes + A.lut[a[x - 1]]];
+        x--; y--;
+      } else if(st == ST_GA) {
+        const bool fr = sp.no_end && x == la;
+        pen = fr ? 0 : (code == ST_GA ? sp.ext : sp.open);
+        y--;
+      } else {
+        const bool fr = sp.no_end && y == lb;
+        pen = fr ? 0 : (code == ST_GB ? sp.ext : sp.open);
+        x--;
+      }
+      cs = (int)((unsigned)cs - (unsigned)pen);
+      if(x == 0 || y == 0) cs = 0;   /* the SW borders are all zero: the hit starts here */
+      st = code;
+    }
+    if(writer) { A.pos_a[r] = x; A.pos_b[r] = y; A.len_a[r] = xe - x; A.len_b[r] = ye - y; }
+  }
+  if(writer) {
     A.aln_start[r] = cap - n;
     A.aln_len[r] = n;
     A.status[r] = status;
+  }
+}
+
+/* one thread per pair, flag bytes read straight from global memory: many
+ * small pairs */
+__global__ void __launch_bounds__(128)
+walk_kernel(const WalkArgs A)
+{
+  for(int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.npairs;
+      r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = A.pair0 + r;
+    const uint8_t *dirp = A.dir + A.dir_off[r];
+    const int64_t dstride = dir_stride((int)(A.off_a[p + 1] - A.off_a[p]));
+    walk_pair(A, r, [&](int cx, int cy) -> unsigned { return dirp[(int64_t)cy * dstride + cx]; }, true);
+  }
+}
+
+/* one warp per pair, for long walks: the flag bytes up and left of the
+ * current cell are fetched a 32 x 128 byte window at a time into shared
+ * memory by all lanes (one round trip to HBM per ~32 steps instead of two
+ * dependent ones per step); the walk itself runs warp-uniformly */
+constexpr int WT_ROWS = 32, WT_COLS = 128, WT_WARPS = 4;
+
+__global__ void __launch_bounds__(WT_WARPS * 32)
+walk_tiled_kernel(const WalkArgs A)
+{
+  __shared__ uint4 s_win[WT_WARPS][WT_ROWS * WT_COLS / 16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint8_t *win = (uint8_t *)s_win[wib];
+  for(int64_t r = (int64_t)blockIdx.x * WT_WARPS + wib; r < A.npairs; r += (int64_t)gridDim.x * WT_WARPS) {
+    const int64_t p = A.pair0 + r;
+    const uint8_t *dirp = A.dir + A.dir_off[r];
+    const int64_t dstride = dir_stride((int)(A.off_a[p + 1] - A.off_a[p]));
+    int r0 = 0, c0 = 0, r1 = -1, c1 = -1;   /* window = rows [r0, r1] x columns [c0, c1] */
+    auto get = [&](int cx, int cy) -> unsigned {
+      if(cx < c0 || cx > c1 || cy < r0 || cy > r1) {
+        /* refill with (cx, cy) in the bottom-right corner block: the walk only moves up and left */
+        __syncwarp();
+        r1 = cy; r0 = cy - (WT_ROWS - 1); if(r0 < 0) r0 = 0;
+        c0 = ((cx >> 4) << 4) + 16 - WT_COLS; if(c0 < 0) c0 = 0;
+        c1 = c0 + WT_COLS - 1;
+#pragma unroll
+        for(int i = 0; i < WT_ROWS / 4; i++) {
+          const int row = r0 + i * 4 + (lane >> 3), col = c0 + 16 * (lane & 7);
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if(row <= r1 && col < dstride) v = *(const uint4 *)(dirp + (int64_t)row * dstride + col);
+          *(uint4 *)(win + (i * 4 + (lane >> 3)) * WT_COLS + 16 * (lane & 7)) = v;
+        }
+        __syncwarp();
+      }
+      return win[(cy - r0) * WT_COLS + (cx - c0)];
+    };
+    walk_pair(A, r, get, lane == 0);
+    __syncwarp();
   }
 }
 

@@ -136,6 +136,8 @@ def load():
     L.seqalign_batch_unknown_pair.argtypes = [vp, vp, vp]
     L.seqalign_batch_last_kernel_ms.restype = ctypes.c_double
     L.seqalign_batch_last_kernel_ms.argtypes = [vp]
+    L.seqalign_batch_last_walk_ms.restype = ctypes.c_double
+    L.seqalign_batch_last_walk_ms.argtypes = [vp]
     L.seqalign_batch_last_launches.restype = ctypes.c_int
     L.seqalign_batch_last_launches.argtypes = [vp]
     L.seqalign_batch_last_kernel.restype = ctypes.c_char_p
@@ -380,6 +382,10 @@ class BatchAligner:
     @property
     def last_kernel_ms(self):
         return self._L.seqalign_batch_last_kernel_ms(self._h)
+
+    @property
+    def last_walk_ms(self):
+        return self._L.seqalign_batch_last_walk_ms(self._h)
 
     @property
     def last_launches(self):

@@ -17,7 +17,7 @@ for rep in range(2):
 s_score = eng.scores().copy()
 for rep in range(2):
     t = time.time(); eng.submit_packed(seqalign.NW, seqalign.MODE_ALIGN, A, OA, B, OB); dt = time.time() - t
-    print(json.dumps(dict(what="NW align %dx%d x%d" % (L, L, n), kernel=eng.last_kernel, kernel_ms=eng.last_kernel_ms, gcups_kernel=cells / eng.last_kernel_ms / 1e6, e2e_s=dt)), flush=True)
+    print(json.dumps(dict(what="NW align %dx%d x%d" % (L, L, n), kernel=eng.last_kernel, kernel_ms=eng.last_kernel_ms, walk_ms=eng.last_walk_ms, gcups_kernel=cells / eng.last_kernel_ms / 1e6, gcups_e2e=cells / dt / 1e9, e2e_s=dt)), flush=True)
 assert (eng.scores() == s_score).all()
 # parity of two pairs against the oracle (score + strings); the oracle needs 3 x 400 MB per pair
 for i in range(2):

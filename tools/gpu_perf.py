@@ -45,13 +45,24 @@ for L in (64, 100, 128, 250, 300, 512):
     n = int(2.0e9 / (L * L))
     a, oa, b, ob = synthetic_batch(20 + L, n, L, L)
     timeit("dna%d score-only" % L, "sw_cli", seqalign.SW, 3, a, oa, b, ob, n * L * L)
-# align mode
-sc = specs["sw_cli"](); eng.set_scoring(sc)
+# align mode (score + end cell + traceback strings on the host)
+def align(tag, name, algo, a, oa, b, ob, cells, walk=None):
+    if walk: os.environ["SEQALIGN_WALK"] = walk
+    else: os.environ.pop("SEQALIGN_WALK", None)
+    sc = specs[name](); eng.set_scoring(sc)
+    best = None
+    for r in range(2):
+        t = time.time(); eng.submit_packed(algo, seqalign.MODE_ALIGN, a, oa, b, ob); dt = time.time() - t
+        if best is None or dt < best[0]: best = (dt, eng.last_kernel_ms, eng.last_walk_ms)
+    res = dict(tag=tag, scoring=name, kernel=eng.last_kernel, kernel_ms=round(best[1], 3), walk_ms=round(best[2], 3),
+               gcups_kernel=round(cells / best[1] / 1e6, 1), e2e_ms=round(best[0] * 1e3, 2), gcups_e2e=round(cells / best[0] / 1e9, 1))
+    print(json.dumps(res), flush=True)
+    rows.append(res)
 n = 20000
-t = time.time(); eng.submit_packed(seqalign.SW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); dt = time.time() - t
-print(json.dumps(dict(tag="dna150 SW align 20k", e2e_ms=dt * 1e3, kernel_ms=eng.last_kernel_ms, gcups_kernel=n * 22500 / eng.last_kernel_ms / 1e6, kernel=eng.last_kernel)))
-sc = specs["nw_default"](); eng.set_scoring(sc)
-t = time.time(); eng.submit_packed(seqalign.NW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); dt = time.time() - t
-print(json.dumps(dict(tag="dna150 NW align 20k", e2e_ms=dt * 1e3, kernel_ms=eng.last_kernel_ms, gcups_kernel=n * 22500 / eng.last_kernel_ms / 1e6, kernel=eng.last_kernel)))
+align("dna150 SW align 20k", "sw_cli", seqalign.SW, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1], n * 22500.0)
+align("dna150 NW align 20k", "nw_default", seqalign.NW, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1], n * 22500.0)
+align("dna150 NW align 20k tiled walk", "nw_default", seqalign.NW, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1], n * 22500.0, walk="tiled")
+align("prot400 SW align 50k (config 4), thread walk", "blosum62", seqalign.SW, PA, POA, PB, POB, c4, walk="thread")
+align("prot400 SW align 50k (config 4), tiled walk", "blosum62", seqalign.SW, PA, POA, PB, POB, c4, walk="tiled")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gpu_perf.json"), "w"), indent=1)
