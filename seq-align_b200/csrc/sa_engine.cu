@@ -48,9 +48,10 @@ struct seqalign_batch {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t scan_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   enum { MAX_CHUNKS = 8 };
-  cudaEvent_t ev_copy[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {};
+  cudaEvent_t ev_copy[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {}, ev_scan[MAX_CHUNKS] = {};
   std::string err;
   char unk_a = 0, unk_b = 0;
 
@@ -192,28 +193,30 @@ struct BatchMeta {
  * scan_collect waits for it and decodes the meta block. */
 int scan_launch(seqalign_batch *eng, const uint8_t *d_a, const uint8_t *d_b,
                 const int64_t *d_off_a, const int64_t *d_off_b, size_t n,
-                int64_t approx_bytes, cudaStream_t st)
+                int64_t approx_bytes, cudaStream_t st, int slot = 0)
 {
-  TRY(ensure_dev(eng, eng->d_meta, META_WORDS * 8));
-  TRY(ensure_pin(eng, eng->h_meta, META_WORDS * 8));
-  CU_TRY(cudaMemsetAsync(eng->d_meta.p, 0, META_WORDS * 8, st));
-  CU_TRY(cudaMemsetAsync((unsigned long long *)eng->d_meta.p + META_MIN_LA, 0xff, 16, st));
+  /* one meta block per chunk slot, so several scans can be in flight */
+  TRY(ensure_dev(eng, eng->d_meta, seqalign_batch::MAX_CHUNKS * META_WORDS * 8));
+  TRY(ensure_pin(eng, eng->h_meta, seqalign_batch::MAX_CHUNKS * META_WORDS * 8));
+  unsigned long long *dm = (unsigned long long *)eng->d_meta.p + (size_t)slot * META_WORDS;
+  CU_TRY(cudaMemsetAsync(dm, 0, META_WORDS * 8, st));
+  CU_TRY(cudaMemsetAsync(dm + META_MIN_LA, 0xff, 16, st));
   int64_t work = approx_bytes / 16 + (int64_t)n;
   int grid = (int)((work + 255) / 256);
   if(grid > eng->num_sms * 8) grid = eng->num_sms * 8;
   if(grid < 1) grid = 1;
-  SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, d_b, d_off_a, d_off_b,
-            (int64_t)n, (unsigned long long *)eng->d_meta.p);
+  SA_LAUNCH(scan_kernel, grid, 256, 0, st, d_a, d_b, d_off_a, d_off_b, (int64_t)n, dm);
   CU_TRY(cudaGetLastError());
   eng->last_launches++;
-  CU_TRY(cudaMemcpyAsync(eng->h_meta.p, eng->d_meta.p, META_WORDS * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync((uint64_t *)eng->h_meta.p + (size_t)slot * META_WORDS, dm, META_WORDS * 8,
+                         cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
-int scan_collect(seqalign_batch *eng, size_t n, cudaStream_t st, BatchMeta *bm)
+/* decode the meta block of a finished scan */
+void scan_decode(const seqalign_batch *eng, size_t n, int slot, BatchMeta *bm)
 {
-  CU_TRY(cudaStreamSynchronize(st));
-  const uint64_t *m = (const uint64_t *)eng->h_meta.p;
+  const uint64_t *m = (const uint64_t *)eng->h_meta.p + (size_t)slot * META_WORDS;
   for(int i = 0; i < 4; i++) { bm->pres_a[i] = m[META_PRES_A + i]; bm->pres_b[i] = m[META_PRES_B + i]; }
   bm->max_la = (int64_t)m[META_MAX_LA];
   bm->max_lb = (int64_t)m[META_MAX_LB];
@@ -221,6 +224,12 @@ int scan_collect(seqalign_batch *eng, size_t n, cudaStream_t st, BatchMeta *bm)
   bm->max_cells = (int64_t)m[META_MAX_CELLS];
   bm->min_la = n ? (int64_t)m[META_MIN_LA] : 0;
   bm->min_lb = n ? (int64_t)m[META_MIN_LB] : 0;
+}
+
+int scan_collect(seqalign_batch *eng, size_t n, cudaStream_t st, BatchMeta *bm)
+{
+  CU_TRY(cudaStreamSynchronize(st));
+  scan_decode(eng, n, 0, bm);
   return 0;
 }
 
@@ -915,16 +924,24 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       if(a1 > a0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_a.p + a0, h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
       if(b1 > b0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_b.p + b0, h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
       CU_TRY(cudaEventRecord(eng->ev_copy[c], cs));
+      /* the alphabet/shape scan of a chunk runs on its own stream as soon as
+       * the chunk has landed, next to the DP kernel of the chunk before it */
+      const size_t c0 = bounds[c], m = bounds[c + 1] - c0;
+      if(m == 0) continue;
+      CU_TRY(cudaStreamWaitEvent(eng->scan_stream, eng->ev_copy[c], 0));
+      TRY(scan_launch(eng, d_a, d_b, d_oa + c0, d_ob + c0, m,
+                      h_off_a[c0 + m] - h_off_a[c0] + h_off_b[c0 + m] - h_off_b[c0], eng->scan_stream, c));
+      CU_TRY(cudaEventRecord(eng->ev_scan[c], eng->scan_stream));
     }
     for(int c = 0; c < nchunks; c++) {
       const size_t c0 = bounds[c], m = bounds[c + 1] - c0;
       if(m == 0) continue;
-      CU_TRY(cudaStreamWaitEvent(st, eng->ev_copy[c], 0));
       DevBatch db;
       db.a = d_a; db.b = d_b; db.off_a = d_oa + c0; db.off_b = d_ob + c0; db.n = m;
       BatchMeta bm;
-      TRY(scan_batch(eng, d_a, d_b, db.off_a, db.off_b, m,
-                     h_off_a[c0 + m] - h_off_a[c0] + h_off_b[c0 + m] - h_off_b[c0], st, &bm));
+      CU_TRY(cudaEventSynchronize(eng->ev_scan[c]));
+      scan_decode(eng, m, c, &bm);
+      CU_TRY(cudaStreamWaitEvent(st, eng->ev_copy[c], 0));
       TRY(upload_tables(eng, bm, st));
       if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
       int32_t *ds = (int32_t *)eng->d_score.p + c0, *dx = (int32_t *)eng->d_xend.p + c0, *dy = (int32_t *)eng->d_yend.p + c0;
@@ -1020,10 +1037,12 @@ seqalign_batch_t *seqalign_batch_create(int device)
   eng->smem_optin = p.sharedMemPerBlockOptin;
   bool ok = cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&eng->scan_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&eng->ev0) == cudaSuccess && cudaEventCreate(&eng->ev1) == cudaSuccess;
   for(int i = 0; ok && i < seqalign_batch::MAX_CHUNKS; i++)
     ok = cudaEventCreate(&eng->ev_copy[i]) == cudaSuccess && cudaEventCreate(&eng->ev_k0[i]) == cudaSuccess &&
-         cudaEventCreate(&eng->ev_k1[i]) == cudaSuccess;
+         cudaEventCreate(&eng->ev_k1[i]) == cudaSuccess &&
+         cudaEventCreate(&eng->ev_scan[i]) == cudaSuccess;
   if(!ok) {
     g_create_error = "cannot create stream/events";
     delete eng;
@@ -1050,8 +1069,10 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
     if(eng->ev_copy[i]) cudaEventDestroy(eng->ev_copy[i]);
     if(eng->ev_k0[i]) cudaEventDestroy(eng->ev_k0[i]);
     if(eng->ev_k1[i]) cudaEventDestroy(eng->ev_k1[i]);
+    if(eng->ev_scan[i]) cudaEventDestroy(eng->ev_scan[i]);
   }
   if(eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
+  if(eng->scan_stream) cudaStreamDestroy(eng->scan_stream);
   if(eng->ev0) cudaEventDestroy(eng->ev0);
   if(eng->ev1) cudaEventDestroy(eng->ev1);
   if(eng->stream) cudaStreamDestroy(eng->stream);

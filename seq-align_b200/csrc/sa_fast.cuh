@@ -96,7 +96,20 @@ __device__ __forceinline__ int sext_byte_dyn(unsigned w, int k)
   }
 }
 
+/* keep a value in its register: ptxas otherwise rematerialises lane indices
+ * from SR_TID inside the step loop (an S2R + dependent ops every row) */
+__device__ __forceinline__ int pin_reg(int v)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+
 enum { TRACK_NONE = 0, TRACK_TREE = 1, TRACK_COLUMN = 2 };
+
+/* DIR kernels with K not a multiple of 8 stage their rows in shared memory */
+__host__ __device__ constexpr bool fast_dir_staged(int K) { return K % 8 != 0; }
 
 /* lane stride (in 32-bit words) of an int32 profile row: K, bumped by 4 when
  * K/4 is even so that 128-bit loads of 8 consecutive lanes hit disjoint banks */
@@ -134,12 +147,19 @@ fast_score_kernel(const FastArgs A)
   constexpr int KW = PROF32 ? K : (K + 3) / 4;            /* profile words per lane */
   constexpr int KS = PROF32 ? prof32_stride(K) : KW;      /* lane stride in words */
   constexpr int PSTRIDE = 32 * KS * 4;    /* bytes per profile row */
+  /* DIR: how a lane's K flag bytes of a row reach global memory.  K a multiple
+   * of 8: one aligned 8/16-byte store per lane.  Otherwise (K = 12, 20) the
+   * rows are staged in a shared-memory ring (G+1 rows per pair) and each
+   * finished row leaves as full 16-byte vectors, coalesced over the group:
+   * scattered 4-byte stores made the L1/L2 store path the bottleneck. */
+  constexpr bool STAGED = DIR && fast_dir_staged(K);
+  constexpr int RR = G + 1, RS = G * K;
 
   unsigned char *dsm = SA_DYN_SMEM();
   const ScoreParams &sp = A.sp;
   const int n = sp.ncodes;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int grp = lane / G, lig = lane % G;
+  const int grp = lane / G, lig = pin_reg(lane % G);
 
   /* shared layout: [mbarriers][lut 256][table n*n (int8 or int32) pad16][per-warp: profile | a stages | b stages] */
   uint64_t *s_bar = (uint64_t *)dsm;                       /* FAST_WARPS*2 */
@@ -148,11 +168,12 @@ fast_score_kernel(const FastArgs A)
   int32_t *s_tab32 = (int32_t *)(dsm + 64 + 256);
   const int tw = n + 1;   /* table row width: n codes + the padding code */
   const int tab_bytes = ((PROF32 ? 4 : 1) * n * tw + 15) & ~15;
-  const int warp_bytes = n * PSTRIDE + 2 * NG * (A.a_stage + A.b_stage);
+  const int warp_bytes = n * PSTRIDE + 2 * NG * (A.a_stage + A.b_stage) + (STAGED ? NG * RR * RS : 0);
   unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
   unsigned char *s_prof = wbase;
   unsigned char *s_a = wbase + n * PSTRIDE;                /* [stage][grp][a_stage] */
   unsigned char *s_b = s_a + 2 * NG * A.a_stage;           /* [stage][grp][b_stage] */
+  unsigned char *s_ring = s_b + 2 * NG * A.b_stage + grp * (RR * RS);   /* [row slot][RS] of this group */
   uint64_t *bar = s_bar + wib * 2;
 
   for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
@@ -291,6 +312,8 @@ fast_score_kernel(const FastArgs A)
     for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
     const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
     const unsigned *prow = (const unsigned *)s_prof + lane * KS;
+    /* ring slots: the row this lane writes (y-1 mod RR) and the row the last lane completes */
+    int wslot = (RR - lig) % RR, fslot = 2 % RR;
 
     for(int s = 0; s < nsteps; s++) {
       const int y = s - lig + 1;
@@ -385,10 +408,21 @@ fast_score_kernel(const FastArgs A)
         }
         if constexpr(DIR) {
           if(have) {
-            unsigned *drow = (unsigned *)(dirp + (int64_t)(y - 1) * dstride) + lig * (K / 4);
+            if constexpr(STAGED) {
+              unsigned *rrow = (unsigned *)(s_ring + wslot * RS) + lig * (K / 4);
 #pragma unroll
-            for(int q = 0; q < K / 4; q++)
-              if(lig * K + 4 * q < dstride) drow[q] = dw[q];
+              for(int q = 0; q < K / 4; q++) rrow[q] = dw[q];
+            } else if constexpr(K % 16 == 0) {
+              uint4 *drow = (uint4 *)(dirp + (int64_t)(y - 1) * dstride + lig * K);
+#pragma unroll
+              for(int q = 0; q < K / 16; q++)
+                if(lig * K + 16 * q < dstride) drow[q] = make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]);
+            } else {
+              uint2 *drow = (uint2 *)(dirp + (int64_t)(y - 1) * dstride + lig * K);
+#pragma unroll
+              for(int q = 0; q < K / 8; q++)
+                if(lig * K + 8 * q < dstride) drow[q] = make_uint2(dw[2 * q], dw[2 * q + 1]);
+            }
             if constexpr(HITS) {
               unsigned *mrow = (unsigned *)(A.m16 + A.dir_off[p] + (int64_t)(y - 1) * dstride) + lig * (K / 2);
 #pragma unroll
@@ -402,6 +436,18 @@ fast_score_kernel(const FastArgs A)
         out_h = hl;
         out_gb = gb;
         hd = hl_in; /* next row's diagonal */
+      }
+      if constexpr(STAGED) {
+        /* the group's last lane has just finished row s-G+2: flush it */
+        __syncwarp();
+        const int yc = s - G + 2;
+        if(have && yc >= 1 && yc <= lb) {
+          const uint4 *src = (const uint4 *)(s_ring + fslot * RS);
+          uint4 *dst = (uint4 *)(dirp + (int64_t)(yc - 1) * dstride);
+          for(int i = lig; i < dstride / 16; i += G) dst[i] = src[i];
+        }
+        wslot = wslot + 1 == RR ? 0 : wslot + 1;
+        fslot = fslot + 1 == RR ? 0 : fslot + 1;
       }
     }
 
@@ -515,7 +561,7 @@ fast16_kernel(const FastArgs A)
   const ScoreParams &sp = A.sp;
   const int n = sp.ncodes, tw = n + 1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int grp = lane / G, lig = lane % G;
+  const int grp = lane / G, lig = pin_reg(lane % G);
 
   uint64_t *s_bar = (uint64_t *)dsm;
   uint8_t *s_lut = dsm + 64;
@@ -668,8 +714,26 @@ fast16_kernel(const FastArgs A)
         const unsigned *pl = prow_lo + rb_lo[y - 1] * (PSTRIDE / 4);
         const unsigned *ph = prow_hi + cb_hi[y - 1] * (PSTRIDE / 4);
         unsigned wl[KW], wh[KW];
+        /* widest loads the lane stride (KW words) allows; scalar loads with an
+         * even stride would be 2- or 4-way bank conflicts */
+        if constexpr(KW % 4 == 0) {
 #pragma unroll
-        for(int q = 0; q < KW; q++) { wl[q] = pl[q]; wh[q] = ph[q]; }
+          for(int q = 0; q < KW / 4; q++) {
+            const uint4 u = ((const uint4 *)pl)[q], v = ((const uint4 *)ph)[q];
+            wl[4 * q] = u.x; wl[4 * q + 1] = u.y; wl[4 * q + 2] = u.z; wl[4 * q + 3] = u.w;
+            wh[4 * q] = v.x; wh[4 * q + 1] = v.y; wh[4 * q + 2] = v.z; wh[4 * q + 3] = v.w;
+          }
+        } else if constexpr(KW % 2 == 0) {
+#pragma unroll
+          for(int q = 0; q < KW / 2; q++) {
+            const uint2 u = ((const uint2 *)pl)[q], v = ((const uint2 *)ph)[q];
+            wl[2 * q] = u.x; wl[2 * q + 1] = u.y;
+            wh[2 * q] = v.x; wh[2 * q + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for(int q = 0; q < KW; q++) { wl[q] = pl[q]; wh[q] = ph[q]; }
+        }
         unsigned d = hd, kprev = BB;
 #pragma unroll
         for(int j = 0; j < K; j++) {
@@ -721,12 +785,15 @@ fast16_kernel(const FastArgs A)
 struct FastShape { int G, K; };
 static const FastShape kFastShapes[] = {
     {8, 8}, {8, 12}, {8, 16}, {8, 20}, {16, 12}, {16, 16}, {32, 10}, {32, 12}, {32, 16}};
+static const FastShape kFast16Shapes[] = {
+    {8, 8}, {8, 12}, {8, 13}, {8, 16}, {8, 19}, {8, 20}, {16, 12}, {16, 16}, {16, 19}, {32, 10}, {32, 12}, {32, 16}};
 
-inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage, int b_stage)
+inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage, int b_stage, bool dir = false)
 {
   const int NG = 32 / G;
   const int KS = prof32 ? prof32_stride(K) : (K + 3) / 4;
-  const size_t warp_bytes = (size_t)ncodes * 32 * KS * 4 + 2 * (size_t)NG * (a_stage + b_stage);
+  const size_t ring = dir && fast_dir_staged(K) ? (size_t)NG * (G + 1) * G * K : 0;
+  const size_t warp_bytes = (size_t)ncodes * 32 * KS * 4 + 2 * (size_t)NG * (a_stage + b_stage) + ring;
   const size_t tab = (((size_t)(prof32 ? 4 : 1) * ncodes * (ncodes + 1)) + 15) & ~(size_t)15;
   return 64 + 256 + tab + FAST_WARPS * warp_bytes;
 }
@@ -760,22 +827,28 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
                     shortest * (ft.max_sub > 0 ? ft.max_sub : 0) > (1L << 28)))
       return false;
   }
-  int G = 0, K = 0;
-  for(const FastShape &sh : kFastShapes)
-    if((int64_t)sh.G * sh.K >= max_la && (!want_dir || sh.K % 4 == 0)) { G = sh.G; K = sh.K; break; }
-  if(!G) return false;
   const int n = ft.ncodes;
-  /* int32 profile when it stays small (DNA-sized alphabets); else int8, which
-   * needs sub' = sub - open to fit a signed byte */
-  bool prof32 = (size_t)n * 32 * prof32_stride(K) * 4 <= 16 * 1024;
   const int padsub = ft.min_sub < -1 ? ft.min_sub : -1;
   const bool fits8 = lo >= -127 && hi <= 127 && (long)padsub - sp.open >= -127 && (long)padsub - sp.open <= 127;
-  if(!prof32 && !fits8) return false;
   /* packed 16-bit kernel: SW score only, one shape for the whole batch, and
    * every biased value (score + |open|) inside int16 */
   const bool s16 = sp.is_sw && !want_ends && !want_dir && uniform && fits8 &&
                    shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open < 32000 && sp.open > -16000 &&
                    ft.min_sub > -16000;
+  int G = 0, K = 0;
+  if(s16) {
+    /* the packed kernel has extra shapes that fit common read lengths tightly */
+    for(const FastShape &sh : kFast16Shapes)
+      if((int64_t)sh.G * sh.K >= max_la) { G = sh.G; K = sh.K; break; }
+  } else {
+    for(const FastShape &sh : kFastShapes)
+      if((int64_t)sh.G * sh.K >= max_la && (!want_dir || sh.K % 4 == 0)) { G = sh.G; K = sh.K; break; }
+  }
+  if(!G) return false;
+  /* int32 profile when it stays small (DNA-sized alphabets); else int8, which
+   * needs sub' = sub - open to fit a signed byte */
+  bool prof32 = (size_t)n * 32 * prof32_stride(K) * 4 <= 16 * 1024;
+  if(!prof32 && !fits8) return false;
   if(s16) prof32 = false;
   plan->s16 = s16;
   plan->dir = want_dir;
@@ -783,7 +856,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
   plan->a_stage = (int)((G * K + 15 + 15) & ~15) + 16;
   plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16;
-  plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage);
+  plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
   if(s16) {
     const size_t warp_bytes = 2 * (size_t)n * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
     plan->smem = 64 + 256 + (((size_t)n * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
@@ -854,20 +927,24 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   const int NG = (plan.s16 ? 2 : 1) * (32 / plan.G);
   const int64_t nsets = (F.npairs + NG - 1) / NG;
   const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
-#define SA_FAST_CASE(g, k)                                                                    \
+#define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
     void (*kfn)(const FastArgs) = fast16_kernel<g, k>;                                        \
     if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1; \
     SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F); \
     return 0;                                                                                 \
-  }                                                                                           \
+  }
+#define SA_FAST_CASE(g, k)                                                                    \
+  SA_FAST16_CASE(g, k)                                                                        \
   if(plan.G == g && plan.K == k)                                                              \
     return plan.prof32 ? fast_launch_gkp<g, k, true>(plan, F, num_sms, need, st)               \
                        : fast_launch_gkp<g, k, false>(plan, F, num_sms, need, st)
+  SA_FAST16_CASE(8, 13) SA_FAST16_CASE(8, 19) SA_FAST16_CASE(16, 19)
   SA_FAST_CASE(8, 8); SA_FAST_CASE(8, 12); SA_FAST_CASE(8, 16); SA_FAST_CASE(8, 20);
   SA_FAST_CASE(16, 12); SA_FAST_CASE(16, 16);
   SA_FAST_CASE(32, 10); SA_FAST_CASE(32, 12); SA_FAST_CASE(32, 16);
 #undef SA_FAST_CASE
+#undef SA_FAST16_CASE
   return -1;
 }
 

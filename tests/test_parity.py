@@ -101,6 +101,22 @@ def test_headline_config_sample(engine, big):
     _score_check(engine, scoring_from_spec(SPECS["nw_default"]), SW, a, oa, b, ob, general=False)
 
 
+@pytest.mark.parametrize("la", [97, 100, 104, 150, 152, 153, 300, 304])
+def test_fast16_tight_shapes(engine, big, la):
+    """packed 16-bit kernel on the shapes cut for common read lengths (8x13, 8x19,
+    16x19 lanes x columns): odd pair counts leave the high half of a register empty"""
+    n, lb = (333, la) if big else (5, 36)
+    a, oa, b, ob = synthetic_batch(900 + la, n, la, lb)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    es, _, _ = orc_batch_sw(orc_from_scoring(sc), a, oa, b, ob)
+    engine.set_scoring(sc)
+    engine.force_general(3)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast16_sw_score"
+    assert np.array_equal(engine.scores(), es)
+    engine.force_general(0)
+
+
 def test_protein_config_sample(engine, big):
     """BASELINE config 4 shape: SW, protein 400x400, BLOSUM62"""
     n, L = (400, 400) if big else (2, 70)
@@ -240,6 +256,26 @@ def test_alignments_ragged(engine, big, name, algo):
     engine.force_general(0)
     if name in ("sw_cli", "nw_default", "blosum62", "wild_n", "mutations"):
         assert any(k.startswith("fast_") for k in kernels) and any("general_dir" in k for k in kernels), kernels
+
+
+@pytest.mark.parametrize("la", [60, 90, 120, 150, 180, 250, 300, 400])
+def test_alignments_every_fill_shape(engine, big, la):
+    """flag-byte fill over each lanes x columns shape: rows staged through the shared-memory
+    ring (12 / 20 columns per lane) and direct 8 / 16-byte stores, ragged len_b per group"""
+    n, maxb = (24, la) if big else (5, 30)
+    rng = np.random.default_rng(la)
+    a_all, _, b_all, _ = synthetic_batch(300 + la, n, la, maxb)
+    sa = [a_all[i * la:(i + 1) * la].tobytes() for i in range(n)]
+    sb = [b_all[i * maxb:i * maxb + int(rng.integers(1, maxb + 1))].tobytes() for i in range(n)]
+    sa[1] = sa[1][:la - 7]          # one narrower pair: dstride below the shape's width
+    for name, algo in (("sw_cli", SW), ("nw_default", NW)):
+        sc = scoring_from_spec(SPECS[name])
+        o = orc_from_scoring(sc)
+        engine.set_scoring(sc)
+        engine.submit(algo, MODE_ALIGN, sa, sb)
+        assert engine.last_kernel.startswith("fast_")
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            _check_alignment(engine.alignment(i), algo, o, a, b)
 
 
 def test_alignments_wide_and_waves(engine, big, monkeypatch):

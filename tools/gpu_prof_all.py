@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""One launch of every kernel family on its BASELINE shape, for a single ncu capture
+(ncu -k regex:... --set full python tools/gpu_prof_all.py)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import *
+specs = scoring_specs()
+eng = seqalign.BatchAligner(0)
+A, OA, B, OB = synthetic_batch(2, 100000, 150, 150)
+eng.set_scoring(specs["sw_cli"]())
+eng.force_general(3); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, A, OA, B, OB); print(eng.last_kernel, eng.last_kernel_ms)
+eng.force_general(0); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, A, OA, B, OB); print(eng.last_kernel, eng.last_kernel_ms)
+n = 20000
+eng.submit_packed(seqalign.SW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); print(eng.last_kernel, eng.last_kernel_ms, eng.last_walk_ms)
+eng.set_hit_limits(8, 60)
+eng.submit_packed(seqalign.SW, seqalign.MODE_HITS, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); print(eng.last_kernel, eng.last_kernel_ms)
+PA, POA, PB, POB = synthetic_batch(4, 20000, 400, 400, kind="protein")
+eng.set_scoring(specs["blosum62"]())
+eng.submit_packed(seqalign.SW, seqalign.MODE_ALIGN, PA, POA, PB, POB); print(eng.last_kernel, eng.last_kernel_ms, eng.last_walk_ms)
+eng.force_general(3); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, PA, POA, PB, POB); print(eng.last_kernel, eng.last_kernel_ms)
+eng.force_general(0)
+L = 10000; n = 296
+eng.set_scoring(scoring_from_spec(SPECS["free_ends"]))
+LA, LOA, LB, LOB = synthetic_batch(3, n, L, L, block=16)
+eng.submit_packed(seqalign.NW, seqalign.MODE_SCORE, LA, LOA, LB, LOB); print(eng.last_kernel, eng.last_kernel_ms)
+eng.submit_packed(seqalign.NW, seqalign.MODE_ALIGN, LA, LOA, LB, LOB); print(eng.last_kernel, eng.last_kernel_ms, eng.last_walk_ms)
