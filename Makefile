@@ -20,7 +20,7 @@ HOST_SRCS = $(PKG)/host/sa_scoring.c $(PKG)/host/sa_alignment.c $(PKG)/host/sa_n
 HOST_OBJS = $(HOST_SRCS:.c=.o)
 CU_DEPS = $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h)
 
-all: $(LIBDIR)/libseqalign_b200.so $(LIBDIR)/libalign.a
+all: $(LIBDIR)/libseqalign_b200.so $(LIBDIR)/libalign.a tools
 
 $(PKG)/host/%.o: $(PKG)/host/%.c $(wildcard include/*.h $(PKG)/host/*.h)
 	$(CC) $(CFLAGS) -c $< -o $@
@@ -44,10 +44,33 @@ $(EMU)/libseqalign_emu.so: $(PKG)/csrc/sa_engine.cu $(CU_DEPS) $(EMU)/cuda_emu.c
 	for f in $(HOST_SRCS); do $(CC) $(CFLAGS) -c $$f -o $(EMU)/`basename $$f .c`_emu.o || exit 1; done
 	$(CXX) -shared -o $@ $(EMU)/sa_engine_emu.o $(EMU)/cuda_emu.o $(EMU)/sa_scoring_emu.o $(EMU)/sa_alignment_emu.o $(EMU)/sa_nw_emu.o $(EMU)/sa_sw_emu.o
 
+# batching command-line tools (same flags / stdout as the reference's bin/*)
+TOOLS = bin/needleman_wunsch bin/smith_waterman bin/lcs
+TOOL_COMMON = $(PKG)/tools/sa_cli.c
+TOOL_DEPS = $(wildcard $(PKG)/tools/*.h include/*.h) $(LIBDIR)/libseqalign_b200.so
+TOOL_LINK = -L$(LIBDIR) -lseqalign_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -lz
+tools: $(TOOLS)
+bin/needleman_wunsch: $(PKG)/tools/nw_main.c $(TOOL_COMMON) $(TOOL_DEPS)
+	mkdir -p bin
+	$(CC) $(CFLAGS) -I$(PKG)/tools $< $(TOOL_COMMON) -o $@ $(TOOL_LINK)
+bin/smith_waterman: $(PKG)/tools/sw_main.c $(TOOL_COMMON) $(TOOL_DEPS)
+	mkdir -p bin
+	$(CC) $(CFLAGS) -I$(PKG)/tools $< $(TOOL_COMMON) -o $@ $(TOOL_LINK)
+bin/lcs: $(PKG)/tools/lcs_main.c $(TOOL_DEPS)
+	mkdir -p bin
+	$(CC) $(CFLAGS) $< -o $@ $(TOOL_LINK)
+
+# the same tool sources against the lane emulator (CPU-side tests of the CLI logic)
+emu-tools: $(EMU)/libseqalign_emu.so
+	mkdir -p $(EMU)/bin
+	$(CC) $(CFLAGS) -I$(PKG)/tools $(PKG)/tools/nw_main.c $(TOOL_COMMON) -o $(EMU)/bin/needleman_wunsch -L$(EMU) -lseqalign_emu -Wl,-rpath,'$$ORIGIN/..' -lz
+	$(CC) $(CFLAGS) -I$(PKG)/tools $(PKG)/tools/sw_main.c $(TOOL_COMMON) -o $(EMU)/bin/smith_waterman -L$(EMU) -lseqalign_emu -Wl,-rpath,'$$ORIGIN/..' -lz
+	$(CC) $(CFLAGS) $(PKG)/tools/lcs_main.c -o $(EMU)/bin/lcs -L$(EMU) -lseqalign_emu -Wl,-rpath,'$$ORIGIN/..' -lz
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
 	rm -f $(PKG)/host/*.o $(PKG)/csrc/*.o $(LIBDIR)/*.so $(LIBDIR)/*.a $(EMU)/*.o $(EMU)/*.so
 
-.PHONY: all emu oracle clean
+.PHONY: all emu oracle clean tools emu-tools

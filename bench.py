@@ -42,7 +42,7 @@ import numpy as np  # noqa: E402
 PAIRS = 100000
 LEN = 150
 SEED = 2
-E2E_DEPTH = 3   # batches in flight in the end-to-end arm
+E2E_DEPTH = 4   # batches in flight in the end-to-end arm
 MATCH, MISMATCH, GAP_OPEN, GAP_EXTEND = 2, -2, -2, -1
 WORKLOAD = "SW score-only, %d synthetic DNA pairs %dx%d per GPU per step, scoring 2/-2/-2/-1" % (PAIRS, LEN, LEN)
 REF_BATCH = os.path.join(ROOT, "oracle", "_ref", "ref_batch")

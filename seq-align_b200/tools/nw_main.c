@@ -1,0 +1,139 @@
+/*
+ * nw_main.c -- `needleman_wunsch` command-line tool on the B200 batch engine.
+ *
+ * Same flags and the same bytes on stdout as the reference tool (reference
+ * src/tools/nw_cmdline.c:78-149 for the output layout, :158-196 for main);
+ * the difference is the loop: pairs read from files are aligned as batches
+ * (one launch sequence per batch, score + traceback on the device) instead of
+ * one needleman_wunsch_align() call per pair.  --stdin keeps the per-pair
+ * request/response rhythm the perl wrapper depends on.  --printmatrices needs
+ * the three DP matrices on the host and goes through the single-pair API.
+ */
+#define _GNU_SOURCE
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "needleman_wunsch.h"
+#include "seqalign_b200.h"
+#include "sa_cli.h"
+#include "sa_batch.h"
+
+static sa_opts opt;
+static scoring_t scoring;
+static nw_aligner_t *nw;
+static alignment_t *result;
+static seqalign_batch_t *eng;
+
+/* "Br1:/Br2:" layout of --zam (reference nw_cmdline.c:36-75) */
+static void print_zam(void)
+{
+  int mismatches = 0, indels = 0;
+  for(char *p = result->result_a, *q = result->result_b; *p; p++, q++) {
+    if(*p == '-') *p = '_';
+    if(*q == '-') *q = '_';
+  }
+  printf("Br1:%s\n    ", result->result_a);
+  for(size_t i = 0; result->result_a[i] != '\0'; i++) {
+    const char x = result->result_a[i], y = result->result_b[i];
+    if(x == '_' || y == '_') { putc(' ', stdout); indels++; }
+    else if((scoring.case_sensitive && x != y) || tolower(x) != tolower(y)) { putc('*', stdout); mismatches++; }
+    else putc('|', stdout);
+  }
+  printf("\nBr2:%s\n%i %i\n\n", result->result_b, mismatches, indels);
+}
+
+/* one aligned pair from `result` (reference nw_cmdline.c:94-148) */
+static void print_pair(const char *name_a, const char *name_b)
+{
+  if(opt.zam) { print_zam(); fflush(stdout); return; }
+  if(opt.print_fasta && name_a) { fputs(name_a, stdout); putc('\n', stdout); }
+  if(opt.print_fasta && opt.print_pretty && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
+  if(opt.print_colour) alignment_colour_print_against(result->result_a, result->result_b, scoring.case_sensitive);
+  else fputs(result->result_a, stdout);
+  putc('\n', stdout);
+  if(opt.print_pretty) { alignment_print_spacer(result->result_a, result->result_b, &scoring); putc('\n', stdout); }
+  else if(opt.print_fasta && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
+  if(opt.print_colour) alignment_colour_print_against(result->result_b, result->result_a, scoring.case_sensitive);
+  else fputs(result->result_b, stdout);
+  putc('\n', stdout);
+  if(opt.print_scores) printf("score: %i\n", result->score);
+  putc('\n', stdout);
+  fflush(stdout);
+}
+
+/* single-pair API: fills nw's matrices too (for --printmatrices), and reports
+ * unknown character pairs exactly where the reference would stop */
+static void align_single(const char *a, const char *b, const char *name_a, const char *name_b)
+{
+  needleman_wunsch_align(a, b, &scoring, nw, result);
+  if(opt.print_matrices && !opt.zam) alignment_print_matrices(nw);
+  print_pair(name_a, name_b);
+}
+
+static void align_batch(const char *const *a, const size_t *la, const char *const *b, const size_t *lb,
+                        char *const *name_a, char *const *name_b, size_t n)
+{
+  if(n == 0) return;
+  int rc = SEQALIGN_ERR_ARG;
+  if(!opt.print_matrices) rc = seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+  if(rc == SEQALIGN_OK) {
+    for(size_t i = 0; i < n; i++) {
+      alignment_ensure_capacity(result, la[i] + lb[i]);
+      rc = seqalign_batch_alignment(eng, i, result);
+      if(rc < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+      print_pair(name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
+    }
+    return;
+  }
+  if(!opt.print_matrices && rc != SEQALIGN_ERR_UNKNOWN_PAIR) {
+    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
+    exit(EXIT_FAILURE);
+  }
+  /* pair by pair: prints everything up to the offending pair, then the
+   * reference's "Unknown character pair" message and exit(EXIT_FAILURE) */
+  for(size_t i = 0; i < n; i++) align_single(a[i], b[i], name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
+}
+
+static void flush_pairs(sa_pairs *p, sa_reader *r)
+{
+  (void)r;
+  align_batch((const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->name_a, p->name_b, p->n);
+  sa_pairs_clear(p);
+}
+
+int main(int argc, char **argv)
+{
+  scoring_system_default(&scoring);
+  sa_cli_parse(argc, argv, &scoring, SA_TOOL_NW, &opt);
+  /* the matrices only travel to the host when they are going to be printed */
+  if(!opt.print_matrices) setenv("SEQALIGN_SKIP_MATRICES", "1", 1);
+
+  eng = seqalign_batch_create(0);
+  if(!eng) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); return EXIT_FAILURE; }
+  if(seqalign_batch_set_scoring(eng, &scoring) != SEQALIGN_OK) {
+    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
+    return EXIT_FAILURE;
+  }
+  nw = needleman_wunsch_new();
+  result = alignment_create(256);
+
+  if(opt.seq1) {
+    const size_t la = strlen(opt.seq1), lb = strlen(opt.seq2);
+    align_batch(&opt.seq1, &la, &opt.seq2, &lb, NULL, NULL, 1);
+  }
+  sa_pairs pairs;
+  memset(&pairs, 0, sizeof(pairs));
+  for(size_t i = 0; i < opt.nfiles; i++) {
+    const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
+    if(f1 && *f1 == '\0' && !f2) f1 = "-";
+    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, &pairs, flush_pairs);
+  }
+  sa_pairs_free(&pairs);
+  needleman_wunsch_free(nw);
+  alignment_free(result);
+  seqalign_batch_destroy(eng);
+  sa_cli_free(&opt);
+  return EXIT_SUCCESS;
+}

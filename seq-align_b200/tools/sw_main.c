@@ -1,0 +1,258 @@
+/*
+ * sw_main.c -- `smith_waterman` command-line tool on the B200 batch engine.
+ *
+ * Same flags and stdout as the reference tool (reference
+ * src/tools/sw_cmdline.c:125-314 for the per-pair output, :323-362 for main).
+ * Pairs read from files are aligned as batches in the engine's multi-hit mode
+ * (fill, candidate sort, masked walks all on the device: the whole of
+ * smith_waterman_align2 + the fetch loop, reference smith_waterman.c:137-277);
+ * the tool then prints each pair's hits down to its own --minscore default.
+ * The single-pair API is used where the batch mode does not apply: --stdin
+ * (hits are fetched one keystroke at a time), --printmatrices, scoring shapes
+ * outside the specialised kernel, and pairs whose hit list filled the
+ * per-pair cap.  Every pair gets a fresh visited mask (the reference's reuse
+ * of a partly cleared mask across pairs, smith_waterman.c:149, is not
+ * reproduced -- DESIGN.md "known upstream defects").
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "smith_waterman.h"
+#include "seqalign_b200.h"
+#include "sa_cli.h"
+#include "sa_batch.h"
+
+static sa_opts opt;
+static scoring_t scoring;
+static sw_aligner_t *sw;
+static alignment_t *result;
+static seqalign_batch_t *eng;
+static size_t alignment_index = 0;
+static int wait_on_keystroke = 0;
+static sa_reader *prompt_input = NULL;
+
+/* hits kept per pair by the device when --maxhits is absent or large */
+#define HIT_CAP 32
+
+static size_t zmax(size_t a, size_t b) { return a > b ? a : b; }
+static size_t zmin(size_t a, size_t b) { return a < b ? a : b; }
+
+/* one sequence line of a hit (reference sw_cmdline.c:49-82) */
+static void print_part(const char *row, const char *other, size_t pos, size_t len, const char *whole,
+                       size_t spaces_left, size_t spaces_right, size_t ctx_left, size_t ctx_right)
+{
+  fputs("  ", stdout);
+  for(size_t i = 0; i < spaces_left; i++) putc(' ', stdout);
+  if(ctx_left > 0) {
+    if(opt.print_colour) fputs(align_col_context, stdout);
+    printf("%.*s", (int)ctx_left, whole + pos - ctx_left);
+    if(opt.print_colour) fputs(align_col_stop, stdout);
+  }
+  if(opt.print_colour) alignment_colour_print_against(row, other, scoring.case_sensitive);
+  else fputs(row, stdout);
+  if(ctx_right > 0) {
+    if(opt.print_colour) fputs(align_col_context, stdout);
+    printf("%.*s", (int)ctx_right, whole + pos + len);
+    if(opt.print_colour) fputs(align_col_stop, stdout);
+  }
+  for(size_t i = 0; i < spaces_right; i++) putc(' ', stdout);
+  printf("  [pos: %li; len: %lu]\n", (long)pos, (unsigned long)len);
+}
+
+/* the hit in `result` (reference sw_cmdline.c:219-306) */
+static void print_hit(const char *seq_a, const char *seq_b, size_t len_a, size_t len_b, size_t hit_index)
+{
+  printf("hit %zu.%zu score: %i\n", alignment_index, hit_index, result->score);
+  size_t ctx_l = 0, ctx_r = 0, ls_a = 0, ls_b = 0, rs_a = 0, rs_b = 0;
+  if(opt.context) {
+    ctx_l = zmin(zmax(result->pos_a, result->pos_b), opt.context);
+    const size_t rem_a = len_a - (result->pos_a + result->len_a), rem_b = len_b - (result->pos_b + result->len_b);
+    ctx_r = zmin(zmax(rem_a, rem_b), opt.context);
+    ls_a = ctx_l > result->pos_a ? ctx_l - result->pos_a : 0;
+    ls_b = ctx_l > result->pos_b ? ctx_l - result->pos_b : 0;
+    rs_a = ctx_r > rem_a ? ctx_r - rem_a : 0;
+    rs_b = ctx_r > rem_b ? ctx_r - rem_b : 0;
+  }
+  print_part(result->result_a, result->result_b, result->pos_a, result->len_a, seq_a, ls_a, rs_a, ctx_l - ls_a, ctx_r - rs_a);
+  if(opt.print_pretty) {
+    const size_t ml = zmax(ls_a, ls_b), mr = zmax(rs_a, rs_b);
+    fputs("  ", stdout);
+    for(size_t i = 0; i < ml; i++) putc(' ', stdout);
+    for(size_t i = 0; i < ctx_l - ml; i++) putc('.', stdout);
+    alignment_print_spacer(result->result_a, result->result_b, &scoring);
+    for(size_t i = 0; i < ctx_r - mr; i++) putc('.', stdout);
+    for(size_t i = 0; i < mr; i++) putc(' ', stdout);
+    putc('\n', stdout);
+  }
+  print_part(result->result_b, result->result_a, result->pos_b, result->len_b, seq_b, ls_b, rs_b, ctx_l - ls_b, ctx_r - rs_b);
+  printf("\n");
+  fflush(stdout);
+}
+
+/* pair header up to the blank line (reference sw_cmdline.c:157-190) */
+static void print_header(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b,
+                         size_t len_a, size_t len_b, aligner_t *matrices)
+{
+  printf("== Alignment %zu lengths (%lu, %lu):\n", alignment_index, (unsigned long)len_a, (unsigned long)len_b);
+  if(matrices) alignment_print_matrices(matrices);
+  if(opt.print_fasta && name_a) { fputs(name_a, stdout); putc('\n', stdout); }
+  if(opt.print_seq) { fputs(seq_a, stdout); putc('\n', stdout); }
+  if(opt.print_fasta && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
+  if(opt.print_seq) { fputs(seq_b, stdout); putc('\n', stdout); }
+  putc('\n', stdout);
+}
+
+/* --minscore default of a pair (reference sw_cmdline.c:192-202) */
+static int pair_min_score(size_t len_a, size_t len_b)
+{
+  if(opt.min_score_set) return opt.min_score;
+  if(wait_on_keystroke) return 0;
+  const double frac = 0.2 * (double)zmin(len_a, len_b);
+  return (int)(scoring.match * (frac >= 2 ? frac : 2));
+}
+
+/* interactive prompt between hits (reference sw_cmdline.c:84-122) */
+static int next_hit_wanted(void)
+{
+  if(!wait_on_keystroke) return 1;
+  int r = 0, answered = 0, next = 0;
+  while(!answered) {
+    printf("next [h]it or [a]lignment: ");
+    fflush(stdout);
+    while((r = sa_reader_getc(prompt_input)) != -1 && r != '\n' && r != '\r') {
+      if(r == 'h' || r == 'H') { next = 1; answered = 1; }
+      else if(r == 'a' || r == 'A') { next = 0; answered = 1; }
+    }
+    if(r == -1) { putc('\n', stdout); exit(EXIT_SUCCESS); }
+  }
+  return next;
+}
+
+static int rejects_pair(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b)
+{
+  if((name_a || name_b) && wait_on_keystroke) {
+    fprintf(stderr, "Error: Interactive input takes seq only (no FASTA/FASTQ) '%s:%s'\n", name_a, name_b);
+    fflush(stderr);
+    exit(EXIT_FAILURE);
+  }
+  if(seq_a[0] == '\0' || seq_b[0] == '\0') {
+    fprintf(stderr, "Error: Sequences must have length > 0\n");
+    fflush(stderr);
+    if(opt.print_fasta && name_a && name_b) fprintf(stderr, "%s\n%s\n", name_a, name_b);
+    fflush(stderr);
+    return 1;
+  }
+  return 0;
+}
+
+/* single-pair API: smith_waterman_align + fetch loop, hit by hit */
+static void align_single(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b)
+{
+  if(rejects_pair(seq_a, seq_b, name_a, name_b)) return;
+  smith_waterman_align(seq_a, seq_b, &scoring, sw);
+  aligner_t *al = smith_waterman_get_aligner(sw);
+  const size_t len_a = al->score_width - 1, len_b = al->score_height - 1;
+  print_header(seq_a, seq_b, name_a, name_b, len_a, len_b, opt.print_matrices ? al : NULL);
+  const int min_score = pair_min_score(len_a, len_b);
+  fflush(stdout);
+  size_t hit_index = 0;
+  while(next_hit_wanted() && smith_waterman_fetch(sw, result) && result->score >= min_score &&
+        (!opt.max_hits_set || hit_index < opt.max_hits))
+    print_hit(seq_a, seq_b, len_a, len_b, hit_index++);
+  fputs("==\n", stdout);
+  fflush(stdout);
+  alignment_index++;
+}
+
+static void align_batch(const char *const *a, const size_t *la, const char *const *b, const size_t *lb,
+                        char *const *name_a, char *const *name_b, size_t n)
+{
+  if(n == 0) return;
+  int batch_ok = !opt.print_matrices && !wait_on_keystroke;
+  size_t cap = HIT_CAP;
+  if(batch_ok) {
+    /* empty sequences are reported at print time; the engine sees them as pairs without hits */
+    int min_all = 0, have = 0;
+    for(size_t i = 0; i < n; i++) {
+      if(la[i] == 0 || lb[i] == 0) continue;
+      const int m = pair_min_score(la[i], lb[i]);
+      if(!have || m < min_all) { min_all = m; have = 1; }
+    }
+    if(opt.max_hits_set && opt.max_hits < HIT_CAP) cap = opt.max_hits ? opt.max_hits : 1;
+    seqalign_batch_set_hit_limits(eng, cap, min_all < 1 ? 1 : min_all);
+    const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, a, la, b, lb, n);
+    if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0; /* single-pair API handles both */
+    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+  }
+  for(size_t i = 0; i < n; i++) {
+    const char *na = name_a ? name_a[i] : NULL, *nb = name_b ? name_b[i] : NULL;
+    if(!batch_ok) { align_single(a[i], b[i], na, nb); continue; }
+    if(rejects_pair(a[i], b[i], na, nb)) continue;
+    const int min_score = pair_min_score(la[i], lb[i]);
+    const size_t nh = seqalign_batch_hit_count(eng, i);
+    const size_t want = opt.max_hits_set ? opt.max_hits : (size_t)-1;
+    /* the device list is complete unless it is full and the caller wants more */
+    if(nh == cap && want > cap) {
+      seqalign_batch_hit(eng, i, nh - 1, result);
+      if(result->score >= min_score) { align_single(a[i], b[i], na, nb); continue; }
+    }
+    print_header(a[i], b[i], na, nb, la[i], lb[i], NULL);
+    fflush(stdout);
+    size_t hit_index = 0;
+    for(size_t h = 0; h < nh && hit_index < want; h++) {
+      if(seqalign_batch_hit(eng, i, h, result) != 1) break;
+      if(result->score < min_score) break;
+      print_hit(a[i], b[i], la[i], lb[i], hit_index++);
+    }
+    fputs("==\n", stdout);
+    fflush(stdout);
+    alignment_index++;
+  }
+}
+
+static void flush_pairs(sa_pairs *p, sa_reader *r)
+{
+  prompt_input = r;
+  align_batch((const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->name_a, p->name_b, p->n);
+  sa_pairs_clear(p);
+}
+
+int main(int argc, char **argv)
+{
+  /* smith_waterman's own defaults (reference sw_cmdline.c:37-46) */
+  scoring_system_default(&scoring);
+  scoring.match = 2;
+  scoring.mismatch = -2;
+  scoring.gap_open = -2;
+  scoring.gap_extend = -1;
+  sa_cli_parse(argc, argv, &scoring, SA_TOOL_SW, &opt);
+
+  eng = seqalign_batch_create(0);
+  if(!eng) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); return EXIT_FAILURE; }
+  if(seqalign_batch_set_scoring(eng, &scoring) != SEQALIGN_OK) {
+    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
+    return EXIT_FAILURE;
+  }
+  sw = smith_waterman_new();
+  result = alignment_create(256);
+
+  if(opt.seq1) {
+    const size_t la = strlen(opt.seq1), lb = strlen(opt.seq2);
+    align_batch(&opt.seq1, &la, &opt.seq2, &lb, NULL, NULL, 1);
+  }
+  sa_pairs pairs;
+  memset(&pairs, 0, sizeof(pairs));
+  for(size_t i = 0; i < opt.nfiles; i++) {
+    const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
+    if(f1 && *f1 == '\0' && !f2) { wait_on_keystroke = 1; f1 = "-"; }
+    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, &pairs, flush_pairs);
+  }
+  sa_pairs_free(&pairs);
+  smith_waterman_free(sw);
+  alignment_free(result);
+  seqalign_batch_destroy(eng);
+  sa_cli_free(&opt);
+  return EXIT_SUCCESS;
+}

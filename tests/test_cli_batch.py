@@ -1,0 +1,92 @@
+"""The batching command-line tools (seq-align_b200/tools -> bin/needleman_wunsch,
+bin/smith_waterman, bin/lcs) against stdout recorded from the reference's own tools.
+
+Two golden sets:
+  tests/golden/cli_vectors.json        single-pair invocations (tools/gen_cli_golden.py)
+  tests/golden/cli_batch_vectors.json  multi-pair files in every input format, scoring files,
+                                       stdin protocols, error cases (tools/gen_cli_batch_golden.py)
+Backends as for the parity tests: on a GPU box the real binaries in bin/ (gpu-marked); in the
+build container the same tool sources linked against the lane emulator (tests/emu/bin).
+"""
+import gzip
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import BACKEND
+from helpers import ROOT
+
+GOLD1 = json.load(open(os.path.join(ROOT, "tests", "golden", "cli_vectors.json")))["cases"]
+GOLD2 = json.load(open(os.path.join(ROOT, "tests", "golden", "cli_batch_vectors.json")))["cases"]
+GOLD1 = [c for c in GOLD1 if c["tool"] in ("needleman_wunsch", "smith_waterman", "lcs")]
+
+pytestmark = [pytest.mark.parity]
+
+
+@pytest.fixture(scope="module")
+def tool_dir():
+    if BACKEND == "gpu":
+        d = os.path.join(ROOT, "bin")
+        if not os.path.exists(os.path.join(d, "needleman_wunsch")):
+            subprocess.check_call(["make", "-s", "-C", ROOT, "tools"])
+        return d
+    subprocess.check_call(["make", "-s", "-C", ROOT, "emu-tools"])
+    return os.path.join(ROOT, "tests", "emu", "bin")
+
+
+def _run(tool_dir, case):
+    with tempfile.TemporaryDirectory() as td:
+        args = []
+        for x in case["argv"]:
+            if x in case["files"]:
+                f = case["files"][x]
+                if isinstance(f, str):
+                    f = dict(text=f, gz=False)
+                path = os.path.join(td, x[1:] + (".gz" if f["gz"] else ".txt"))
+                if f["gz"]:
+                    with gzip.open(path, "wt") as fh:
+                        fh.write(f["text"])
+                else:
+                    with open(path, "w", newline="") as fh:
+                        fh.write(f["text"])
+                args.append(path)
+            else:
+                args.append(x)
+        p = subprocess.run([os.path.join(tool_dir, case["tool"])] + args, input=case["stdin"],
+                           capture_output=True, text=True, timeout=600)
+        return p.returncode, p.stdout, p.stderr.replace(td, "<tmp>")
+
+
+@pytest.mark.parametrize("i", range(len(GOLD1)))
+def test_single_pair_invocations(tool_dir, i):
+    case = GOLD1[i]
+    rc, out, err = _run(tool_dir, case)
+    assert rc == case["rc"], err
+    assert out == case["stdout"], (case["tool"], case["argv"])
+
+
+@pytest.mark.parametrize("i", range(len(GOLD2)))
+def test_batched_invocations(tool_dir, i):
+    case = GOLD2[i]
+    rc, out, err = _run(tool_dir, case)
+    assert rc == case["rc"], (case["argv"], err)
+    if case["rc"] == 0 or not case["stderr_first"].startswith("Error: "):
+        assert out == case["stdout"], (case["tool"], case["argv"])
+    if case["stderr_first"] is not None:
+        # usage errors print the usage text on stdout/stderr in their own words; the message is the contract
+        assert err.split("\n")[0] == case["stderr_first"], (case["argv"], err[:300])
+
+
+def test_interactive_smith_waterman_prompt(tool_dir):
+    """--stdin: hits are handed out one keystroke at a time (reference sw_cmdline.c:84-122);
+    'h' = next hit, 'a' = next alignment, EOF ends the session"""
+    stdin = "ACGTACGTTTGACCA\nTTACGTACGAAGACC\nh\nh\na\ngacag\ntgaagt\nh\n"
+    p = subprocess.run([os.path.join(tool_dir, "smith_waterman"), "--stdin"], input=stdin, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0
+    out = p.stdout
+    assert out.count("next [h]it or [a]lignment: ") == 5
+    assert "== Alignment 0 lengths (15, 15):" in out and "== Alignment 1 lengths (5, 6):" in out
+    assert "hit 0.0 score:" in out and "hit 0.1 score:" in out and "hit 1.0 score:" in out

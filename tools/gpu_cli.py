@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Throughput of the batching command-line tools next to the reference's own
+tools (tests/integration/_ref_own, unmodified sources + the reference's DP, one pair per call)
+on the same FASTA input.  Wall clock of the whole process, GPU context creation included."""
+import json, os, subprocess, sys, tempfile, time, hashlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import synthetic_batch
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+NREF = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+a, oa, b, ob = synthetic_batch(2, N, 150, 150)
+td = tempfile.mkdtemp()
+def write(path, n):
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(">a%d\n%s\n>b%d\n%s\n" % (i, a[i * 150:(i + 1) * 150].tobytes().decode(), i, b[i * 150:(i + 1) * 150].tobytes().decode()))
+big, small = os.path.join(td, "big.fa"), os.path.join(td, "small.fa")
+write(big, N); write(small, NREF)
+def run(exe, args, path):
+    t = time.time()
+    p = subprocess.run([exe] + args + ["--file", path], capture_output=True)
+    dt = time.time() - t
+    assert p.returncode == 0, p.stderr[:500]
+    return dt, p.stdout
+rows = []
+for tool, args in (("needleman_wunsch", ["--printscores"]), ("smith_waterman", ["--maxhits", "1"]), ("smith_waterman", [])):
+    ours, ref = os.path.join(ROOT, "bin", tool), os.path.join(ROOT, "tests", "integration", "_ref_own", tool)
+    run(ours, args, small)                       # warm the driver / page cache
+    t_small, out_small = run(ours, args, small)
+    t_big, out_big = run(ours, args, big)
+    row = dict(tool=tool, args=args, pairs=N, seconds=round(t_big, 3), pairs_per_s=round(N / t_big), gcups=round(N * 22500 / t_big / 1e9, 1),
+               small_pairs=NREF, small_seconds=round(t_small, 3), stdout_mb=round(len(out_big) / 1e6, 1),
+               marginal_pairs_per_s=round((N - NREF) / max(t_big - t_small, 1e-9)))
+    if os.path.exists(ref):
+        t_ref, out_ref = run(ref, args, small)
+        # NW output must be identical; SW beyond pair 0 differs by the reference's stale-mask defect
+        row.update(ref_seconds=round(t_ref, 3), ref_pairs_per_s=round(NREF / t_ref), speedup_marginal=round(row["marginal_pairs_per_s"] / (NREF / t_ref), 1),
+                   same_stdout_as_reference=out_small == out_ref, first_pair_same=out_small.split(b"\n\n")[0] == out_ref.split(b"\n\n")[0])
+    print(json.dumps(row), flush=True)
+    rows.append(row)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gpu_cli.json"), "w"), indent=1)

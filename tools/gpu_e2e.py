@@ -14,7 +14,7 @@ for _ in range(3): d.copy_(pa, non_blocking=True)
 torch.cuda.synchronize(); t = time.perf_counter()
 for _ in range(20): d.copy_(pa, non_blocking=True)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 20
-print("pinned H2D 15 MB: %.3f ms  (%.1f GB/s) -> a 31.6 MB step needs %.3f ms of PCIe" % (dt * 1e3, len(A) / dt / 1e9, dt * 31.6 / 15), flush=True)
+print("pinned H2D 15 MB: %.3f ms  (%.1f GB/s) -> a 31.6 MB step needs %.3f ms of PCIe" % (dt * 1e3, len(A) / dt / 1e9, dt * 1e3 * 31.6 / 15), flush=True)
 ptrs = (pa.data_ptr(), poa.data_ptr(), pb.data_ptr(), pob.data_ptr())
 eng = seqalign.BatchAligner(0, seqalign.Scoring.sw_cli_default())
 for chunks in ("1", "2", "3", "4", "6", "8"):
