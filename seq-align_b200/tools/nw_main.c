@@ -47,7 +47,7 @@ static void print_zam(void)
 /* one aligned pair from `result` (reference nw_cmdline.c:94-148) */
 static void print_pair(const char *name_a, const char *name_b)
 {
-  if(opt.zam) { print_zam(); fflush(stdout); return; }
+  if(opt.zam) { print_zam(); if(opt.interactive) fflush(stdout); return; }
   if(opt.print_fasta && name_a) { fputs(name_a, stdout); putc('\n', stdout); }
   if(opt.print_fasta && opt.print_pretty && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
   if(opt.print_colour) alignment_colour_print_against(result->result_a, result->result_b, scoring.case_sensitive);
@@ -60,7 +60,9 @@ static void print_pair(const char *name_a, const char *name_b)
   putc('\n', stdout);
   if(opt.print_scores) printf("score: %i\n", result->score);
   putc('\n', stdout);
-  fflush(stdout);
+  /* the reference flushes after every pair; a batch is flushed once (same
+   * bytes), --stdin keeps the per-pair flush its callers wait for */
+  if(opt.interactive) fflush(stdout);
 }
 
 /* single-pair API: fills nw's matrices too (for --printmatrices), and reports
@@ -77,14 +79,18 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
 {
   if(n == 0) return;
   int rc = SEQALIGN_ERR_ARG;
+  double t0 = sa_now();
   if(!opt.print_matrices) rc = seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+  sa_t_align += sa_now() - t0;
   if(rc == SEQALIGN_OK) {
+    t0 = sa_now();
     for(size_t i = 0; i < n; i++) {
       alignment_ensure_capacity(result, la[i] + lb[i]);
       rc = seqalign_batch_alignment(eng, i, result);
       if(rc < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
       print_pair(name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
     }
+    sa_t_print += sa_now() - t0;
     return;
   }
   if(!opt.print_matrices && rc != SEQALIGN_ERR_UNKNOWN_PAIR) {
@@ -100,6 +106,7 @@ static void flush_pairs(sa_pairs *p, sa_reader *r)
 {
   (void)r;
   align_batch((const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->name_a, p->name_b, p->n);
+  fflush(stdout);
   sa_pairs_clear(p);
 }
 
@@ -122,18 +129,20 @@ int main(int argc, char **argv)
   if(opt.seq1) {
     const size_t la = strlen(opt.seq1), lb = strlen(opt.seq2);
     align_batch(&opt.seq1, &la, &opt.seq2, &lb, NULL, NULL, 1);
+    fflush(stdout);
   }
   sa_pairs pairs;
   memset(&pairs, 0, sizeof(pairs));
   for(size_t i = 0; i < opt.nfiles; i++) {
     const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
     if(f1 && *f1 == '\0' && !f2) f1 = "-";
-    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, &pairs, flush_pairs);
+    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, SA_BATCH_MAX_PAIRS, &pairs, flush_pairs);
   }
   sa_pairs_free(&pairs);
   needleman_wunsch_free(nw);
   alignment_free(result);
   seqalign_batch_destroy(eng);
   sa_cli_free(&opt);
+  sa_timing_report();
   return EXIT_SUCCESS;
 }

@@ -10,7 +10,23 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "sa_cli.h"
+
+/* SEQALIGN_CLI_TIMING=1: seconds spent reading, aligning and printing, on stderr at exit */
+static double sa_t_read = 0, sa_t_align = 0, sa_t_print = 0;
+static inline double sa_now(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static inline void sa_timing_report(void)
+{
+  const char *e = getenv("SEQALIGN_CLI_TIMING");
+  if(e && e[0] == '1')
+    fprintf(stderr, "timing: read %.3f s, align %.3f s, print %.3f s\n", sa_t_read, sa_t_align, sa_t_print);
+}
 
 typedef struct {
   char **a, **b, **name_a, **name_b; /* owned copies; names NULL when the record had none */
@@ -60,7 +76,7 @@ static inline void sa_pairs_free(sa_pairs *p)
 }
 
 /* a batch is full at this many pairs or bytes of sequence */
-#define SA_BATCH_MAX_PAIRS ((size_t)1 << 17)
+#define SA_BATCH_MAX_PAIRS ((size_t)1 << 16)
 #define SA_BATCH_MAX_BYTES ((size_t)256 << 20)
 
 /* Read every pair of one input (path2 == NULL: consecutive records of path1)
@@ -69,7 +85,7 @@ static inline void sa_pairs_free(sa_pairs *p)
  * wrappers, reference perl/NeedlemanWunsch.pm:182-210).  Messages as
  * reference src/alignment_cmdline.c:584-632. */
 static inline void sa_for_each_batch(const char *path1, const char *path2, int interactive, int buffered,
-                                     sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
+                                     size_t max_pairs, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
 {
   sa_reader *r1 = sa_reader_open(path1, buffered), *r2 = r1;
   if(!r1) { fprintf(stderr, "Alignment Error: couldn't open file %s\n", path1); fflush(stderr); return; }
@@ -80,6 +96,7 @@ static inline void sa_for_each_batch(const char *path1, const char *path2, int i
   sa_record rec1, rec2;
   memset(&rec1, 0, sizeof(rec1)); memset(&rec2, 0, sizeof(rec2));
   unsigned long count = 0;
+  double t0 = sa_now();
   for(; sa_reader_next(r1, &rec1) > 0; count++) {
     if(sa_reader_next(r2, &rec2) <= 0) {
       flush(pairs, r1);
@@ -87,8 +104,13 @@ static inline void sa_for_each_batch(const char *path1, const char *path2, int i
       break;
     }
     sa_pairs_add(pairs, &rec1, &rec2);
-    if(interactive || pairs->n >= SA_BATCH_MAX_PAIRS || pairs->bytes >= SA_BATCH_MAX_BYTES) flush(pairs, r1);
+    if(interactive || pairs->n >= max_pairs || pairs->bytes >= SA_BATCH_MAX_BYTES) {
+      sa_t_read += sa_now() - t0;
+      flush(pairs, r1);
+      t0 = sa_now();
+    }
   }
+  sa_t_read += sa_now() - t0;
   flush(pairs, r1);
   if(count == 0) { fprintf(stderr, "Alignment Warning: empty input\n"); fflush(stderr); }
   sa_reader_close(r1);

@@ -33,8 +33,11 @@ static size_t alignment_index = 0;
 static int wait_on_keystroke = 0;
 static sa_reader *prompt_input = NULL;
 
-/* hits kept per pair by the device when --maxhits is absent or large */
-#define HIT_CAP 32
+/* hits kept per pair by the device when --maxhits is absent or large (a pair
+ * that fills its list is redone through the single-pair API), and pairs per
+ * batch: the engine reserves cap x (len_a + len_b) bytes of strings per pair */
+#define HIT_CAP 8
+#define SW_BATCH_PAIRS ((size_t)1 << 14)
 
 static size_t zmax(size_t a, size_t b) { return a > b ? a : b; }
 static size_t zmin(size_t a, size_t b) { return a < b ? a : b; }
@@ -88,7 +91,8 @@ static void print_hit(const char *seq_a, const char *seq_b, size_t len_a, size_t
   }
   print_part(result->result_b, result->result_a, result->pos_b, result->len_b, seq_b, ls_b, rs_b, ctx_l - ls_b, ctx_r - rs_b);
   printf("\n");
-  fflush(stdout);
+  /* flushed per hit where someone waits for it; a batch is flushed once (same bytes) */
+  if(opt.interactive) fflush(stdout);
 }
 
 /* pair header up to the blank line (reference sw_cmdline.c:157-190) */
@@ -182,10 +186,13 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
     }
     if(opt.max_hits_set && opt.max_hits < HIT_CAP) cap = opt.max_hits ? opt.max_hits : 1;
     seqalign_batch_set_hit_limits(eng, cap, min_all < 1 ? 1 : min_all);
+    const double t0 = sa_now();
     const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, a, la, b, lb, n);
+    sa_t_align += sa_now() - t0;
     if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0; /* single-pair API handles both */
     else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
   }
+  const double t1 = sa_now();
   for(size_t i = 0; i < n; i++) {
     const char *na = name_a ? name_a[i] : NULL, *nb = name_b ? name_b[i] : NULL;
     if(!batch_ok) { align_single(a[i], b[i], na, nb); continue; }
@@ -199,7 +206,6 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
       if(result->score >= min_score) { align_single(a[i], b[i], na, nb); continue; }
     }
     print_header(a[i], b[i], na, nb, la[i], lb[i], NULL);
-    fflush(stdout);
     size_t hit_index = 0;
     for(size_t h = 0; h < nh && hit_index < want; h++) {
       if(seqalign_batch_hit(eng, i, h, result) != 1) break;
@@ -207,9 +213,10 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
       print_hit(a[i], b[i], la[i], lb[i], hit_index++);
     }
     fputs("==\n", stdout);
-    fflush(stdout);
     alignment_index++;
   }
+  fflush(stdout);
+  sa_t_print += sa_now() - t1;
 }
 
 static void flush_pairs(sa_pairs *p, sa_reader *r)
@@ -247,12 +254,13 @@ int main(int argc, char **argv)
   for(size_t i = 0; i < opt.nfiles; i++) {
     const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
     if(f1 && *f1 == '\0' && !f2) { wait_on_keystroke = 1; f1 = "-"; }
-    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, &pairs, flush_pairs);
+    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, SW_BATCH_PAIRS, &pairs, flush_pairs);
   }
   sa_pairs_free(&pairs);
   smith_waterman_free(sw);
   alignment_free(result);
   seqalign_batch_destroy(eng);
   sa_cli_free(&opt);
+  sa_timing_report();
   return EXIT_SUCCESS;
 }

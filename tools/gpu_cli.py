@@ -18,9 +18,11 @@ big, small = os.path.join(td, "big.fa"), os.path.join(td, "small.fa")
 write(big, N); write(small, NREF)
 def run(exe, args, path):
     t = time.time()
-    p = subprocess.run([exe] + args + ["--file", path], capture_output=True)
+    p = subprocess.run([exe] + args + ["--file", path], capture_output=True, env=dict(os.environ, SEQALIGN_CLI_TIMING="1"))
     dt = time.time() - t
     assert p.returncode == 0, p.stderr[:500]
+    global last_timing
+    last_timing = p.stderr.decode().strip().split("\n")[-1] if p.stderr else ""
     return dt, p.stdout
 rows = []
 for tool, args in (("needleman_wunsch", ["--printscores"]), ("smith_waterman", ["--maxhits", "1"]), ("smith_waterman", [])):
@@ -30,7 +32,7 @@ for tool, args in (("needleman_wunsch", ["--printscores"]), ("smith_waterman", [
     t_big, out_big = run(ours, args, big)
     row = dict(tool=tool, args=args, pairs=N, seconds=round(t_big, 3), pairs_per_s=round(N / t_big), gcups=round(N * 22500 / t_big / 1e9, 1),
                small_pairs=NREF, small_seconds=round(t_small, 3), stdout_mb=round(len(out_big) / 1e6, 1),
-               marginal_pairs_per_s=round((N - NREF) / max(t_big - t_small, 1e-9)))
+               marginal_pairs_per_s=round((N - NREF) / max(t_big - t_small, 1e-9)), phases=last_timing)
     if os.path.exists(ref):
         t_ref, out_ref = run(ref, args, small)
         # NW output must be identical; SW beyond pair 0 differs by the reference's stale-mask defect
