@@ -14,7 +14,7 @@
 #include "sa_cli.h"
 
 /* SEQALIGN_CLI_TIMING=1: seconds spent reading, aligning and printing, on stderr at exit */
-static double sa_t_read = 0, sa_t_align = 0, sa_t_print = 0;
+static double sa_t_read = 0, sa_t_align = 0, sa_t_print = 0, sa_t_init = 0, sa_t_start = 0;
 static inline double sa_now(void)
 {
   struct timespec ts;
@@ -25,7 +25,8 @@ static inline void sa_timing_report(void)
 {
   const char *e = getenv("SEQALIGN_CLI_TIMING");
   if(e && e[0] == '1')
-    fprintf(stderr, "timing: read %.3f s, align %.3f s, print %.3f s\n", sa_t_read, sa_t_align, sa_t_print);
+    fprintf(stderr, "timing: init %.3f s, read %.3f s, align %.3f s, print %.3f s, total %.3f s\n", sa_t_init, sa_t_read,
+            sa_t_align, sa_t_print, sa_now() - sa_t_start);
 }
 
 typedef struct {

@@ -236,7 +236,9 @@ int main(int argc, char **argv)
   scoring.gap_extend = -1;
   sa_cli_parse(argc, argv, &scoring, SA_TOOL_SW, &opt);
 
+  sa_t_start = sa_now();
   eng = seqalign_batch_create(0);
+  sa_t_init = sa_now() - sa_t_start;
   if(!eng) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); return EXIT_FAILURE; }
   if(seqalign_batch_set_scoring(eng, &scoring) != SEQALIGN_OK) {
     fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));

@@ -1,0 +1,127 @@
+// microbench2.cu -- can packed fp16 (HMNMX2 / HFMA2) carry part of the DP next to
+// the integer DPX ops?  Measures HMNMX2, HFMA2, HFMA2.RELU alone, together with
+// VIADDMNMX.S16x2 / VIMNMX3.S16x2 (do the pipes overlap?), and a whole SW cell in
+// fp16x2 alone and interleaved with the s16x2 cell.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench2 microbench2.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+enum Op { HMAX2, HADD2, HFMA2RELU, DPX, DPX_PLUS_HMAX2, DPX_PLUS_HFMA2, CELL_H16, CELL_S16, CELL_BOTH, NOPS };
+static const char *names[] = {"HMNMX2", "HFMA2 (add.f16x2)", "HFMA2.RELU", "VIADDMNMX.S16x2 x8",
+                              "VIADDMNMX.S16x2 x8 + HMNMX2 x8 (independent)", "VIADDMNMX.S16x2 x8 + HFMA2 x8 (independent)",
+                              "SW cell fp16x2 (4 cell pairs/iter)", "SW cell s16x2 (4 cell pairs/iter)",
+                              "SW cell s16x2 + fp16x2 interleaved (8 cell pairs/iter)"};
+static const int ops_per_iter[] = {8, 8, 8, 8, 16, 16, 0, 0, 0};
+static const int cells_per_iter[] = {0, 0, 0, 0, 0, 0, 8, 8, 16};
+
+__device__ __forceinline__ unsigned hmax2(unsigned a, unsigned b) { unsigned d; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hadd2(unsigned a, unsigned b) { unsigned d; asm volatile("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hfma2relu(unsigned a, unsigned b, unsigned c) { unsigned d; asm volatile("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+template <int OP>
+__global__ void __launch_bounds__(256) bench(int iters, int seed, unsigned one, unsigned hone, int *sink)
+{
+  unsigned v[8], u[8];
+#pragma unroll
+  for(int k = 0; k < 8; k++) { v[k] = threadIdx.x * (k + 1) + seed; u[k] = 0x3c003c00u + ((threadIdx.x + k) & 7); }
+  unsigned a = seed * 3 + 1, b = 0xffffffffu /* -1,-1 */, hb = 0xbc00bc00u /* -1.0,-1.0 */, hopen = 0xc200c200u /* -3,-3 */;
+  unsigned c = seed, hc = 0;
+  unsigned w = seed * 0x01010101u;
+  for(int i = 0; i < iters; i++) {
+    if(OP == HMAX2) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) u[k] = hmax2(u[k], u[(k + 3) & 7] ^ 1);
+    } else if(OP == HADD2) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) u[k] = hadd2(u[k], hb);
+    } else if(OP == HFMA2RELU) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) u[k] = hfma2relu(u[k], hone, hb);
+    } else if(OP == DPX) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) v[k] = __viaddmax_s16x2(v[k], b, v[(k + 3) & 7]);
+    } else if(OP == DPX_PLUS_HMAX2) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) { v[k] = __viaddmax_s16x2(v[k], b, v[(k + 3) & 7]); u[k] = hmax2(u[k], u[(k + 3) & 7] ^ 1); }
+    } else if(OP == DPX_PLUS_HFMA2) {
+#pragma unroll
+      for(int k = 0; k < 8; k++) { v[k] = __viaddmax_s16x2(v[k], b, v[(k + 3) & 7]); u[k] = hadd2(u[k], hb); }
+    }
+    if(OP == CELL_S16 || OP == CELL_BOTH) {
+      unsigned hl = v[0], gb = v[1], d = v[2], kprev = 0, cc = c;
+#pragma unroll
+      for(int k = 0; k < 4; k++) {
+        unsigned sub;
+        asm volatile("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(sub) : "r"(w + k), "r"(w ^ (unsigned)i));
+        unsigned m = __viaddmax_s16x2(d, sub, 0x00020002u);
+        v[4 + k] = __viaddmax_s16x2(v[4 + k], b, v[k]);
+        gb = __viaddmax_s16x2(gb, b, hl);
+        unsigned h = __vimax3_s16x2(m, v[4 + k], gb);
+        if(k & 1) cc = __vimax3_s16x2(cc, kprev, m);
+        kprev = m;
+        d = v[k];
+        hl = h * one + a;
+        v[k] = hl;
+      }
+      v[1] ^= gb;
+      c = cc;
+    }
+    if(OP == CELL_H16 || OP == CELL_BOTH) {
+      // the same cell in packed fp16: M = relu(d*1 + sub); GA = max(GA+ext, H'up); GB likewise;
+      // H = max(max(M,GA),GB); H' = H + open; best = max(best, M)
+      unsigned hl = u[0], gb = u[1], d = u[2], cc = hc;
+#pragma unroll
+      for(int k = 0; k < 4; k++) {
+        unsigned sub;
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(sub) : "r"(w + k), "r"(0x40004000u ^ (unsigned)(i & 1)));
+        unsigned m = hfma2relu(d, hone, sub);
+        u[4 + k] = hmax2(hadd2(u[4 + k], hb), u[k]);
+        gb = hmax2(hadd2(gb, hb), hl);
+        unsigned h = hmax2(hmax2(m, u[4 + k]), gb);
+        cc = hmax2(cc, m);
+        d = u[k];
+        hl = hadd2(h, hopen);
+        u[k] = hl;
+      }
+      u[1] ^= gb & 1;
+      hc = cc;
+    }
+  }
+  unsigned s = c ^ hc;
+#pragma unroll
+  for(int k = 0; k < 8; k++) s ^= v[k] ^ u[k];
+  if(s == 0x7fffffff) sink[0] = (int)s;
+}
+
+template <int OP>
+void run(int sms, int clock_khz)
+{
+  const int blocks = sms * 4, threads = 256, iters = 4096;
+  int *sink; cudaMalloc(&sink, 4);
+  bench<OP><<<blocks, threads>>>(16, 1, 1u, 0x3c003c00u, sink);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  bench<OP><<<blocks, threads>>>(iters, 3, 1u, 0x3c003c00u, sink);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double total = (double)blocks * threads * iters;
+  printf("{\"op\": \"%s\", \"ms\": %.3f, \"lane_ops_per_clk_per_sm\": %.1f, \"cell_pairs_gcups_x2\": %.1f}\n", names[OP], ms,
+         total * ops_per_iter[OP] / ms / 1e6 * 1e9 / (sms * (double)clock_khz * 1e3), total * cells_per_iter[OP] / ms / 1e6);
+  cudaFree(sink);
+}
+
+int main()
+{
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, p.multiProcessorCount, p.clockRate);
+  run<HMAX2>(p.multiProcessorCount, p.clockRate);
+  run<HADD2>(p.multiProcessorCount, p.clockRate);
+  run<HFMA2RELU>(p.multiProcessorCount, p.clockRate);
+  run<DPX>(p.multiProcessorCount, p.clockRate);
+  run<DPX_PLUS_HMAX2>(p.multiProcessorCount, p.clockRate);
+  run<DPX_PLUS_HFMA2>(p.multiProcessorCount, p.clockRate);
+  run<CELL_H16>(p.multiProcessorCount, p.clockRate);
+  run<CELL_S16>(p.multiProcessorCount, p.clockRate);
+  run<CELL_BOTH>(p.multiProcessorCount, p.clockRate);
+  return 0;
+}
