@@ -548,6 +548,28 @@ __device__ __forceinline__ unsigned pack_sub2_dyn(unsigned wlo, unsigned whi, in
   }
 }
 
+/* N loads of W words each from the profile rows at shared addresses pl / ph */
+template <int N, int W, int Q = 0, int KWT>
+__device__ __forceinline__ void fast16_load_rows(unsigned pl, unsigned ph, unsigned (&wl)[KWT], unsigned (&wh)[KWT],
+                                                 const unsigned char *dsm)
+{
+  if constexpr(Q < N) {
+    if constexpr(W == 4) {
+      const uint4 u = lds_b128<16 * Q>(pl, dsm), v = lds_b128<16 * Q>(ph, dsm);
+      wl[4 * Q] = u.x; wl[4 * Q + 1] = u.y; wl[4 * Q + 2] = u.z; wl[4 * Q + 3] = u.w;
+      wh[4 * Q] = v.x; wh[4 * Q + 1] = v.y; wh[4 * Q + 2] = v.z; wh[4 * Q + 3] = v.w;
+    } else if constexpr(W == 2) {
+      const uint2 u = lds_b64<8 * Q>(pl, dsm), v = lds_b64<8 * Q>(ph, dsm);
+      wl[2 * Q] = u.x; wl[2 * Q + 1] = u.y;
+      wh[2 * Q] = v.x; wh[2 * Q + 1] = v.y;
+    } else {
+      wl[Q] = lds_b32<4 * Q>(pl, dsm);
+      wh[Q] = lds_b32<4 * Q>(ph, dsm);
+    }
+    fast16_load_rows<N, W, Q + 1>(pl, ph, wl, wh, dsm);
+  }
+}
+
 template <int G, int K>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast16_kernel(const FastArgs A)
@@ -700,39 +722,38 @@ fast16_kernel(const FastArgs A)
 #pragma unroll
     for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
     const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
-    const unsigned *prow_lo = (const unsigned *)s_prof + lane * KW;
-    const unsigned *prow_hi = prow_lo + n * (PSTRIDE / 4);
+    const unsigned prow_lo = smem_addr(s_prof, dsm) + (unsigned)lane * (KW * 4);
+    const unsigned prow_hi = prow_lo + (unsigned)n * PSTRIDE;
+    /* Everything of the row step that is not the recurrence stays off the ALU
+     * pipe (it is the saturated one): the column-0 constants of a pair's first
+     * lane come from multiply-adds with per-lane constants instead of selects,
+     * the row's position in seq_b is a running shared-memory offset advanced
+     * by an IMAD, and the codes of the next row are fetched one step ahead. */
+    const unsigned nf = (unsigned)pin_reg(lig != 0), gbc = (unsigned)pin_reg(lig == 0 ? (int)BB : 0);
+    unsigned ilo = smem_addr(rb_lo, dsm) - (unsigned)lig, ihi = smem_addr(cb_hi, dsm) - (unsigned)lig;
+    unsigned clo = lds_u8(ilo, dsm), chi = lds_u8(ihi, dsm);   /* row 1 of lane 0; later lanes read slack bytes they do not use */
 
     for(int s = 0; s < nsteps; s++) {
-      const int y = s - lig + 1;
-      const bool active = y >= 1 && y <= lb;
-      unsigned hl = __shfl_up_sync(FULL, out_h, 1);
-      unsigned gb = __shfl_up_sync(FULL, out_gb, 1);
-      if(lig == 0) { hl = 0; gb = BB; }     /* column 0 */
+      const bool active = (unsigned)(s - lig) < (unsigned)lb;   /* 1 <= y <= lb, y = s - lig + 1 */
+      unsigned hl = __shfl_up_sync(FULL, out_h, 1) * nf;        /* column 0: H'* = 0 */
+      unsigned gb = __shfl_up_sync(FULL, out_gb, 1) * nf + gbc; /*           GB* = B  */
       const unsigned hl_in = hl;
+      const unsigned cl = clo, ch = chi;
+      ilo = ilo * mul_one + 1u;
+      ihi = ihi * mul_one + 1u;
+      clo = lds_u8(ilo, dsm); chi = lds_u8(ihi, dsm);
       if(active) {
-        const unsigned *pl = prow_lo + rb_lo[y - 1] * (PSTRIDE / 4);
-        const unsigned *ph = prow_hi + cb_hi[y - 1] * (PSTRIDE / 4);
+        /* profile rows of the two codes, through 32-bit shared addresses (row
+         * offset by IMAD); widest loads the lane stride (KW words) allows --
+         * scalar loads with an even stride would be 2- or 4-way bank conflicts */
+        const unsigned pl = cl * (unsigned)PSTRIDE + prow_lo, ph = ch * (unsigned)PSTRIDE + prow_hi;
         unsigned wl[KW], wh[KW];
-        /* widest loads the lane stride (KW words) allows; scalar loads with an
-         * even stride would be 2- or 4-way bank conflicts */
         if constexpr(KW % 4 == 0) {
-#pragma unroll
-          for(int q = 0; q < KW / 4; q++) {
-            const uint4 u = ((const uint4 *)pl)[q], v = ((const uint4 *)ph)[q];
-            wl[4 * q] = u.x; wl[4 * q + 1] = u.y; wl[4 * q + 2] = u.z; wl[4 * q + 3] = u.w;
-            wh[4 * q] = v.x; wh[4 * q + 1] = v.y; wh[4 * q + 2] = v.z; wh[4 * q + 3] = v.w;
-          }
+          fast16_load_rows<KW / 4, 4>(pl, ph, wl, wh, dsm);
         } else if constexpr(KW % 2 == 0) {
-#pragma unroll
-          for(int q = 0; q < KW / 2; q++) {
-            const uint2 u = ((const uint2 *)pl)[q], v = ((const uint2 *)ph)[q];
-            wl[2 * q] = u.x; wl[2 * q + 1] = u.y;
-            wh[2 * q] = v.x; wh[2 * q + 1] = v.y;
-          }
+          fast16_load_rows<KW / 2, 2>(pl, ph, wl, wh, dsm);
         } else {
-#pragma unroll
-          for(int q = 0; q < KW; q++) { wl[q] = pl[q]; wh[q] = ph[q]; }
+          fast16_load_rows<KW, 1>(pl, ph, wl, wh, dsm);
         }
         unsigned d = hd, kprev = BB;
 #pragma unroll
@@ -855,7 +876,8 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
   plan->a_stage = (int)((G * K + 15 + 15) & ~15) + 16;
-  plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16;
+  /* (the packed kernel prefetches seq_b codes one row ahead in every lane: up to G+1 bytes past the end) */
+  plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16 + (s16 ? 48 : 0);
   plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
   if(s16) {
     const size_t warp_bytes = 2 * (size_t)n * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);

@@ -131,6 +131,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
       "}\n" ::"r"(smem_u32(bar)), "r"(phase)
       : "memory");
 }
+/* byte loads through a 32-bit shared-memory address kept in a register (the
+ * hot loops advance it with an IMAD, off the ALU pipe); `base` is the start
+ * of dynamic shared memory and only used by the host-side emulation */
+__device__ __forceinline__ unsigned smem_addr(const void *p, const unsigned char *) { return smem_u32(p); }
+__device__ __forceinline__ unsigned lds_u8(unsigned addr, const unsigned char *)
+{
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned lds_b32(unsigned addr, const unsigned char *)
+{
+  unsigned v;
+  asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint2 lds_b64(unsigned addr, const unsigned char *)
+{
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint4 lds_b128(unsigned addr, const unsigned char *)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+  return v;
+}
 /* make generic-proxy smem writes/reads ordered against the async proxy */
 __device__ __forceinline__ void fence_async_smem()
 {
@@ -147,6 +178,11 @@ __host__ __device__ inline void bulk_g2s(void *dst, const void *src, uint32_t by
   for(uint32_t i = 0; i < bytes; i++) d[i] = s[i];
 }
 __host__ __device__ inline void mbar_wait(uint64_t *, uint32_t) {}
+__host__ __device__ inline unsigned smem_addr(const void *p, const unsigned char *base) { return (unsigned)((const unsigned char *)p - base); }
+__host__ __device__ inline unsigned lds_u8(unsigned addr, const unsigned char *base) { return base[addr]; }
+template <int OFF> inline unsigned lds_b32(unsigned addr, const unsigned char *base) { return *(const unsigned *)(base + addr + OFF); }
+template <int OFF> inline uint2 lds_b64(unsigned addr, const unsigned char *base) { return *(const uint2 *)(base + addr + OFF); }
+template <int OFF> inline uint4 lds_b128(unsigned addr, const unsigned char *base) { return *(const uint4 *)(base + addr + OFF); }
 __host__ __device__ inline void fence_async_smem() {}
 #endif
 
