@@ -100,17 +100,38 @@ def gather_results(local, bounds, dst=0, group=None):
     return torch.cat([bucket[r][:, : counts[r]] for r in range(world)], dim=1)
 
 
-def align_sharded(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, src=0, device="cpu", group=None):
+def align_sharded(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, src=0, device="cpu", group=None,
+                  want_ends=True, timings=None):
     """Score mode over all ranks: scatter from `src`, align locally, gather
-    (score, x_end, y_end) back to `src` as an int32 tensor [3, n]."""
+    (score, x_end, y_end) back to `src` as an int32 tensor [3, n].
+    want_ends=False (CUDA tensors): scores only, rows 1-2 stay 0 and the engine
+    may use its packed 16-bit kernel.  timings: dict that receives the seconds
+    spent in scatter / align / gather on this rank (device synchronised)."""
+    import time
+
+    def tick():
+        if timings is not None and str(device) != "cpu":
+            torch.cuda.synchronize()
+        return time.perf_counter()
+
+    t0 = tick()
     a, oa, b, ob, _, bounds = scatter_pairs(seq_a, off_a, seq_b, off_b, src, device, group)
+    t1 = tick()
     n_local = oa.numel() - 1
     if a.is_cuda:
         out = torch.zeros((3, n_local), dtype=torch.int32, device=a.device)
         if n_local:
             engine.run_device(algo, a.data_ptr(), oa.data_ptr(), b.data_ptr(), ob.data_ptr(), n_local,
-                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              out[0].data_ptr(), out[1].data_ptr() if want_ends else 0,
+                              out[2].data_ptr() if want_ends else 0,
                               torch.cuda.current_stream().cuda_stream)
+        t2 = tick()
+        res = gather_results(out, bounds, src, group)
+        t3 = tick()
+        if timings is not None:
+            timings.update(scatter=t1 - t0, align=t2 - t1, gather=t3 - t2, kernel_ms=engine.last_kernel_ms,
+                           kernel=engine.last_kernel, n_local=n_local)
+        return res
     else:
         engine.submit_packed(algo, MODE_SCORE, a.numpy(), oa.numpy(), b.numpy(), ob.numpy())
         out = torch.from_numpy(np.stack(engine.ends()).astype(np.int32))
