@@ -40,47 +40,68 @@ def shard_bounds(off_a, off_b, world):
 
 def _as_tensor(x, device):
     t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
-    return t.to(device)
+    return t.to(device, non_blocking=True)
+
+
+def shard_bounds_tensor(toa, tob, world):
+    """shard_bounds() on int64 offset tensors, computed where they live (for a
+    batch that is already on the GPU this avoids a host pass over every pair)"""
+    n = toa.numel() - 1
+    if n <= 0:
+        return [0] * (world + 1)
+    w = torch.cumsum(toa.diff() * tob.diff() + 1, 0)
+    total = int(w[-1].item())
+    # same cut points as the numpy version: first index with w > total*r/world (float64 targets)
+    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64, device=w.device)
+    cuts = torch.searchsorted(w.to(torch.float64), targets, right=True).tolist() if world > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [n]
+    for r in range(1, world + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return bounds
 
 
 def scatter_pairs(seq_a, off_a, seq_b, off_b, src=0, device="cpu", group=None):
     """Rank `src` passes the packed batch (numpy arrays or tensors; other ranks
     pass None) and every rank gets back its shard as tensors on `device`:
-    (seq_a, off_a, seq_b, off_b, first_pair, bounds), offsets rebased to 0."""
+    (seq_a, off_a, seq_b, off_b, first_pair, bounds), offsets rebased to 0.
+    The shard table is computed on `device`, the shards travel as ONE grouped
+    send/recv (dist.batch_isend_irecv: NCCL over NVLink for CUDA tensors)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     meta = torch.zeros(3 * (world + 1), dtype=torch.int64, device=device)
     if rank == src:
-        off_a = np.asarray(off_a, dtype=np.int64)
-        off_b = np.asarray(off_b, dtype=np.int64)
-        bounds = shard_bounds(off_a, off_b, world)
-        meta[: world + 1] = torch.tensor(bounds)
-        meta[world + 1: 2 * (world + 1)] = torch.tensor(off_a[bounds])
-        meta[2 * (world + 1):] = torch.tensor(off_b[bounds])
-    dist.broadcast(meta, src, group=group)
+        toa = _as_tensor(off_a, device).to(torch.int64)
+        tob = _as_tensor(off_b, device).to(torch.int64)
+        bounds = shard_bounds_tensor(toa, tob, world)
+        bt = torch.tensor(bounds, device=device)
+        meta[: world + 1] = bt
+        meta[world + 1: 2 * (world + 1)] = toa[bt]
+        meta[2 * (world + 1):] = tob[bt]
+    if world > 1:
+        dist.broadcast(meta, src, group=group)
     m = meta.cpu().numpy()
     bounds, ba, bb = m[: world + 1], m[world + 1: 2 * (world + 1)], m[2 * (world + 1):]
     n_local = int(bounds[rank + 1] - bounds[rank])
-    mine = [torch.empty(int(ba[rank + 1] - ba[rank]), dtype=torch.uint8, device=device),
-            torch.empty(n_local + 1, dtype=torch.int64, device=device),
-            torch.empty(int(bb[rank + 1] - bb[rank]), dtype=torch.uint8, device=device),
-            torch.empty(n_local + 1, dtype=torch.int64, device=device)]
     if rank == src:
         ta, tb = _as_tensor(seq_a, device), _as_tensor(seq_b, device)
-        toa, tob = _as_tensor(off_a, device), _as_tensor(off_b, device)
-        reqs = []
+        ops, keep, mine = [], [], None
         for r in range(world):
             parts = [ta[ba[r]: ba[r + 1]], toa[bounds[r]: bounds[r + 1] + 1] - int(ba[r]),
                      tb[bb[r]: bb[r + 1]], tob[bounds[r]: bounds[r + 1] + 1] - int(bb[r])]
             if r == src:
-                for dst_t, p in zip(mine, parts):
-                    dst_t.copy_(p)
+                mine = parts            # views of the source buffers: no copy for the local shard
             else:
-                reqs += [dist.isend(p.contiguous(), r, group=group) for p in parts]
-        for q in reqs:
-            q.wait()
+                keep += parts
+                ops += [dist.P2POp(dist.isend, p, r, group) for p in parts]
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
     else:
-        for t in mine:
-            dist.recv(t, src, group=group)
+        mine = [torch.empty(int(ba[rank + 1] - ba[rank]), dtype=torch.uint8, device=device),
+                torch.empty(n_local + 1, dtype=torch.int64, device=device),
+                torch.empty(int(bb[rank + 1] - bb[rank]), dtype=torch.uint8, device=device),
+                torch.empty(n_local + 1, dtype=torch.int64, device=device)]
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, t, src, group) for t in mine]):
+            q.wait()
     return mine[0], mine[1], mine[2], mine[3], int(bounds[rank]), [int(v) for v in bounds]
 
 

@@ -29,6 +29,14 @@ def test_shard_bounds_balanced():
     assert b[0] == 0 and b[2] == 200 and 140 < b[1] < 160
     cells = la * la
     assert abs(cells[:b[1]].sum() - cells[b[1]:].sum()) < 0.05 * cells.sum()
+    # the tensor version (used by scatter_pairs, runs where the offsets live) cuts at the same places
+    from seqalign.distributed import shard_bounds_tensor
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        la = rng.integers(0, 300, 5000); lb = rng.integers(0, 300, 5000)
+        oa = np.concatenate([[0], np.cumsum(la)]); ob = np.concatenate([[0], np.cumsum(lb)])
+        assert shard_bounds_tensor(torch.from_numpy(oa), torch.from_numpy(ob), world) == shard_bounds(oa, ob, world)
+    assert shard_bounds_tensor(torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64), 3) == [0, 0, 0, 0]
 
 
 def _worker(rank, world, port, lib, seed, out_path):

@@ -37,7 +37,7 @@ if rank == 0:
     ua = np.concatenate([p[0] for p in parts]); ub = np.concatenate([p[2] for p in parts])
     reps = TOTAL // UNIQUE
     seq_a = torch.from_numpy(np.tile(ua, reps)).pin_memory(); seq_b = torch.from_numpy(np.tile(ub, reps)).pin_memory()
-    off_a = np.arange(0, (TOTAL + 1) * L, L, dtype=np.int64); off_b = off_a.copy()
+    off_a = torch.from_numpy(np.arange(0, (TOTAL + 1) * L, L, dtype=np.int64)).pin_memory(); off_b = off_a.clone().pin_memory()
     print("rank 0: %d pairs (%d unique) built in %.1f s, %.2f GB" % (TOTAL, UNIQUE, time.time() - t, 2 * seq_a.numel() / 1e9), file=sys.stderr, flush=True)
 rows = []
 for rep in range(3):
@@ -68,10 +68,10 @@ for rep in range(3):
 if rank == 0:
     # parity of the first 100k pairs against a plain one-GPU host-buffer run
     n = 100000
-    eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, seq_a[: n * L].numpy(), off_a[: n + 1], seq_b[: n * L].numpy(), off_b[: n + 1])
+    eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, seq_a[: n * L].numpy(), off_a[: n + 1].numpy(), seq_b[: n * L].numpy(), off_b[: n + 1].numpy())
     same = bool(np.array_equal(eng.scores(), scores[:n].cpu().numpy()))
     o = orc_from_scoring(seqalign.Scoring.sw_cli_default())
-    es, _, _ = orc_batch_sw(o, seq_a[: 2000 * L].numpy(), off_a[:2001], seq_b[: 2000 * L].numpy(), off_b[:2001])
+    es, _, _ = orc_batch_sw(o, seq_a[: 2000 * L].numpy(), off_a[:2001].numpy(), seq_b[: 2000 * L].numpy(), off_b[:2001].numpy())
     oracle_same = bool(np.array_equal(es, scores[:2000].cpu().numpy()))
     print(json.dumps(dict(first_100k_same_as_one_gpu=same, first_2000_same_as_oracle=oracle_same)), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
