@@ -157,3 +157,58 @@ def align_sharded(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, 
         engine.submit_packed(algo, MODE_SCORE, a.numpy(), oa.numpy(), b.numpy(), ob.numpy())
         out = torch.from_numpy(np.stack(engine.ends()).astype(np.int32))
     return gather_results(out, bounds, src, group)
+
+
+def share_cuda_tensors(tensors, src=0, group=None):
+    """CUDA IPC: rank `src` passes device tensors, every other rank gets tensors
+    that alias the SAME memory on src's GPU (cudaIpcOpenMemHandle with lazy peer
+    access, through torch's own reductions).  Kernels of the other ranks then
+    read it over NVLink / NVSwitch directly -- nothing is copied."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    rank = dist.get_rank(group)
+    box = [[reduce_tensor(t) for t in tensors] if rank == src else None]
+    dist.broadcast_object_list(box, src, group=group)
+    if rank == src:
+        return list(tensors)
+    return [fn(*args) for fn, args in box[0]]
+
+
+def align_sharded_peer(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, src=0, group=None,
+                       want_ends=False, timings=None):
+    """align_sharded() without the scatter: the batch stays in the HBM of rank
+    `src` (CUDA tensors there, None elsewhere); every rank maps it through CUDA
+    IPC and its DP kernel pulls its own pair range over NVLink while it computes
+    (TMA bulk loads from peer memory: 0.0135 B/cell, ~65 GB/s per GPU at full
+    speed, far below a link).  Only the scores travel back (gather).  Returns
+    [3, n] int32 on `src` like align_sharded."""
+    import time
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def tick():
+        torch.cuda.synchronize()
+        return time.perf_counter()
+
+    t0 = tick()
+    a, oa, b, ob = share_cuda_tensors([seq_a, off_a, seq_b, off_b] if rank == src else None, src, group)
+    box = [shard_bounds_tensor(oa, ob, world) if rank == src else None]
+    dist.broadcast_object_list(box, src, group=group)
+    bounds = box[0]
+    first, n_local = bounds[rank], bounds[rank + 1] - bounds[rank]
+    t1 = tick()
+    out = torch.zeros((3, n_local), dtype=torch.int32, device=dev)
+    if n_local:
+        # offsets stay absolute: the kernels address seq + off[p], so a shard is just a window of the offset arrays
+        engine.run_device(algo, a.data_ptr(), oa.data_ptr() + 8 * first, b.data_ptr(), ob.data_ptr() + 8 * first, n_local,
+                          out[0].data_ptr(), out[1].data_ptr() if want_ends else 0, out[2].data_ptr() if want_ends else 0,
+                          torch.cuda.current_stream().cuda_stream)
+    t2 = tick()
+    res = gather_results(out, bounds, src, group)
+    t3 = tick()
+    if timings is not None:
+        timings.update(scatter=t1 - t0, align=t2 - t1, gather=t3 - t2, kernel_ms=engine.last_kernel_ms,
+                       kernel=engine.last_kernel, n_local=n_local)
+    del a, oa, b, ob
+    dist.barrier(group=group)   # the owner may reuse the buffers only after every reader is done
+    return res
+

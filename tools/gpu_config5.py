@@ -17,10 +17,12 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from helpers import *
-from seqalign.distributed import align_sharded
+from seqalign.distributed import align_sharded, align_sharded_peer
 
-TOTAL = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-UNIQUE = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+PEER = "--peer" in sys.argv   # zero-copy: ranks read rank 0's HBM over NVLink instead of receiving a scatter
+argv = [x for x in sys.argv[1:] if not x.startswith("--")]
+TOTAL = int(argv[0]) if len(argv) > 0 else 10_000_000
+UNIQUE = int(argv[1]) if len(argv) > 1 else 1_000_000
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -48,10 +50,17 @@ for rep in range(3):
         da, db = seq_a.to(dev, non_blocking=True), seq_b.to(dev, non_blocking=True)   # host -> GPU 0 over PCIe
         torch.cuda.synchronize()
         t_h2d = time.perf_counter() - t0
-        res = align_sharded(eng, seqalign.SW, da, off_a, db, off_b, src=0, device=dev, want_ends=False, timings=tm)
+        if PEER:
+            doa, dob = off_a.to(dev, non_blocking=True), off_b.to(dev, non_blocking=True)
+            res = align_sharded_peer(eng, seqalign.SW, da, doa, db, dob, src=0, want_ends=False, timings=tm)
+        else:
+            res = align_sharded(eng, seqalign.SW, da, off_a, db, off_b, src=0, device=dev, want_ends=False, timings=tm)
     else:
         t_h2d = 0.0
-        res = align_sharded(eng, seqalign.SW, src=0, device=dev, want_ends=False, timings=tm)
+        if PEER:
+            res = align_sharded_peer(eng, seqalign.SW, src=0, want_ends=False, timings=tm)
+        else:
+            res = align_sharded(eng, seqalign.SW, src=0, device=dev, want_ends=False, timings=tm)
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
     stats = torch.tensor([tm["scatter"], tm["align"], tm["gather"], tm["kernel_ms"] / 1e3, t_all], device=dev, dtype=torch.float64)
@@ -60,7 +69,7 @@ for rep in range(3):
         scores = res[0]
         cells = TOTAL * L * L
         sc, al, ga, km, ta = [float(x) for x in stats.tolist()]
-        rows.append(dict(rep=rep, n_gpus=world, pairs=TOTAL, h2d_rank0_s=round(t_h2d, 4), scatter_s=round(sc, 4), align_s=round(al, 4),
+        rows.append(dict(rep=rep, mode="peer" if PEER else "scatter", n_gpus=world, pairs=TOTAL, h2d_rank0_s=round(t_h2d, 4), scatter_s=round(sc, 4), align_s=round(al, 4),
                          gather_s=round(ga, 4), kernel_s_max=round(km, 4), total_s=round(ta, 4), kernel=tm["kernel"],
                          gcups_align=round(cells / al / 1e9, 1), gcups_from_gpu0=round(cells / (sc + al + ga) / 1e9, 1),
                          gcups_from_host=round(cells / ta / 1e9, 1), checksum=int(scores.to(torch.int64).sum().item())))
@@ -76,6 +85,6 @@ if rank == 0:
     print(json.dumps(dict(first_100k_same_as_one_gpu=same, first_2000_same_as_oracle=oracle_same)), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(dict(rows=rows, first_100k_same_as_one_gpu=same, first_2000_same_as_oracle=oracle_same),
-              open(os.path.join(ROOT, "gpurun_out", "config5_n%d.json" % world), "w"), indent=1)
+              open(os.path.join(ROOT, "gpurun_out", "config5_%s_n%d.json" % ("peer" if PEER else "scatter", world)), "w"), indent=1)
 eng.close()
 dist.destroy_process_group()
