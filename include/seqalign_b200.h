@@ -135,6 +135,15 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
                               size_t n, void *d_score, void *d_x_end,
                               void *d_y_end, void *stream);
 
+/* Let the kernels of `device` read buffers that live on `peer` (same node,
+ * NVLink / NVSwitch): cudaDeviceEnablePeerAccess.  With it the device
+ * pointers handed to seqalign_batch_run_device may be peer memory, e.g. a
+ * batch held by another rank and mapped through CUDA IPC -- the DP kernels'
+ * bulk loads then pull the sequences across NVLink while they compute and no
+ * scatter step is needed (seqalign.distributed.align_sharded_peer).  The
+ * reference has no counterpart (single process, single thread). */
+int seqalign_enable_peer_access(int device, int peer);
+
 /* seqalign_batch_run_device launches speculatively with the previous run's
  * plan (same scoring, algorithm and outputs) and verifies against this
  * batch's scan afterwards; these count how often the guess held / was redone. */

@@ -1012,6 +1012,20 @@ int seqalign_device_count(void)
 
 const char *seqalign_version(void) { return "seqalign_b200 0.1 (sm_100a)"; }
 
+int seqalign_enable_peer_access(int device, int peer)
+{
+  if(device == peer) return SEQALIGN_OK;
+  int can = 0;
+  if(cudaSetDevice(device) != cudaSuccess || cudaDeviceCanAccessPeer(&can, device, peer) != cudaSuccess || !can) {
+    cudaGetLastError();
+    return SEQALIGN_ERR_CUDA;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  cudaGetLastError();
+  return SEQALIGN_OK;
+}
+
 const char *seqalign_last_create_error(void) { return g_create_error.c_str(); }
 
 seqalign_batch_t *seqalign_batch_create(int device)

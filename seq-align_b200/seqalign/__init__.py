@@ -117,6 +117,7 @@ def load():
     vp, sz, i32p = ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)
     L.seqalign_device_count.restype = ctypes.c_int
     L.seqalign_version.restype = ctypes.c_char_p
+    L.seqalign_enable_peer_access.argtypes = [ctypes.c_int, ctypes.c_int]
     L.seqalign_last_create_error.restype = ctypes.c_char_p
     L.seqalign_batch_create.restype = vp
     L.seqalign_batch_create.argtypes = [ctypes.c_int]
@@ -484,3 +485,11 @@ class PipelinedAligner:
         self._pool.shutdown(wait=True)
         for e in self._all:
             e.close()
+
+
+def enable_peer_access(device, peer):
+    """kernels of `device` may read memory of `peer` (NVLink); see seqalign_enable_peer_access"""
+    rc = load().seqalign_enable_peer_access(int(device), int(peer))
+    if rc != 0:
+        raise SeqAlignError(rc, "device %d cannot access device %d as a peer" % (device, peer))
+

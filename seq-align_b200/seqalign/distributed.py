@@ -191,6 +191,9 @@ def align_sharded_peer(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=N
 
     t0 = tick()
     a, oa, b, ob = share_cuda_tensors([seq_a, off_a, seq_b, off_b] if rank == src else None, src, group)
+    if a.device != dev:
+        from . import enable_peer_access
+        enable_peer_access(dev.index, a.device.index)
     box = [shard_bounds_tensor(oa, ob, world) if rank == src else None]
     dist.broadcast_object_list(box, src, group=group)
     bounds = box[0]
