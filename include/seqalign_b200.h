@@ -144,6 +144,19 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
  * reference has no counterpart (single process, single thread). */
 int seqalign_enable_peer_access(int device, int peer);
 
+/* A batch that one process holds in the HBM of its GPU and other processes
+ * (one per GPU, same node) align in place: the owner allocates the buffer
+ * and passes the 64-byte handle to its peers by any means (MPI, a pipe,
+ * torch.distributed); a peer opens it ON ITS OWN DEVICE, which maps the
+ * owner's memory for that device's kernels (cudaIpcOpenMemHandle with lazy
+ * peer access, NVLink / NVSwitch).  Pointers into the mapping are valid
+ * arguments of seqalign_batch_run_device on the peer. */
+typedef struct { unsigned char bytes[64]; } seqalign_ipc_handle_t;
+int seqalign_shared_alloc(int device, size_t bytes, void **d_ptr, seqalign_ipc_handle_t *handle);
+int seqalign_shared_free(int device, void *d_ptr);
+int seqalign_shared_open(int device, const seqalign_ipc_handle_t *handle, void **d_ptr);
+int seqalign_shared_close(int device, void *d_ptr);
+
 /* seqalign_batch_run_device launches speculatively with the previous run's
  * plan (same scoring, algorithm and outputs) and verifies against this
  * batch's scan afterwards; these count how often the guess held / was redone. */

@@ -1012,6 +1012,41 @@ int seqalign_device_count(void)
 
 const char *seqalign_version(void) { return "seqalign_b200 0.1 (sm_100a)"; }
 
+int seqalign_shared_alloc(int device, size_t bytes, void **d_ptr, seqalign_ipc_handle_t *handle)
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(seqalign_ipc_handle_t), "handle size");
+  if(!d_ptr || !handle) return SEQALIGN_ERR_ARG;
+  *d_ptr = nullptr;
+  cudaIpcMemHandle_t h;
+  if(cudaSetDevice(device) != cudaSuccess || cudaMalloc(d_ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_NOMEM; }
+  if(cudaIpcGetMemHandle(&h, *d_ptr) != cudaSuccess) { cudaGetLastError(); cudaFree(*d_ptr); *d_ptr = nullptr; return SEQALIGN_ERR_CUDA; }
+  memcpy(handle->bytes, &h, sizeof(h));
+  return SEQALIGN_OK;
+}
+
+int seqalign_shared_free(int device, void *d_ptr)
+{
+  if(cudaSetDevice(device) != cudaSuccess || cudaFree(d_ptr) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  return SEQALIGN_OK;
+}
+
+int seqalign_shared_open(int device, const seqalign_ipc_handle_t *handle, void **d_ptr)
+{
+  if(!d_ptr || !handle) return SEQALIGN_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle->bytes, sizeof(h));
+  /* opened with `device` current: the mapping is made for this device's kernels */
+  if(cudaSetDevice(device) != cudaSuccess ||
+     cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  return SEQALIGN_OK;
+}
+
+int seqalign_shared_close(int device, void *d_ptr)
+{
+  if(cudaSetDevice(device) != cudaSuccess || cudaIpcCloseMemHandle(d_ptr) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  return SEQALIGN_OK;
+}
+
 int seqalign_enable_peer_access(int device, int peer)
 {
   if(device == peer) return SEQALIGN_OK;

@@ -118,6 +118,10 @@ def load():
     L.seqalign_device_count.restype = ctypes.c_int
     L.seqalign_version.restype = ctypes.c_char_p
     L.seqalign_enable_peer_access.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.seqalign_shared_alloc.argtypes = [ctypes.c_int, sz, ctypes.POINTER(vp), vp]
+    L.seqalign_shared_free.argtypes = [ctypes.c_int, vp]
+    L.seqalign_shared_open.argtypes = [ctypes.c_int, vp, ctypes.POINTER(vp)]
+    L.seqalign_shared_close.argtypes = [ctypes.c_int, vp]
     L.seqalign_last_create_error.restype = ctypes.c_char_p
     L.seqalign_batch_create.restype = vp
     L.seqalign_batch_create.argtypes = [ctypes.c_int]
@@ -492,4 +496,44 @@ def enable_peer_access(device, peer):
     rc = load().seqalign_enable_peer_access(int(device), int(peer))
     if rc != 0:
         raise SeqAlignError(rc, "device %d cannot access device %d as a peer" % (device, peer))
+
+
+class SharedBuffer:
+    """Device memory one process owns and its peers (one process per GPU, same
+    node) map onto their own device (seqalign_shared_alloc / _open).  `handle`
+    is 64 opaque bytes to hand to the peers; `tensor()` views the memory as a
+    torch uint8 tensor without copying."""
+
+    def __init__(self, device, nbytes=None, handle=None):
+        L = load()
+        self.device, self.ptr = int(device), ctypes.c_void_p()
+        self.owner = handle is None
+        if self.owner:
+            buf = ctypes.create_string_buffer(64)
+            rc = L.seqalign_shared_alloc(self.device, int(nbytes), ctypes.byref(self.ptr), buf)
+            self.handle, self.nbytes = buf.raw, int(nbytes)
+        else:
+            rc = L.seqalign_shared_open(self.device, ctypes.create_string_buffer(handle, 64), ctypes.byref(self.ptr))
+            self.handle, self.nbytes = handle, int(nbytes)
+        if rc != 0:
+            raise SeqAlignError(rc, "cannot %s a shared device buffer on device %d" % ("allocate" if self.owner else "open", self.device))
+
+    @property
+    def address(self):
+        return self.ptr.value
+
+    def tensor(self):
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=(self.nbytes,), typestr="|u1", data=(self.ptr.value, False), version=2)
+        return torch.as_tensor(v, device="cuda:%d" % self.device)
+
+    def close(self):
+        if self.ptr.value:
+            L = load()
+            (L.seqalign_shared_free if self.owner else L.seqalign_shared_close)(self.device, self.ptr)
+            self.ptr = ctypes.c_void_p()
 

@@ -159,28 +159,61 @@ def align_sharded(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, 
     return gather_results(out, bounds, src, group)
 
 
-def share_cuda_tensors(tensors, src=0, group=None):
-    """CUDA IPC: rank `src` passes device tensors, every other rank gets tensors
-    that alias the SAME memory on src's GPU (cudaIpcOpenMemHandle with lazy peer
-    access, through torch's own reductions).  Kernels of the other ranks then
-    read it over NVLink / NVSwitch directly -- nothing is copied."""
-    from torch.multiprocessing.reductions import reduce_tensor
-    rank = dist.get_rank(group)
-    box = [[reduce_tensor(t) for t in tensors] if rank == src else None]
-    dist.broadcast_object_list(box, src, group=group)
-    if rank == src:
-        return list(tensors)
-    return [fn(*args) for fn, args in box[0]]
+class SharedBatch:
+    """A packed batch [seq_a | seq_b | off_a | off_b] in ONE device buffer that
+    the owner's peers can map (seqalign.SharedBuffer, CUDA IPC).  The owner
+    fills it once (host -> its GPU); nobody copies it again."""
+
+    def __init__(self, buf, n, ta, tb, pos):
+        self.buf, self.n, self.ta, self.tb, self.pos = buf, n, ta, tb, pos
+        t = buf.tensor()
+        self.seq_a = t[pos[0]: pos[0] + ta]
+        self.seq_b = t[pos[1]: pos[1] + tb]
+        self.off_a = t[pos[2]: pos[2] + 8 * (n + 1)].view(torch.int64)
+        self.off_b = t[pos[3]: pos[3] + 8 * (n + 1)].view(torch.int64)
+
+    @staticmethod
+    def _layout(n, ta, tb):
+        pos, at = [], 0
+        for size in (ta + 32, tb + 32, 8 * (n + 1), 8 * (n + 1)):   # +32: the kernels' 16-byte bulk loads may run past the end
+            pos.append(at)
+            at = (at + size + 255) & ~255
+        return pos, at
+
+    @classmethod
+    def create(cls, device, seq_a, off_a, seq_b, off_b):
+        """owner side: numpy arrays or (pinned) host / device tensors"""
+        from . import SharedBuffer
+        ts = [torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x for x in (seq_a, off_a, seq_b, off_b)]
+        n, ta, tb = ts[1].numel() - 1, ts[0].numel(), ts[2].numel()
+        pos, total = cls._layout(n, ta, tb)
+        sb = cls(SharedBuffer(device, total), n, ta, tb, pos)
+        sb.seq_a.copy_(ts[0].view(torch.uint8), non_blocking=True)
+        sb.seq_b.copy_(ts[2].view(torch.uint8), non_blocking=True)
+        sb.off_a.copy_(ts[1].to(torch.int64), non_blocking=True)
+        sb.off_b.copy_(ts[3].to(torch.int64), non_blocking=True)
+        return sb
+
+    def meta(self):
+        return dict(handle=self.buf.handle, nbytes=self.buf.nbytes, n=self.n, ta=self.ta, tb=self.tb, pos=self.pos)
+
+    @classmethod
+    def open(cls, device, meta):
+        from . import SharedBuffer
+        return cls(SharedBuffer(device, meta["nbytes"], meta["handle"]), meta["n"], meta["ta"], meta["tb"], meta["pos"])
+
+    def close(self):
+        del self.seq_a, self.seq_b, self.off_a, self.off_b
+        self.buf.close()
 
 
-def align_sharded_peer(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=None, src=0, group=None,
-                       want_ends=False, timings=None):
+def align_sharded_peer(engine, algo, batch=None, src=0, group=None, want_ends=False, timings=None):
     """align_sharded() without the scatter: the batch stays in the HBM of rank
-    `src` (CUDA tensors there, None elsewhere); every rank maps it through CUDA
-    IPC and its DP kernel pulls its own pair range over NVLink while it computes
-    (TMA bulk loads from peer memory: 0.0135 B/cell, ~65 GB/s per GPU at full
-    speed, far below a link).  Only the scores travel back (gather).  Returns
-    [3, n] int32 on `src` like align_sharded."""
+    `src` (a SharedBatch there, None elsewhere); every other rank maps it onto
+    its own device through CUDA IPC and its DP kernel pulls its pair range over
+    NVLink while it computes (TMA bulk loads from peer memory: 0.0135 B/cell,
+    ~65 GB/s per GPU at full speed, far below a link).  Only the scores travel
+    back (gather).  Returns [3, n] int32 on `src` like align_sharded."""
     import time
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -190,20 +223,19 @@ def align_sharded_peer(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=N
         return time.perf_counter()
 
     t0 = tick()
-    a, oa, b, ob = share_cuda_tensors([seq_a, off_a, seq_b, off_b] if rank == src else None, src, group)
-    if a.device != dev:
-        from . import enable_peer_access
-        enable_peer_access(dev.index, a.device.index)
-    box = [shard_bounds_tensor(oa, ob, world) if rank == src else None]
+    box = [(batch.meta(), shard_bounds_tensor(batch.off_a, batch.off_b, world)) if rank == src else None]
     dist.broadcast_object_list(box, src, group=group)
-    bounds = box[0]
+    meta, bounds = box[0]
+    mine = batch if rank == src else SharedBatch.open(dev.index, meta)
     first, n_local = bounds[rank], bounds[rank + 1] - bounds[rank]
     t1 = tick()
     out = torch.zeros((3, n_local), dtype=torch.int32, device=dev)
     if n_local:
+        base = mine.buf.address
         # offsets stay absolute: the kernels address seq + off[p], so a shard is just a window of the offset arrays
-        engine.run_device(algo, a.data_ptr(), oa.data_ptr() + 8 * first, b.data_ptr(), ob.data_ptr() + 8 * first, n_local,
-                          out[0].data_ptr(), out[1].data_ptr() if want_ends else 0, out[2].data_ptr() if want_ends else 0,
+        engine.run_device(algo, base + mine.pos[0], base + mine.pos[2] + 8 * first, base + mine.pos[1],
+                          base + mine.pos[3] + 8 * first, n_local, out[0].data_ptr(),
+                          out[1].data_ptr() if want_ends else 0, out[2].data_ptr() if want_ends else 0,
                           torch.cuda.current_stream().cuda_stream)
     t2 = tick()
     res = gather_results(out, bounds, src, group)
@@ -211,7 +243,7 @@ def align_sharded_peer(engine, algo, seq_a=None, off_a=None, seq_b=None, off_b=N
     if timings is not None:
         timings.update(scatter=t1 - t0, align=t2 - t1, gather=t3 - t2, kernel_ms=engine.last_kernel_ms,
                        kernel=engine.last_kernel, n_local=n_local)
-    del a, oa, b, ob
-    dist.barrier(group=group)   # the owner may reuse the buffers only after every reader is done
+    if rank != src:
+        mine.close()
+    dist.barrier(group=group)   # the owner may reuse or free the buffer only after every reader is done
     return res
-

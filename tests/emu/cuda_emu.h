@@ -263,6 +263,12 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEve
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+static const unsigned cudaIpcMemLazyEnablePeerAccess = 1;
+/* single process: a "handle" is the pointer itself */
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 static const cudaError_t cudaErrorPeerAccessAlreadyEnabled = (cudaError_t)704;
 static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }

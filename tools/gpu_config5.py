@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from helpers import *
-from seqalign.distributed import align_sharded, align_sharded_peer
+from seqalign.distributed import align_sharded, align_sharded_peer, SharedBatch
 
 PEER = "--peer" in sys.argv   # zero-copy: ranks read rank 0's HBM over NVLink instead of receiving a scatter
 argv = [x for x in sys.argv[1:] if not x.startswith("--")]
@@ -47,13 +47,16 @@ for rep in range(3):
     tm = {}
     t0 = time.perf_counter()
     if rank == 0:
-        da, db = seq_a.to(dev, non_blocking=True), seq_b.to(dev, non_blocking=True)   # host -> GPU 0 over PCIe
-        torch.cuda.synchronize()
-        t_h2d = time.perf_counter() - t0
         if PEER:
-            doa, dob = off_a.to(dev, non_blocking=True), off_b.to(dev, non_blocking=True)
-            res = align_sharded_peer(eng, seqalign.SW, da, doa, db, dob, src=0, want_ends=False, timings=tm)
+            batch = SharedBatch.create(local, seq_a, off_a, seq_b, off_b)    # host -> GPU 0 over PCIe, straight into the shared buffer
+            torch.cuda.synchronize()
+            t_h2d = time.perf_counter() - t0
+            res = align_sharded_peer(eng, seqalign.SW, batch, src=0, want_ends=False, timings=tm)
+            batch.close()
         else:
+            da, db = seq_a.to(dev, non_blocking=True), seq_b.to(dev, non_blocking=True)   # host -> GPU 0 over PCIe
+            torch.cuda.synchronize()
+            t_h2d = time.perf_counter() - t0
             res = align_sharded(eng, seqalign.SW, da, off_a, db, off_b, src=0, device=dev, want_ends=False, timings=tm)
     else:
         t_h2d = 0.0
