@@ -876,8 +876,14 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
   plan->a_stage = (int)((G * K + 15 + 15) & ~15) + 16;
-  /* (the packed kernel prefetches seq_b codes one row ahead in every lane: up to G+1 bytes past the end) */
-  plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16 + (s16 ? 48 : 0);
+  plan->b_stage = (int)((max_lb + 15 + 15) & ~(int64_t)15) + 16;
+  if(s16) {
+    /* exact sizes (a fifth CTA per SM depends on them): a bulk copy brings at
+     * most floor16(len + 30) bytes; the packed kernel also reads seq_b codes one
+     * row ahead in every lane, up to G + 1 bytes past the end of the sequence */
+    plan->a_stage = (int)((G * K + 15 + 15) & ~15);
+    plan->b_stage = (int)((max_lb + 15 + 15 + G + 1) & ~(int64_t)15);
+  }
   plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
   if(s16) {
     const size_t warp_bytes = 2 * (size_t)n * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
@@ -952,8 +958,11 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
 #define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
     void (*kfn)(const FastArgs) = fast16_kernel<g, k>;                                        \
-    if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1; \
-    SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F); \
+    /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
+    const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
+    const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \
+    if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16) != cudaSuccess) return -1; \
+    SA_LAUNCH(kfn, fast_grid(kfn, smem16, num_sms, need), FAST_WARPS * 32, smem16, st, F);    \
     return 0;                                                                                 \
   }
 #define SA_FAST_CASE(g, k)                                                                    \

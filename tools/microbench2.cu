@@ -6,13 +6,15 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum Op { HMAX2, HADD2, HFMA2RELU, DPX, DPX_PLUS_HMAX2, DPX_PLUS_HFMA2, CELL_H16, CELL_S16, CELL_BOTH, NOPS };
+enum Op { HMAX2, HADD2, HFMA2RELU, DPX, DPX_PLUS_HMAX2, DPX_PLUS_HFMA2, CELL_H16, CELL_S16, CELL_BOTH, CELL_S16_NOIMAD, CELL_S16_INDEP, CELL_S16_LDS, NOPS };
 static const char *names[] = {"HMNMX2", "HFMA2 (add.f16x2)", "HFMA2.RELU", "VIADDMNMX.S16x2 x8",
                               "VIADDMNMX.S16x2 x8 + HMNMX2 x8 (independent)", "VIADDMNMX.S16x2 x8 + HFMA2 x8 (independent)",
                               "SW cell fp16x2 (4 cell pairs/iter)", "SW cell s16x2 (4 cell pairs/iter)",
-                              "SW cell s16x2 + fp16x2 interleaved (8 cell pairs/iter)"};
-static const int ops_per_iter[] = {8, 8, 8, 8, 16, 16, 0, 0, 0};
-static const int cells_per_iter[] = {0, 0, 0, 0, 0, 0, 8, 8, 16};
+                              "SW cell s16x2 + fp16x2 interleaved (8 cell pairs/iter)",
+                              "SW cell s16x2 without the H+open IMAD", "SW cell s16x2, cells independent (no gb/hl chain)",
+                              "SW cell s16x2 + profile words from shared memory (LDS per 4 cells)"};
+static const int ops_per_iter[] = {8, 8, 8, 8, 16, 16, 0, 0, 0, 0, 0, 0};
+static const int cells_per_iter[] = {0, 0, 0, 0, 0, 0, 8, 8, 16, 8, 8, 8};
 
 __device__ __forceinline__ unsigned hmax2(unsigned a, unsigned b) { unsigned d; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ unsigned hadd2(unsigned a, unsigned b) { unsigned d; asm volatile("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
@@ -21,6 +23,9 @@ __device__ __forceinline__ unsigned hfma2relu(unsigned a, unsigned b, unsigned c
 template <int OP>
 __global__ void __launch_bounds__(256) bench(int iters, int seed, unsigned one, unsigned hone, int *sink)
 {
+  __shared__ unsigned sm[1024];
+  for(int q = threadIdx.x; q < 1024; q += blockDim.x) sm[q] = q * seed * 0x01010101u;
+  __syncthreads();
   unsigned v[8], u[8];
 #pragma unroll
   for(int k = 0; k < 8; k++) { v[k] = threadIdx.x * (k + 1) + seed; u[k] = 0x3c003c00u + ((threadIdx.x + k) & 7); }
@@ -66,6 +71,32 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, unsigned one, 
       v[1] ^= gb;
       c = cc;
     }
+    if(OP == CELL_S16_NOIMAD || OP == CELL_S16_INDEP || OP == CELL_S16_LDS) {
+      unsigned hl = v[0], gb = v[1], d = v[2], kprev = 0, cc = c;
+      unsigned wl = w, wh = w ^ (unsigned)i;
+      if(OP == CELL_S16_LDS) { wl = sm[(threadIdx.x * 5 + (i & 3)) & 1023]; wh = sm[(threadIdx.x * 5 + 640 + (i & 3)) & 1023]; }
+#pragma unroll
+      for(int k = 0; k < 4; k++) {
+        unsigned sub;
+        if(k == 0) asm volatile("prmt.b32 %0, %1, %2, 0xc480;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else if(k == 1) asm volatile("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else if(k == 2) asm volatile("prmt.b32 %0, %1, %2, 0xe6a2;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else asm volatile("prmt.b32 %0, %1, %2, 0xf7b3;" : "=r"(sub) : "r"(wl), "r"(wh));
+        unsigned m = __viaddmax_s16x2(d, sub, 0x00020002u);
+        v[4 + k] = __viaddmax_s16x2(v[4 + k], b, v[k]);
+        if(OP == CELL_S16_INDEP) gb = __viaddmax_s16x2(u[k], b, u[4 + k]);
+        else gb = __viaddmax_s16x2(gb, b, hl);
+        unsigned h = __vimax3_s16x2(m, v[4 + k], gb);
+        if(k & 1) cc = __vimax3_s16x2(cc, kprev, m);
+        kprev = m;
+        d = v[k];
+        if(OP == CELL_S16_NOIMAD) hl = h ^ 1u;   /* LOP3: keeps the chain, on the ALU pipe -- compare against the IMAD version */
+        else hl = h * one + a;
+        if(OP == CELL_S16_INDEP) u[k] = hl; else v[k] = hl;
+      }
+      v[1] ^= gb;
+      c = cc;
+    }
     if(OP == CELL_H16 || OP == CELL_BOTH) {
       // the same cell in packed fp16: M = relu(d*1 + sub); GA = max(GA+ext, H'up); GB likewise;
       // H = max(max(M,GA),GB); H' = H + open; best = max(best, M)
@@ -94,9 +125,9 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, unsigned one, 
 }
 
 template <int OP>
-void run(int sms, int clock_khz)
+void run(int sms, int clock_khz, int blocks_per_sm = 4, int threads = 256)
 {
-  const int blocks = sms * 4, threads = 256, iters = 4096;
+  const int blocks = sms * blocks_per_sm, iters = 4096;
   int *sink; cudaMalloc(&sink, 4);
   bench<OP><<<blocks, threads>>>(16, 1, 1u, 0x3c003c00u, sink);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -105,7 +136,7 @@ void run(int sms, int clock_khz)
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   const double total = (double)blocks * threads * iters;
-  printf("{\"op\": \"%s\", \"ms\": %.3f, \"lane_ops_per_clk_per_sm\": %.1f, \"cell_pairs_gcups_x2\": %.1f}\n", names[OP], ms,
+  printf("{\"op\": \"%s\", \"warps_per_scheduler\": %d, \"ms\": %.3f, \"lane_ops_per_clk_per_sm\": %.1f, \"cell_pairs_gcups_x2\": %.1f}\n", names[OP], blocks_per_sm * threads / 128, ms,
          total * ops_per_iter[OP] / ms / 1e6 * 1e9 / (sms * (double)clock_khz * 1e3), total * cells_per_iter[OP] / ms / 1e6);
   cudaFree(sink);
 }
@@ -123,5 +154,10 @@ int main()
   run<CELL_H16>(p.multiProcessorCount, p.clockRate);
   run<CELL_S16>(p.multiProcessorCount, p.clockRate);
   run<CELL_BOTH>(p.multiProcessorCount, p.clockRate);
+  run<CELL_S16_NOIMAD>(p.multiProcessorCount, p.clockRate);
+  run<CELL_S16_INDEP>(p.multiProcessorCount, p.clockRate);
+  run<CELL_S16_LDS>(p.multiProcessorCount, p.clockRate);
+  for(int w = 3; w <= 8; w++) run<CELL_S16>(p.multiProcessorCount, p.clockRate, w, 128);
+  for(int w = 4; w <= 6; w++) run<CELL_S16_LDS>(p.multiProcessorCount, p.clockRate, w, 128);
   return 0;
 }
