@@ -43,6 +43,7 @@ PAIRS = 100000
 LEN = 150
 SEED = 2
 E2E_DEPTH = 4   # batches in flight in the end-to-end arm
+NCU_TRAFFIC_BYTES = 31644160   # dram read + write of one fast16 launch on this workload (ncu --set full)
 MATCH, MISMATCH, GAP_OPEN, GAP_EXTEND = 2, -2, -2, -1
 WORKLOAD = "SW score-only, %d synthetic DNA pairs %dx%d per GPU per step, scoring 2/-2/-2/-1" % (PAIRS, LEN, LEN)
 REF_BATCH = os.path.join(ROOT, "oracle", "_ref", "ref_batch")
@@ -175,21 +176,34 @@ def reference_arm(args):
 
 
 def issue_peak_gcups(kernel_name):
-    """Measured issue-rate ceiling (Gcells/s, event-timed) of the instruction mix of the
-    kernel that ran, from tools/microbench.cu run on this GPU just now."""
-    want = "s16x2 mix" if kernel_name.startswith("fast16") else (
-        "int32 end-cell mix" if kernel_name.endswith("_end") else "int32 score-only mix")
+    """ALU-pipe issue ceiling (Gcells/s) of the kernel that ran, from tools/microbench.cu run on
+    this GPU just now: (measured lane-ops/clk/SM of the kernel's DPX instruction) x SMs x clock
+    / (ALU-pipe instructions per cell).  Also returns the event-timed rate of the whole cell's
+    instruction mix as a cross-check."""
+    s16 = kernel_name.startswith("fast16")
+    want = "s16x2 mix" if s16 else ("int32 end-cell mix" if kernel_name.endswith("_end") else "int32 score-only mix")
+    # ALU-pipe instructions per cell: packed kernel 5.5 per cell PAIR (PRMT, 3 x VIADDMNMX.S16x2,
+    # VIMNMX3.S16x2, half a VIMNMX3 of the running best); int32 kernels 4.5 / 5.5 per cell
+    alu_per_cell = 2.75 if s16 else (5.5 if kernel_name.endswith("_end") else 4.5)
+    op = "VIADDMNMX.S16x2.RELU" if s16 else "VIADDMNMX"
     exe = os.path.join(ROOT, "bin", "microbench")
+    rate, mix, dev = None, None, None
     try:
         out = subprocess.check_output([exe], text=True, timeout=60)
         for ln in out.splitlines():
             d = json.loads(ln)
-            if want in d.get("op", ""):
-                return d["cells_gcups"], "live tools/microbench.cu: " + d["op"]
+            if "sms" in d:
+                dev = d
+            elif d.get("op") == op:
+                rate = d["lane_ops_per_clk_per_sm_at_max_clock"]
+            elif want in d.get("op", ""):
+                mix = d["cells_gcups"]
     except Exception:
         pass
-    recorded = {"s16x2 mix": 6900.0, "int32 end-cell mix": 3700.0, "int32 score-only mix": 3900.0}
-    return recorded[want], "recorded (profiles/microbench_r01b.jsonl): " + want
+    if rate is None or dev is None:
+        return (6560.0 if s16 else 3900.0), None, "recorded (profiles/microbench_r01b.jsonl)"
+    peak = dev["sms"] * rate * dev["clock_khz"] * 1e3 / alu_per_cell / 1e9
+    return peak, mix, "live tools/microbench.cu: %s at %.1f lane-ops/clk/SM / %.2f ALU-pipe instr per cell" % (op, rate, alu_per_cell)
 
 
 def main():
@@ -329,7 +343,7 @@ def main():
         # algorithmic traffic, score mode: both sequences read once, score + end cell written
         alg_bytes = PAIRS * (LEN + LEN + 4)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        issue_peak, issue_src = issue_peak_gcups(kernel_name)
+        issue_peak, issue_mix, issue_src = issue_peak_gcups(kernel_name)
         f_mhz = clocks["sm_mhz"] or 1965.0
         line = {
             "metric": "DP cell updates/s (GCUPS)", "value": value, "unit": "GCUPS", "n_gpus": world,
@@ -350,9 +364,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
-                         # workload, from profiles/ncu_fast16_sw_r01_raw.csv (ncu --set full); not re-measured live
-                         "traffic": 31644160 if kernel_name == "fast16_sw_score" else None,
-                         "traffic_source": "profiles/ncu_fast16_sw_r01_raw.csv",
+                         # workload, from profiles/ncu_fast16_r01f_raw.csv (ncu --set full); not re-measured live
+                         "traffic": NCU_TRAFFIC_BYTES if kernel_name == "fast16_sw_score" else None,
+                         "traffic_source": "profiles/ncu_fast16_r01f_raw.csv",
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "kernel": kernel_name, "kernel_ms": k_ms,
                          "kernel_gcups": cells_step / (k_ms * 1e-3) / 1e9,
@@ -360,6 +374,7 @@ def main():
                                  "binding one is INT32/DPX issue, reported under 'issue'",
                          "issue": {"achieved_gcups": cells_step / (k_ms * 1e-3) / 1e9, "peak_gcups": issue_peak,
                                    "frac": cells_step / (k_ms * 1e-3) / 1e9 / issue_peak,
+                                   "mix_gcups": issue_mix,   # the whole cell's instruction mix, microbenchmarked
                                    "sm_mhz": f_mhz, "source": issue_src}},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -831,12 +831,12 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     H.counter = (unsigned long long *)eng->d_counter.p;
     CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
     int sgrid = (int)((m + HITS_WARPS - 1) / HITS_WARPS);
-    if(sgrid > eng->num_sms * 3) sgrid = eng->num_sms * 3;
+    if(sgrid > eng->num_sms * 6) sgrid = eng->num_sms * 6;
     SA_LAUNCH(hits_sort_kernel, sgrid, HITS_WARPS * 32, 0, st, H);
     CU_TRY(cudaGetLastError());
-    int wgrid = (int)((m + 127) / 128);
-    if(wgrid > eng->num_sms * 8) wgrid = eng->num_sms * 8;
-    SA_LAUNCH(hits_walk_kernel, wgrid, 128, 0, st, H);
+    int wgrid = (int)((m + HITS_WALK_WARPS - 1) / HITS_WALK_WARPS);
+    if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;   /* a warp per pair, 64 warps per SM */
+    SA_LAUNCH(hits_walk_kernel, wgrid, HITS_WALK_WARPS * 32, 0, st, H);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(eng->ev1, st));
     eng->last_launches += 2;

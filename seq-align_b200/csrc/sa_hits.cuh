@@ -128,18 +128,25 @@ hits_sort_kernel(const HitsArgs A)
     /* 1. compact the candidates, row-major (y asc, then x asc) */
     int n = 0, maxs = 0;
     const int64_t total = (int64_t)stride * lb;
-    for(int64_t i0 = 0; i0 < total; i0 += 32) {
-      const int64_t i = i0 + lane;
-      int sc = 0, x = 0, y = 0;
-      if(i < total) {
-        x = (int)(i % stride); y = (int)(i / stride);
-        if(x < la) sc = m[i];
+    /* (four tiles of 32 cells per iteration: their loads are in flight together) */
+    for(int64_t i0 = 0; i0 < total; i0 += 128) {
+      int scs[4];
+#pragma unroll
+      for(int q = 0; q < 4; q++) {
+        const int64_t i = i0 + 32 * q + lane;
+        scs[q] = i < total ? (int)m[i] : 0;
       }
-      const bool take = sc >= A.min_score && sc > 0;
-      const unsigned b = __ballot_sync(FULL, take);
-      if(take) k0[n + __popc(b & ((1u << lane) - 1u))] = hit_key(sc, x + 1, y + 1);
-      n += __popc(b);
-      maxs = imax(maxs, sc);
+#pragma unroll
+      for(int q = 0; q < 4; q++) {
+        const int64_t i = i0 + 32 * q + lane;
+        const int x = (int)(i % stride), y = (int)(i / stride);
+        const int sc = (i < total && x < la) ? scs[q] : 0;
+        const bool take = sc >= A.min_score && sc > 0;
+        const unsigned b = __ballot_sync(FULL, take);
+        if(take) k0[n + __popc(b & ((1u << lane) - 1u))] = hit_key(sc, x + 1, y + 1);
+        n += __popc(b);
+        maxs = imax(maxs, sc);
+      }
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) maxs = imax(maxs, __shfl_xor_sync(FULL, maxs, o));
@@ -176,13 +183,24 @@ hits_sort_kernel(const HitsArgs A)
   }
 }
 
-/* one thread per pair: candidates in order through the visited mask */
-__global__ void __launch_bounds__(128)
+/* One WARP per pair.  The walks of a pair are sequential by nature (each one
+ * reads the marks its predecessors left), so the parallelism is across pairs;
+ * a thread per pair made 32 diverging walks share one instruction stream and
+ * left the SMs with a handful of warps, every dependent load exposed (62 ms for
+ * 20k pairs).  Here all lanes of a warp run the SAME walk on the same addresses
+ * (loads coalesce to one transaction, no divergence; lane 0 alone writes), the
+ * machine holds thousands of such warps, and the lanes split the one thing
+ * that is parallel: skipping candidates that are already marked, 32 at a time. */
+constexpr int HITS_WALK_WARPS = 4;
+
+__global__ void __launch_bounds__(HITS_WALK_WARPS * 32)
 hits_walk_kernel(const HitsArgs A)
 {
   const ScoreParams &sp = A.sp;
-  for(int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < A.npairs;
-      p += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for(int64_t p = warp0; p < A.npairs; p += nwarps) {
     const int64_t oa = A.off_a[p], ob = A.off_b[p];
     const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
     const uint8_t *a = A.seq_a + oa, *b = A.seq_b + ob;
@@ -194,13 +212,25 @@ hits_walk_kernel(const HitsArgs A)
     const int cap = la + lb;
     int nh = 0;
 
-    for(int c = 0; c < n && nh < A.max_hits; c++) {
-      const unsigned long long key = keys[c];
+    int c = 0;
+    while(c < n && nh < A.max_hits) {
+      /* next candidate whose end cell is not marked yet (smith_waterman.c:270):
+       * the lanes look at candidates c .. c+31 together */
+      unsigned long long key = 0;
+      bool open_cand = false;
+      if(c + lane < n) {
+        key = keys[c + lane];
+        const int64_t cell = (int64_t)((int)(key & 0xffffu) - 1) * stride + ((int)((key >> 16) & 0xffffu) - 1);
+        open_cand = !((mask[cell >> 5] >> (cell & 31)) & 1u);
+      }
+      const unsigned cand = __ballot_sync(FULL, open_cand);
+      if(cand == 0) { c += 32; continue; }
+      const int j = __ffs(cand) - 1;
+      key = __shfl_sync(FULL, key, j);
+      c += j + 1;   /* the candidates after it are looked at again: this walk may mark them */
+
       const int xe = (int)((key >> 16) & 0xffffu), ye = (int)(key & 0xffffu);
       const int score = (int)(key >> 32);
-      int64_t cell = (int64_t)(ye - 1) * stride + (xe - 1);
-      if((mask[cell >> 5] >> (cell & 31)) & 1u) continue;           /* smith_waterman.c:270 */
-
       uint8_t *ra = A.out_a + A.out_off[p] + (int64_t)nh * cap;
       uint8_t *rb = A.out_b + A.out_off[p] + (int64_t)nh * cap;
       int x = xe, y = ye, st = ST_M, cs = score, len = 0;
@@ -208,35 +238,43 @@ hits_walk_kernel(const HitsArgs A)
       /* smith_waterman.c:187-199 and 217-244 in one pass: the strings are
        * written speculatively and only kept if the walk completes */
       for(;;) {
-        bool border = x == 0 || y == 0;
+        const bool border = x == 0 || y == 0;
+        int64_t cell = 0;
         if(!border) {
           cell = (int64_t)(y - 1) * stride + (x - 1);
-          if((mask[cell >> 5] >> (cell & 31)) & 1u) { ok = false; break; }
-          mask[cell >> 5] |= 1u << (cell & 31);
+          const unsigned word = mask[cell >> 5];
+          if((word >> (cell & 31)) & 1u) { ok = false; break; }
+          __syncwarp();                     /* every lane has read the word before lane 0 changes it */
+          if(lane == 0) mask[cell >> 5] = word | (1u << (cell & 31));
+          __syncwarp();
         }
         if(cs == 0) break;
         len++;
-        ra[cap - len] = st == ST_GA ? '-' : a[x - 1];
-        rb[cap - len] = st == ST_GB ? '-' : b[y - 1];
-        /* predecessor state from the equality flags (as walk_kernel, fmt 1) */
+        /* everything this step may need is requested up front (independent loads) */
         const unsigned f = dirp[cell];
+        const unsigned g_diag = (x > 1 && y > 1) ? dirp[cell - stride - 1] : 0u;
+        const unsigned g_up = y > 1 ? dirp[cell - stride] : 0u;
+        const unsigned g_left = x > 1 ? dirp[cell - 1] : 0u;
+        const unsigned ca = a[x - 1], cb = b[y - 1];
+        if(lane == 0) {
+          ra[cap - len] = st == ST_GA ? '-' : (uint8_t)ca;
+          rb[cap - len] = st == ST_GB ? '-' : (uint8_t)cb;
+        }
+        /* predecessor state from the equality flags (as walk_kernel, fmt 1) */
         int code;
         if(st == ST_M) {
           if(x == 1 || y == 1) code = ST_M;
-          else { const unsigned g = dirp[cell - stride - 1]; code = !(g & 1) ? ST_GA : !(g & 2) ? ST_GB : ST_M; }
+          else code = !(g_diag & 1) ? ST_GA : !(g_diag & 2) ? ST_GB : ST_M;
         } else if(st == ST_GA) {
           if(!(f & 4)) code = ST_GA;
           else if(y == 1) code = ST_M;
-          else { const unsigned g = dirp[cell - stride]; code = !(g & 2) ? ST_GB : ST_M; }
+          else code = !(g_up & 2) ? ST_GB : ST_M;
         } else {
           if(x == 1) code = ST_M;
-          else {
-            const unsigned g = dirp[cell - 1];
-            code = (!(g & 1) && !(f & 16)) ? ST_GA : !(f & 8) ? ST_GB : ST_M;
-          }
+          else code = (!(g_left & 1) && !(f & 16)) ? ST_GA : !(f & 8) ? ST_GB : ST_M;
         }
         int pen;
-        if(st == ST_M) { pen = A.sub[A.lut[b[y - 1]] * sp.ncodes + A.lut[a[x - 1]]]; x--; y--; }
+        if(st == ST_M) { pen = A.sub[A.lut[cb] * sp.ncodes + A.lut[ca]]; x--; y--; }
         else if(st == ST_GA) { pen = code == ST_GA ? sp.ext : sp.open; y--; }
         else { pen = code == ST_GB ? sp.ext : sp.open; x--; }
         cs -= pen;
@@ -244,11 +282,14 @@ hits_walk_kernel(const HitsArgs A)
         st = code;
       }
       if(!ok) continue;
-      int32_t *r = A.rec + ((int64_t)p * A.max_hits + nh) * 8;
-      r[0] = score; r[1] = x; r[2] = y; r[3] = xe - x; r[4] = ye - y; r[5] = len; r[6] = cap - len; r[7] = 0;
+      if(lane == 0) {
+        int32_t *r = A.rec + ((int64_t)p * A.max_hits + nh) * 8;
+        r[0] = score; r[1] = x; r[2] = y; r[3] = xe - x; r[4] = ye - y; r[5] = len; r[6] = cap - len; r[7] = 0;
+      }
       nh++;
     }
-    A.nhits[p] = nh;
+    if(lane == 0) A.nhits[p] = nh;
+    __syncwarp();
   }
 }
 

@@ -81,10 +81,17 @@ __global__ void __launch_bounds__(256) bench(int iters, int seed, int one, int o
       // 4 packed cell pairs as fast16_kernel issues them: PRMT combine,
       // 3 x VIADDMNMX.S16x2, VIMNMX3.S16x2, max3 tree, packed add as IMAD
       unsigned hl = v[0], gb = v[1], d = v[2], kprev = 0, cc = c;
+      // profile words of the two pairs: one shared-memory word each per 4 cells, as in the kernel
+      // (an earlier version derived the PRMT inputs with two extra ALU ops per cell and so
+      // understated this ceiling by about a fifth)
+      const unsigned wl = (unsigned)sm[(threadIdx.x * 5 + (i & 3)) & 1023], wh = (unsigned)sm[(threadIdx.x * 5 + 640 + (i & 3)) & 1023];
 #pragma unroll
       for(int k = 0; k < 4; k++) {
         unsigned sub;
-        asm volatile("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(sub) : "r"(w + k), "r"(w ^ (unsigned)i));
+        if(k == 0) asm volatile("prmt.b32 %0, %1, %2, 0xc480;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else if(k == 1) asm volatile("prmt.b32 %0, %1, %2, 0xd591;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else if(k == 2) asm volatile("prmt.b32 %0, %1, %2, 0xe6a2;" : "=r"(sub) : "r"(wl), "r"(wh));
+        else asm volatile("prmt.b32 %0, %1, %2, 0xf7b3;" : "=r"(sub) : "r"(wl), "r"(wh));
         unsigned m = __viaddmax_s16x2(d, sub, 0x00020002u);
         v[4 + k] = __viaddmax_s16x2(v[4 + k], b, v[k]);
         gb = __viaddmax_s16x2(gb, b, hl);
