@@ -62,32 +62,30 @@ extern const char align_col_mismatch[], align_col_indel[], align_col_context[],
 
 #define aligner_init(a) (memset(a, 0, sizeof(aligner_t)))
 
-/* reference src/alignment.c:170-193 -- GPU fill, matrices copied back */
-void aligner_align(aligner_t *aligner,
-                   const char *seq_a, const char *seq_b,
-                   size_t len_a, size_t len_b,
-                   const scoring_t *scoring, char is_sw);
-/* reference src/alignment.c:195-202 */
-void aligner_destroy(aligner_t *aligner);
+/* reference src/alignment.c:170-193: bind the pair, grow the three buffers to
+ * the next power of two, fill.  Here the fill is the GPU kernel in materialise
+ * mode and the matrices are copied back into the buffers. */
+void aligner_align(aligner_t *self, const char *a, const char *b, size_t n_a, size_t n_b, const scoring_t *model, char is_sw);
 
-/* reference src/alignment.c:205-240 */
+/* reference src/alignment.c:195-202: frees the matrices, zeroes the struct */
+void aligner_destroy(aligner_t *self);
+
+/* reference src/alignment.c:205-240: result buffers, grown in powers of two;
+ * "Out of memory" on stderr and exit(EXIT_FAILURE) when realloc fails */
 alignment_t *alignment_create(size_t capacity);
-void alignment_ensure_capacity(alignment_t *result, size_t strlength);
-void alignment_free(alignment_t *result);
+void alignment_ensure_capacity(alignment_t *out, size_t columns);
+void alignment_free(alignment_t *out);
 
-/* reference src/alignment.c:244-350 -- one backward step over the
- * materialised matrices (host side, for callers that walk themselves) */
-void alignment_reverse_move(enum Matrix *curr_matrix, score_t *curr_score,
-                            size_t *score_x, size_t *score_y,
-                            size_t *arr_index, const aligner_t *aligner);
+/* reference src/alignment.c:244-350: one backward step over the materialised
+ * matrices, predecessor chosen by equality in the order GAP_A, GAP_B, MATCH
+ * (host side, for callers that walk themselves; the batch engine takes the
+ * same decisions at fill time) */
+void alignment_reverse_move(enum Matrix *state, score_t *score, size_t *x, size_t *y, size_t *cell_index, const aligner_t *self);
 
-/* reference src/alignment.c:353-474 */
-void alignment_print_matrices(const aligner_t *aligner);
-void alignment_colour_print_against(const char *alignment_a,
-                                    const char *alignment_b,
-                                    char case_sensitive);
-void alignment_print_spacer(const char *alignment_a, const char *alignment_b,
-                            const scoring_t *scoring);
+/* reference src/alignment.c:353-474: text output, byte for byte */
+void alignment_print_matrices(const aligner_t *self);
+void alignment_colour_print_against(const char *row, const char *other_row, char case_sensitive);
+void alignment_print_spacer(const char *row_a, const char *row_b, const scoring_t *model);
 
 #ifdef __cplusplus
 }

@@ -59,32 +59,34 @@ typedef struct
 extern "C" {
 #endif
 
-/* reference src/alignment_scoring.c:21-55 */
-void scoring_init(scoring_t *scoring, int match, int mismatch,
-                  int gap_open, int gap_extend,
-                  bool no_start_gap_penalty, bool no_end_gap_penalty,
-                  bool no_gaps_in_a, bool no_gaps_in_b,
-                  bool no_mismatches, bool case_sensitive);
-/* reference src/alignment_scoring.c:57-64 */
-void scoring_add_wildcard(scoring_t *scoring, char c, int s);
-/* reference src/alignment_scoring.c:66-72 */
-void scoring_add_mutation(scoring_t *scoring, char a, char b, int score);
-/* reference src/alignment_scoring.c:74-97 (exported there, not declared) */
-void scoring_add_mutations(scoring_t *scoring, const char *str,
-                           const int *scores, char use_match_mismatch);
-/* reference src/alignment_scoring.c:99-112 */
-void scoring_print(const scoring_t *scoring);
-/* reference src/alignment_scoring.c:133-182; exits on an unknown pair */
-void scoring_lookup(const scoring_t *scoring, char a, char b,
-                    int *score, bool *is_match);
+/* reference src/alignment_scoring.c:21-55: clears the tables, stores the
+ * penalties and flags, derives min_penalty / max_penalty */
+void scoring_init(scoring_t *model, int match, int mismatch, int gap_open, int gap_extend, bool free_start_gaps, bool free_end_gaps, bool forbid_gaps_in_a, bool forbid_gaps_in_b, bool forbid_mismatches, bool case_sensitive);
 
-/* built-in systems, reference src/alignment_scoring.c:306-392 */
-void scoring_system_PAM30(scoring_t *scoring);
-void scoring_system_PAM70(scoring_t *scoring);
-void scoring_system_BLOSUM80(scoring_t *scoring);
-void scoring_system_BLOSUM62(scoring_t *scoring);
-void scoring_system_DNA_hybridization(scoring_t *scoring);
-void scoring_system_default(scoring_t *scoring);
+/* reference src/alignment_scoring.c:57-64: `wild` pairs with every character at `score` */
+void scoring_add_wildcard(scoring_t *model, char wild, int score);
+
+/* reference src/alignment_scoring.c:66-72: explicit score for the ordered pair (from, to); no case folding */
+void scoring_add_mutation(scoring_t *model, char from, char to, int score);
+
+/* reference src/alignment_scoring.c:74-97 (exported there, not declared):
+ * a square table over the characters of `alphabet`, row-major */
+void scoring_add_mutations(scoring_t *model, const char *alphabet, const int *table, char use_match_mismatch);
+
+/* reference src/alignment_scoring.c:99-112 */
+void scoring_print(const scoring_t *model);
+
+/* reference src/alignment_scoring.c:133-182: case fold, swap table, wildcards,
+ * match/mismatch; prints "Unknown character pair" and exits when nothing applies */
+void scoring_lookup(const scoring_t *model, char a, char b, int *score_out, bool *is_match_out);
+
+/* built-in systems, reference src/alignment_scoring.c:306-392 (tables in host/sa_scoring_tables.h) */
+void scoring_system_PAM30(scoring_t *model);
+void scoring_system_PAM70(scoring_t *model);
+void scoring_system_BLOSUM80(scoring_t *model);
+void scoring_system_BLOSUM62(scoring_t *model);
+void scoring_system_DNA_hybridization(scoring_t *model);
+void scoring_system_default(scoring_t *model);
 
 #ifdef __cplusplus
 }

@@ -1,10 +1,11 @@
 /*
  * needleman_wunsch.h -- global alignment front-end (B200 build).
  *
- * Drop-in for reference src/needleman_wunsch.h:16-32.  The fill, the
- * end-state choice (src/needleman_wunsch.c:53-66) and the traceback
+ * Drop-in for reference src/needleman_wunsch.h:16-32 (same names, argument
+ * order and types; callers compile unchanged).  The fill, the end-state
+ * choice (src/needleman_wunsch.c:53-66) and the traceback
  * (src/needleman_wunsch.c:79-145) all run on the GPU: the fill kernel emits
- * one direction byte per cell, a walk kernel follows them and writes the two
+ * one traceback byte per cell, a walk kernel follows them and writes the two
  * gapped strings, which are copied into alignment_t.
  */
 #ifndef NEEDLEMAN_WUNSCH_HEADER_SEEN
@@ -13,23 +14,26 @@
 #include "seq_align.h"
 #include "alignment.h"
 
+/* the reference's Needleman-Wunsch aligner is its plain aligner_t */
 typedef aligner_t nw_aligner_t;
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
+/* zeroed aligner; its matrices grow on demand (only filled when the caller
+ * can look at them, see SEQALIGN_SKIP_MATRICES in INTEGRATION.md) */
 nw_aligner_t *needleman_wunsch_new();
-void needleman_wunsch_free(nw_aligner_t *nw);
 
-void needleman_wunsch_align(const char *a, const char *b,
-                            const scoring_t *scoring,
-                            nw_aligner_t *nw, alignment_t *result);
+/* releases the matrices and the aligner itself */
+void needleman_wunsch_free(nw_aligner_t *aligner);
 
-void needleman_wunsch_align2(const char *a, const char *b,
-                             size_t len_a, size_t len_b,
-                             const scoring_t *scoring,
-                             nw_aligner_t *nw, alignment_t *result);
+/* NUL-terminated sequences: strlen() both, then needleman_wunsch_align2 */
+void needleman_wunsch_align(const char *seq_a, const char *seq_b, const scoring_t *model, nw_aligner_t *aligner, alignment_t *out);
+
+/* explicit lengths (no NUL needed).  out->result_a / result_b / length / score
+ * are filled; pos_* and len_* are left alone, as upstream */
+void needleman_wunsch_align2(const char *seq_a, const char *seq_b, size_t n_a, size_t n_b, const scoring_t *model, nw_aligner_t *aligner, alignment_t *out);
 
 #ifdef __cplusplus
 }
