@@ -155,3 +155,25 @@ def test_host_scoring_specs_match_reference():
                 ref.scoring_lookup(buf, ctypes.c_char(bytes([a])), ctypes.c_char(bytes([b])),
                                    ctypes.byref(sc), ctypes.byref(im))
                 assert mine.lookup(bytes([a]), bytes([b])) == (sc.value, im.value), (name, a, b)
+
+
+@pytest.mark.parity
+def test_shared_buffer_entry_points(backend):
+    """seqalign_shared_alloc / open / close / free and seqalign_enable_peer_access: a buffer the
+    owner allocates and a peer maps.  Single process here: opening one's own handle is the case
+    CUDA IPC forbids, so on the GPU only alloc/free and the self-peer no-op are exercised; the
+    cross-process path runs in tools/gpu_config5.py --peer."""
+    import ctypes
+    import seqalign
+    L = seqalign.load()
+    ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    assert L.seqalign_shared_alloc(0, 4096, ctypes.byref(ptr), handle) == 0 and ptr.value
+    assert any(handle.raw)
+    if backend == "emu":
+        peer = ctypes.c_void_p()
+        assert L.seqalign_shared_open(0, handle, ctypes.byref(peer)) == 0 and peer.value == ptr.value
+        assert L.seqalign_shared_close(0, peer) == 0
+    assert L.seqalign_shared_free(0, ptr) == 0
+    assert L.seqalign_enable_peer_access(0, 0) == 0
+    assert L.seqalign_shared_alloc(0, 16, None, handle) == seqalign.ERR_ARG
+

@@ -439,6 +439,96 @@ def test_full_size_invariants(engine, big):
     assert np.array_equal(s[idx], es) and np.array_equal(x[idx], ex) and np.array_equal(y[idx], ey)
 
 
+def _rescore(ra, rb, sub, gap_open, gap_extend, free_ends=False):
+    """score of a gapped alignment under affine gaps (a gap of length N costs open + N*extend),
+    recomputed column by column; free_ends: leading / trailing gap runs cost nothing"""
+    n = len(ra)
+    cols = list(zip(ra, rb))
+    lead, trail = 0, n
+    if free_ends and n:
+        # one leading run of gaps in ONE row lies on the matrix border (free), likewise one trailing run
+        row = 0 if cols[0][0] == 45 else 1 if cols[0][1] == 45 else None
+        while row is not None and lead < n and cols[lead][row] == 45:
+            lead += 1
+        row = 0 if cols[-1][0] == 45 else 1 if cols[-1][1] == 45 else None
+        while row is not None and trail > lead and cols[trail - 1][row] == 45:
+            trail -= 1
+    total, prev = 0, 0   # prev: 0 = match column, 1 = gap in a, 2 = gap in b
+    for x, y in cols[lead:trail]:
+        if x == 45:
+            total += gap_extend + (gap_open if prev != 1 else 0); prev = 1
+        elif y == 45:
+            total += gap_extend + (gap_open if prev != 2 else 0); prev = 2
+        else:
+            total += sub(x, y); prev = 0
+    return total
+
+
+def _cached_lookup(sc):
+    memo = {}
+
+    def look(x, y):
+        if (x, y) not in memo:
+            memo[(x, y)] = sc.lookup(bytes([x]), bytes([y]))[0]
+        return memo[(x, y)]
+    return look
+
+
+def test_full_size_protein_alignments_rescore(engine, big):
+    """BASELINE config 4 at full width (SW, protein 400x400, BLOSUM62, first hit): every
+    reported hit must be a substring pair of its inputs whose column-by-column score equals the
+    reported score, and the score must equal the score-only kernel's; oracle on a sample"""
+    if not big:
+        pytest.skip("full size runs on the GPU only")
+    n, L = 5000, 400
+    a, oa, b, ob = synthetic_batch(4, n, L, L, kind="protein")
+    sc = scoring_from_spec(SPECS["blosum62"])
+    engine.set_scoring(sc)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s_score, xe, ye = [v.copy() for v in engine.ends()]
+    engine.submit_packed(SW, MODE_ALIGN, a, oa, b, ob)
+    assert engine.last_kernel.startswith("fast_sw_dir")
+    look = _cached_lookup(sc)
+    A, B = a.reshape(n, L), b.reshape(n, L)
+    for i in range(0, n, 7):
+        al = engine.alignment(i)
+        if s_score[i] == 0:
+            assert al is None
+            continue
+        assert al.score == s_score[i]
+        assert al.pos_a + al.len_a == xe[i] and al.pos_b + al.len_b == ye[i]
+        assert al.result_a.replace(b"-", b"") == A[i, al.pos_a: al.pos_a + al.len_a].tobytes()
+        assert al.result_b.replace(b"-", b"") == B[i, al.pos_b: al.pos_b + al.len_b].tobytes()
+        assert _rescore(al.result_a, al.result_b, look, sc.s.gap_open, sc.s.gap_extend) == al.score
+    o = orc_from_scoring(sc)
+    for i in range(0, n, 500):
+        _check_alignment(engine.alignment(i), SW, o, A[i].tobytes(), B[i].tobytes())
+
+
+def test_full_size_long_pairs_rescore(engine, big):
+    """BASELINE config 3 at full width (NW 10k x 10k, free start and end gaps, score +
+    traceback): the gapped strings spell the inputs, and their column score with free end
+    gaps equals both the reported score and the score-only kernel's"""
+    if not big:
+        pytest.skip("full size runs on the GPU only")
+    n, L = 8, 10000
+    a, oa, b, ob = synthetic_batch(3, n, L, L, block=16)
+    sc = scoring_from_spec(SPECS["free_ends"])
+    engine.set_scoring(sc)
+    engine.submit_packed(NW, MODE_SCORE, a, oa, b, ob)
+    s_score = engine.scores().copy()
+    engine.submit_packed(NW, MODE_ALIGN, a, oa, b, ob)
+    assert engine.last_kernel.startswith("long_nw_dir")
+    look = _cached_lookup(sc)
+    A, B = a.reshape(n, L), b.reshape(n, L)
+    for i in range(n):
+        al = engine.alignment(i)
+        assert al.score == s_score[i]
+        assert al.result_a.replace(b"-", b"") == A[i].tobytes() and al.result_b.replace(b"-", b"") == B[i].tobytes()
+        assert len(al.result_a) == len(al.result_b)
+        assert _rescore(al.result_a, al.result_b, look, sc.s.gap_open, sc.s.gap_extend, free_ends=True) == al.score
+
+
 def _device_arrays(big, arrays):
     """CUDA copies of numpy arrays (GPU) / the arrays themselves (the emulator's
     device memory is host memory); returns (keepalive, pointers)"""
