@@ -21,6 +21,7 @@
 #include "sa_kernels.cuh"
 #include "sa_fast.cuh"
 #include "sa_hits.cuh"
+#include "sa_mats.cuh"
 #include "sa_long.cuh"
 
 using namespace sa;
@@ -88,7 +89,8 @@ struct seqalign_batch {
   /* multi-hit mode */
   DevBuf d_m16, d_keys0, d_keys1, d_mask, d_ncand, d_which, d_nhits, d_rec;
   /* materialise mode */
-  DevBuf d_mats;
+  DevBuf d_mats, d_mat_off;
+  std::vector<int64_t> mat_off;            /* batch materialise: first int of pair i's match plane, n+1 entries */
   PinBuf h_in_a, h_in_b, h_off_a, h_off_b, h_meta, h_res, h_walk, h_str_a, h_str_b;
 
   /* last batch */
@@ -869,6 +871,60 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   return 0;
 }
 
+/* batch materialise (Smith-Waterman): the three matrices of every pair stay in
+ * device memory, seqalign_batch_matrices() copies one pair's planes out */
+int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
+             const int64_t *h_off_a, const int64_t *h_off_b, cudaStream_t st)
+{
+  const size_t n = db.n;
+  const scoring_t *s = eng->scoring;
+  const ScoreParams sp = make_params(s, true, eng->ft.ncodes);
+  const int NB = mats_blocks(bm.max_la);
+  if(eng->force_mode == 1 || sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches || s->gap_open > 0 ||
+     s->gap_extend > 0 || eng->ft.any_unknown || NB == 0 || eng->ft.min_sub < -32768 || eng->ft.max_sub > 32767 ||
+     (long)bm.max_la * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) > (1L << 28) || sp.open < -(1 << 20))
+    return fail(eng, SEQALIGN_ERR_ARG,
+                "batch materialise needs Smith-Waterman with affine gaps (gap_open <= 0, no gap/mismatch "
+                "restrictions) and len_a <= 511; use aligner_align() for this input");
+  eng->mat_off.assign(n + 1, 0);
+  for(size_t i = 0; i < n; i++)
+    eng->mat_off[i + 1] = eng->mat_off[i] + 3 * ((h_off_a[i + 1] - h_off_a[i]) + 1) * ((h_off_b[i + 1] - h_off_b[i]) + 1);
+  const size_t total = (size_t)eng->mat_off[n];
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  if(total * 4 > free_b + eng->d_mats.cap - (free_b + eng->d_mats.cap) / 8)
+    return fail(eng, SEQALIGN_ERR_NOMEM, "the matrices of this batch do not fit device memory (12 bytes per cell): submit fewer pairs");
+  TRY(ensure_dev(eng, eng->d_mats, total * 4 + 64));
+  TRY(ensure_dev(eng, eng->d_mat_off, n * 8));
+  TRY(ensure_dev(eng, eng->d_score, n * 4));
+  TRY(ensure_dev(eng, eng->d_counter, 8));
+  CU_TRY(cudaMemcpyAsync(eng->d_mat_off.p, eng->mat_off.data(), n * 8, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+  MatsArgs M;
+  memset(&M, 0, sizeof(M));
+  M.seq_a = db.a; M.seq_b = db.b; M.off_a = db.off_a; M.off_b = db.off_b;
+  M.npairs = (int64_t)n; M.sp = sp;
+  M.sub = (const int32_t *)eng->d_sub.p; M.lut = (const uint8_t *)eng->d_lut.p;
+  M.mats = (int32_t *)eng->d_mats.p; M.mat_off = (const int64_t *)eng->d_mat_off.p;
+  M.score = (int32_t *)eng->d_score.p;
+  M.counter = (unsigned long long *)eng->d_counter.p;
+  CU_TRY(cudaEventRecord(eng->ev0, st));
+  if(mats_launch(NB, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
+    return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(eng->ev1, st));
+  eng->last_launches++;
+  TRY(ensure_pin(eng, eng->h_res, n * 4));
+  CU_TRY(cudaMemcpyAsync(eng->h_res.p, eng->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+  eng->last_ms = ms;
+  memcpy(eng->score.data(), eng->h_res.p, n * 4);
+  eng->last_kernel = "mats_sw";
+  return 0;
+}
+
 int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
                   const char *h_b, const int64_t *h_off_b, size_t n)
 {
@@ -878,7 +934,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   eng->last_ms = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
   if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN && mode != SEQALIGN_MODE_SCORE_ONLY &&
-      mode != SEQALIGN_MODE_HITS) || (mode == SEQALIGN_MODE_HITS && algo != SEQALIGN_SW))
+      mode != SEQALIGN_MODE_HITS && mode != SEQALIGN_MODE_MATS) ||
+     ((mode == SEQALIGN_MODE_HITS || mode == SEQALIGN_MODE_MATS) && algo != SEQALIGN_SW))
     return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
   eng->algo = algo; eng->mode = mode;
   eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);
@@ -984,7 +1041,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a + total_b, st, &bm));
     TRY(upload_tables(eng, bm, st));
     if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
-    if(mode == SEQALIGN_MODE_HITS) TRY(run_hits(eng, db, bm, h_off_a, h_off_b, st));
+    if(mode == SEQALIGN_MODE_MATS) TRY(run_mats(eng, db, bm, h_off_a, h_off_b, st));
+    else if(mode == SEQALIGN_MODE_HITS) TRY(run_hits(eng, db, bm, h_off_a, h_off_b, st));
     else TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
   }
   eng->n = n;
@@ -1112,7 +1170,7 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
                  &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
                  &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats, &eng->d_m16, &eng->d_keys0,
-                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd};
+                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd, &eng->d_mat_off};
   for(DevBuf *b : d) b->release();
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};
@@ -1378,6 +1436,19 @@ int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_
   CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   eng->last_ms = ms;
   eng->last_kernel = "general_mats";
+  return 0;
+}
+
+int seqalign_batch_matrices(seqalign_batch_t *eng, size_t i, int32_t *match, int32_t *gap_a, int32_t *gap_b)
+{
+  if(!eng || !match || !gap_a || !gap_b) return SEQALIGN_ERR_ARG;
+  if(eng->mode != SEQALIGN_MODE_MATS || i >= eng->n) return fail(eng, SEQALIGN_ERR_ARG, "no matrices for this index");
+  CU_TRY(cudaSetDevice(eng->device));
+  const size_t cells = (size_t)(eng->mat_off[i + 1] - eng->mat_off[i]) / 3;
+  const int32_t *src = (const int32_t *)eng->d_mats.p + eng->mat_off[i];
+  CU_TRY(cudaMemcpy(match, src, cells * 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(gap_a, src + cells, cells * 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(gap_b, src + 2 * cells, cells * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -1,0 +1,204 @@
+/*
+ * sa_mats.cuh -- sm_100a kernels of the batch alignment engine (part 5):
+ * Smith-Waterman in MATERIALISE mode for whole batches -- the literal
+ * contract of aligner_align() (reference src/alignment.c:170-193): the three
+ * int32 matrices match / gap_a / gap_b of every pair, (len_a+1) x (len_b+1)
+ * each, borders included, row-major with index = y*(len_a+1) + x (reference
+ * src/alignment_macros.h:11).  12 bytes per cell leave the SM: this is the one
+ * mode of the path that the HBM roofline bounds (mode M:
+ * 0.546 Tcells/s at the measured copy bandwidth), so the kernel is built
+ * around its stores, not around its arithmetic.
+ *
+ * Work shape: one warp per pair, one ROW per step.  Lane l owns the columns
+ * x = 32*j + l (j = 0..NB-1, x = 0 is the border column), so that every store
+ * instruction of the warp writes 32 consecutive ints of one matrix row -- a
+ * full 128-byte line straight from registers, no staging.  The price is the
+ * dependency inside a row (gap_b runs along it); it is resolved exactly by a
+ * max-plus prefix scan:
+ *
+ *   T[x]    = max(M[x], GA[x])                      (both need only row y-1)
+ *   GB[x]   = max(0, max over x' < x of  T[x'] + open + (x-1-x')*ext)
+ *           = max(0, open + (x-1)*ext + prefixmax_{x' < x}( T[x'] - x'*ext ))
+ *
+ * which equals the reference's recurrence GB[x] = max(M[x-1]+open,
+ * GA[x-1]+open, GB[x-1]+ext, 0) (alignment.c:140-155 with min = 0): a run of
+ * gap_b always starts from a match or gap_a value because open <= ext, and
+ * the clamps at 0 inside the run are absorbed by the final one (ext <= 0).
+ * The scan is 5 shuffle+max steps per block of 32 columns plus a carry between
+ * blocks; at 12 B/cell the arithmetic has an order of magnitude of slack.
+ *
+ * Smith-Waterman with the scoring shapes of sa_fast.cuh (affine gaps with
+ * gap_open <= 0, no gap / mismatch restrictions), len_a <= 511.  Everything
+ * else goes pair by pair through general_kernel<MODE_MATS>.
+ */
+#ifndef SA_MATS_CUH
+#define SA_MATS_CUH
+
+#include "sa_platform.h"
+#include "sa_kernels.cuh"
+
+namespace sa {
+
+constexpr int MATS_WARPS = 4;
+constexpr int MATS_NEG = -(1 << 29);
+
+struct MatsArgs {
+  const uint8_t *seq_a, *seq_b;
+  const int64_t *off_a, *off_b;
+  int64_t npairs;
+  ScoreParams sp;
+  const int32_t *sub;          /* [cb*ncodes + ca] plain substitution scores */
+  const uint8_t *lut;
+  int32_t *mats;               /* per pair: match | gap_a | gap_b planes, dense */
+  const int64_t *mat_off;      /* first int of pair p's match plane */
+  int32_t *score;              /* best match score per pair (as score mode), may be null */
+  unsigned long long *counter;
+};
+
+/* NB blocks of 32 columns cover x = 0 .. len_a */
+template <int NB>
+__global__ void __launch_bounds__(MATS_WARPS * 32)
+mats_kernel(const MatsArgs A)
+{
+  constexpr int PW = NB * 32;                         /* profile row width (columns) */
+  unsigned char *dsm = SA_DYN_SMEM();
+  const ScoreParams &sp = A.sp;
+  const int n = sp.ncodes;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  /* shared layout: [lut 256][sub n*n int32][per warp: profile n*PW int16] */
+  uint8_t *s_lut = dsm;
+  int32_t *s_sub = (int32_t *)(dsm + 256);
+  int16_t *s_prof = (int16_t *)(dsm + 256 + ((n * n * 4 + 15) & ~15)) + (size_t)wib * n * PW;
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+  for(int i = threadIdx.x; i < n * n; i += blockDim.x) s_sub[i] = A.sub[i];
+  __syncthreads();
+  const int open = sp.open, ext = sp.ext;
+
+  for(;;) {
+    unsigned long long t = 0;
+    if(lane == 0) t = atomicAdd(A.counter, 1ull);
+    t = __shfl_sync(FULL, t, 0);
+    if(t >= (unsigned long long)A.npairs) break;
+    const int64_t p = (int64_t)t;
+    const int64_t oa = A.off_a[p], ob = A.off_b[p];
+    const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
+    const int W = la + 1;
+    const int64_t cells = (int64_t)W * (lb + 1);
+    int32_t *pm = A.mats + A.mat_off[p], *pga = pm + cells, *pgb = pga + cells;
+
+    /* query profile: s_prof[c][x] = sub(a[x-1], c) for 1 <= x <= len_a */
+    __syncwarp();
+#pragma unroll
+    for(int j = 0; j < NB; j++) {
+      const int x = 32 * j + lane;
+      const int ca = (x >= 1 && x <= la) ? s_lut[A.seq_a[oa + x - 1]] : -1;
+      for(int c = 0; c < n; c++) s_prof[c * PW + x] = ca >= 0 ? (int16_t)s_sub[c * n + ca] : (int16_t)0;
+    }
+    __syncwarp();
+
+    /* row 0: borders, all three matrices 0 (alignment.c:47-57) */
+    int hp[NB], gap[NB];
+#pragma unroll
+    for(int j = 0; j < NB; j++) {
+      hp[j] = 0; gap[j] = 0;
+      const int x = 32 * j + lane;
+      if(x <= la) { pm[x] = 0; pga[x] = 0; pgb[x] = 0; }
+    }
+    int best = 0;
+    int codes = 0;
+    for(int y = 1; y <= lb; y++) {
+      /* codes of 32 rows of seq_b at a time, one per lane */
+      if(((y - 1) & 31) == 0) codes = (y + lane <= lb) ? s_lut[A.seq_b[ob + y - 1 + lane]] : 0;
+      const int c = __shfl_sync(FULL, codes, (y - 1) & 31);
+      const int16_t *prow = s_prof + c * PW;
+      const int64_t row = (int64_t)y * W;
+      int diag_carry = 0;          /* H[y-1] of the last column of the block before (x = 32j - 1) */
+      int run = MATS_NEG;          /* prefix maximum of T[x'] - x'*ext over the blocks before */
+#pragma unroll
+      for(int j = 0; j < NB; j++) {
+        const int x = 32 * j + lane;
+        const bool cell = x >= 1 && x <= la;
+        int diag = __shfl_up_sync(FULL, hp[j], 1);
+        if(lane == 0) diag = diag_carry;
+        diag_carry = __shfl_sync(FULL, hp[j], 31);
+        const int sub = prow[x];
+        /* match and gap_a need only the row above (alignment.c:101-137) */
+        const int m = cell ? addmax(diag, sub, 0) : 0;
+        const int ga = cell ? max3(gap[j] + ext, hp[j] + open, 0) : 0;
+        const int tt = x <= la ? imax(m, ga) : MATS_NEG;           /* x = 0: the border's 0 */
+        /* gap_b: exclusive prefix maximum of u along the row */
+        int incl = tt - x * ext;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, o);
+          if(lane >= o) incl = imax(incl, v);
+        }
+        int excl = __shfl_up_sync(FULL, incl, 1);
+        if(lane == 0) excl = MATS_NEG;
+        excl = imax(excl, run);
+        run = imax(run, __shfl_sync(FULL, incl, 31));
+        const int gb = cell ? imax(excl + open + (x - 1) * ext, 0) : 0;
+        const int h = imax(imax(m, ga), gb);
+        if(x <= la) { pm[row + x] = m; pga[row + x] = ga; pgb[row + x] = gb; }
+        best = imax(best, m);
+        hp[j] = cell ? h : 0;
+        gap[j] = ga;
+      }
+    }
+    if(A.score) {
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1) best = imax(best, __shfl_xor_sync(FULL, best, o));
+      if(lane == 0) A.score[p] = best;
+    }
+  }
+}
+
+inline size_t mats_smem_bytes(int NB, int ncodes)
+{
+  return 256 + (((size_t)ncodes * ncodes * 4 + 15) & ~(size_t)15) + (size_t)MATS_WARPS * ncodes * NB * 32 * 2;
+}
+
+/* smallest instantiated block count covering max_la + 1 columns; 0 if none */
+inline int mats_blocks(int64_t max_la)
+{
+  static const int kNB[] = {1, 2, 3, 4, 5, 6, 8, 10, 13, 16};
+  for(int nb : kNB) if((int64_t)nb * 32 >= max_la + 1) return nb;
+  return 0;
+}
+
+template <int NB>
+int mats_launch_nb(const MatsArgs &M, size_t smem, int num_sms, cudaStream_t st)
+{
+  void (*kfn)(const MatsArgs) = mats_kernel<NB>;
+  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  int per_sm = 1;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)num_sms * per_sm;
+  const int64_t need = (M.npairs + MATS_WARPS - 1) / MATS_WARPS;
+  if(grid > need) grid = need;
+  SA_LAUNCH(kfn, (int)(grid < 1 ? 1 : grid), MATS_WARPS * 32, smem, st, M);
+  return 0;
+}
+
+inline int mats_launch(int NB, const MatsArgs &M, int ncodes, int num_sms, size_t smem_optin, cudaStream_t st)
+{
+  const size_t smem = mats_smem_bytes(NB, ncodes);
+  if(smem > smem_optin) return -1;
+  switch(NB) {
+    case 1: return mats_launch_nb<1>(M, smem, num_sms, st);
+    case 2: return mats_launch_nb<2>(M, smem, num_sms, st);
+    case 3: return mats_launch_nb<3>(M, smem, num_sms, st);
+    case 4: return mats_launch_nb<4>(M, smem, num_sms, st);
+    case 5: return mats_launch_nb<5>(M, smem, num_sms, st);
+    case 6: return mats_launch_nb<6>(M, smem, num_sms, st);
+    case 8: return mats_launch_nb<8>(M, smem, num_sms, st);
+    case 10: return mats_launch_nb<10>(M, smem, num_sms, st);
+    case 13: return mats_launch_nb<13>(M, smem, num_sms, st);
+    case 16: return mats_launch_nb<16>(M, smem, num_sms, st);
+  }
+  return -1;
+}
+
+} // namespace sa
+
+#endif

@@ -25,6 +25,7 @@ MODE_SCORE = 0
 MODE_ALIGN = 1
 MODE_SCORE_ONLY = 2
 MODE_HITS = 3
+MODE_MATS = 4
 
 ERR_CUDA = -1
 ERR_UNKNOWN_PAIR = -2
@@ -153,6 +154,7 @@ def load():
     L.seqalign_batch_hit_count.restype = sz
     L.seqalign_batch_hit_count.argtypes = [vp, sz]
     L.seqalign_batch_hit.argtypes = [vp, sz, sz, vp]
+    L.seqalign_batch_matrices.argtypes = [vp, sz, vp, vp, vp]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -377,6 +379,14 @@ class BatchAligner:
         self._check(self._L.seqalign_fill_matrices(self._h, a, len(a), b, len(b), 1 if is_sw else 0,
                                                     m.ctypes.data, ga.ctypes.data, gb.ctypes.data))
         shape = (len(b) + 1, len(a) + 1)
+        return m.reshape(shape), ga.reshape(shape), gb.reshape(shape)
+
+    def matrices(self, i, len_a, len_b):
+        """MODE_MATS: (match, gap_a, gap_b) of pair i as (len_b+1, len_a+1) int32 arrays"""
+        cells = (len_a + 1) * (len_b + 1)
+        m, ga, gb = (np.empty(cells, dtype=np.int32) for _ in range(3))
+        self._check(self._L.seqalign_batch_matrices(self._h, i, m.ctypes.data, ga.ctypes.data, gb.ctypes.data))
+        shape = (len_b + 1, len_a + 1)
         return m.reshape(shape), ga.reshape(shape), gb.reshape(shape)
 
     def speculation_stats(self):

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import seqalign
-from seqalign import NW, SW, MODE_SCORE, MODE_ALIGN, MODE_HITS
+from seqalign import NW, SW, MODE_SCORE, MODE_ALIGN, MODE_HITS, MODE_MATS
 from helpers import (ROOT, SPECS, orc_batch_nw, orc_batch_sw, orc_fill, orc_from_scoring, orc_nw,
                      orc_sw_hits, ragged_batch, scoring_from_spec, synthetic_batch)
 
@@ -308,6 +308,44 @@ def test_matrices(engine, big, name):
             rc, em, ega, egb = orc_fill(o, a, b, is_sw)
             assert rc == 0
             assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (a, b, is_sw)
+
+
+@pytest.mark.parametrize("name", ["sw_cli", "nw_default", "linear_gap", "wild_n", "mutations", "blosum62", "pam30"])
+def test_batch_matrices(engine, big, name):
+    """MODE_MATS: aligner_align() for a whole batch (row-per-step kernel with the gap_b prefix scan):
+    all three matrices of every pair, element for element, against the oracle's fill; widths
+    around the 32-column blocks, empty sequences"""
+    n, maxlen = (60, 200) if big else (10, 45)
+    sa, sb = ragged_batch(5200 + _h(name) % 100, n, maxlen, maxlen, alphabet=_alphabet(name))
+    widths = [31, 32, 33, 63, 64, 65] + ([127, 160, 300, 511] if big else [])
+    for w in widths:
+        x, y = ragged_batch(w, 1, w, w, alphabet=_alphabet(name), min_len=w)
+        sa += [x[0]]; sb += [y[0][: 40 if big else 12]]
+    sa += [b"", sa[0]]; sb += [sb[0], b""]
+    sc = scoring_from_spec(SPECS[name])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    engine.submit(SW, MODE_MATS, sa, sb)
+    assert engine.last_kernel == "mats_sw"
+    scores = engine.scores()
+    for i, (a, b) in enumerate(zip(sa, sb)):
+        m, ga, gb = engine.matrices(i, len(a), len(b))
+        rc, em, ega, egb = orc_fill(o, a, b, True)
+        assert rc == 0
+        assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, i, a, b)
+        assert scores[i] == em.max()
+
+
+def test_batch_matrices_rejects_other_shapes(engine):
+    """scoring shapes outside the specialised kernel are refused, not approximated"""
+    sc = scoring_from_spec(SPECS["no_gaps_a"])
+    engine.set_scoring(sc)
+    with pytest.raises(seqalign.SeqAlignError) as e:
+        engine.submit(SW, MODE_MATS, [b"ACGT"], [b"ACGT"])
+    assert e.value.code == seqalign.ERR_ARG
+    with pytest.raises(seqalign.SeqAlignError):
+        engine.submit(NW, MODE_MATS, [b"ACGT"], [b"ACGT"])
 
 
 @pytest.mark.parametrize("chunk", range(4))
