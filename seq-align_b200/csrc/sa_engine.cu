@@ -909,7 +909,10 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   M.score = (int32_t *)eng->d_score.p;
   M.counter = (unsigned long long *)eng->d_counter.p;
   CU_TRY(cudaEventRecord(eng->ev0, st));
-  if(mats_launch(NB, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
+  /* packed 16-bit prefix scans when every scan value (score + x*|ext|) fits */
+  const long shortest = (long)(bm.max_la < bm.max_lb ? bm.max_la : bm.max_lb);
+  const bool pack = shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
+  if(mats_launch(NB, pack, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
     return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(eng->ev1, st));
@@ -921,7 +924,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   eng->last_ms = ms;
   memcpy(eng->score.data(), eng->h_res.p, n * 4);
-  eng->last_kernel = "mats_sw";
+  eng->last_kernel = pack ? "mats_sw_packed" : "mats_sw";
   return 0;
 }
 

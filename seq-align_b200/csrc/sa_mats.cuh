@@ -42,6 +42,26 @@ namespace sa {
 constexpr int MATS_WARPS = 4;
 constexpr int MATS_NEG = -(1 << 29);
 
+__device__ __forceinline__ void st_stream(int32_t *p, int v)
+{
+#if defined(__CUDA_ARCH__)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
+/* two-input max as a three-input DPX op: VIMNMX3 issues at full rate on the
+ * ALU pipe, the two-input IMNMX only at half rate (tools/microbench.cu) */
+__device__ __forceinline__ int fmax2(int a, int b)
+{
+  int c = b;
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(c));   /* keeps ptxas from folding max3(a,b,b) back into the two-input form */
+#endif
+  return max3(a, b, c);
+}
+
 struct MatsArgs {
   const uint8_t *seq_a, *seq_b;
   const int64_t *off_a, *off_b;
@@ -55,8 +75,31 @@ struct MatsArgs {
   unsigned long long *counter;
 };
 
-/* NB blocks of 32 columns cover x = 0 .. len_a */
+/* one block of a row, everything that needs only row y-1: match, gap_a and
+ * the scan input u = max(M, GA) - x*ext.  diag: H[y-1][x-1] comes from the
+ * lane before; lane 0 takes it from lane 31 of the block before, which that
+ * lane sends instead of its own value (one rotating shuffle, no second one) */
 template <int NB>
+__device__ __forceinline__ void mats_block_head(int j, int lane, int la, const int16_t *prow, const int (&hp)[NB],
+                                                const int (&gap)[NB], int &prev_old, int open, int ext,
+                                                int &m, int &ga, int &u)
+{
+  const int x = 32 * j + lane;
+  const bool cell = x >= 1 && x <= la;
+  const int send = lane == 31 ? prev_old : hp[j];
+  const int diag = __shfl_sync(FULL, send, (lane + 31) & 31);
+  prev_old = hp[j];
+  const int sub = prow[x];
+  m = cell ? addmax(diag, sub, 0) : 0;
+  ga = cell ? max3(gap[j] + ext, hp[j] + open, 0) : 0;
+  u = x <= la ? fmax2(m, ga) - x * ext : 0;          /* x = 0: the border's 0; past len_a: never read by a real cell */
+}
+
+/* NB blocks of 32 columns cover x = 0 .. len_a.
+ * CS: streaming stores (st.global.cs) -- an experiment, no measurable difference.
+ * PACK: the prefix scans of two neighbouring blocks share their shuffles, the two
+ * values packed in the halves of a register (needs every scan value in int16). */
+template <int NB, bool CS, bool PACK>
 __global__ void __launch_bounds__(MATS_WARPS * 32)
 mats_kernel(const MatsArgs A)
 {
@@ -112,42 +155,60 @@ mats_kernel(const MatsArgs A)
       const int c = __shfl_sync(FULL, codes, (y - 1) & 31);
       const int16_t *prow = s_prof + c * PW;
       const int64_t row = (int64_t)y * W;
-      int diag_carry = 0;          /* H[y-1] of the last column of the block before (x = 32j - 1) */
-      int run = MATS_NEG;          /* prefix maximum of T[x'] - x'*ext over the blocks before */
-#pragma unroll
-      for(int j = 0; j < NB; j++) {
+      int prev_old = 0;            /* this lane's H[y-1] in the block before (lane 31's is the one that travels) */
+      int run = MATS_NEG;          /* prefix maximum of u over the blocks before */
+
+      /* the tail of a block: gap_b from the exclusive prefix maximum, H, stores */
+      auto finish = [&](int j, int m, int ga, int excl_in_block, int total) {
         const int x = 32 * j + lane;
         const bool cell = x >= 1 && x <= la;
-        int diag = __shfl_up_sync(FULL, hp[j], 1);
-        if(lane == 0) diag = diag_carry;
-        diag_carry = __shfl_sync(FULL, hp[j], 31);
-        const int sub = prow[x];
-        /* match and gap_a need only the row above (alignment.c:101-137) */
-        const int m = cell ? addmax(diag, sub, 0) : 0;
-        const int ga = cell ? max3(gap[j] + ext, hp[j] + open, 0) : 0;
-        const int tt = x <= la ? imax(m, ga) : MATS_NEG;           /* x = 0: the border's 0 */
-        /* gap_b: exclusive prefix maximum of u along the row */
-        int incl = tt - x * ext;
-#pragma unroll
-        for(int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(FULL, incl, o);
-          if(lane >= o) incl = imax(incl, v);
+        const int excl = lane == 0 ? run : fmax2(excl_in_block, run);
+        run = fmax2(run, total);
+        const int gb = cell ? fmax2(excl + open + (x - 1) * ext, 0) : 0;
+        const int h = max3(m, ga, gb);
+        if(x <= la) {
+          if(CS) { st_stream(pm + row + x, m); st_stream(pga + row + x, ga); st_stream(pgb + row + x, gb); }
+          else { pm[row + x] = m; pga[row + x] = ga; pgb[row + x] = gb; }
         }
-        int excl = __shfl_up_sync(FULL, incl, 1);
-        if(lane == 0) excl = MATS_NEG;
-        excl = imax(excl, run);
-        run = imax(run, __shfl_sync(FULL, incl, 31));
-        const int gb = cell ? imax(excl + open + (x - 1) * ext, 0) : 0;
-        const int h = imax(imax(m, ga), gb);
-        if(x <= la) { pm[row + x] = m; pga[row + x] = ga; pgb[row + x] = gb; }
-        best = imax(best, m);
+        best = fmax2(best, m);
         hp[j] = cell ? h : 0;
         gap[j] = ga;
+      };
+
+      if constexpr(PACK) {
+#pragma unroll
+        for(int j = 0; j < NB; j += 2) {
+          int m0, ga0, u0, m1 = 0, ga1 = 0, u1 = 0;
+          mats_block_head<NB>(j, lane, la, prow, hp, gap, prev_old, open, ext, m0, ga0, u0);
+          if(j + 1 < NB) mats_block_head<NB>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, m1, ga1, u1);
+          unsigned w = ((unsigned)u0 & 0xffffu) | ((unsigned)u1 << 16);
+#pragma unroll
+          for(int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, w, o);
+            if(lane >= o) w = max3_s16x2(w, v, v);
+          }
+          const unsigned e = __shfl_up_sync(FULL, w, 1), tot = __shfl_sync(FULL, w, 31);
+          finish(j, m0, ga0, (int)(short)(e & 0xffffu), (int)(short)(tot & 0xffffu));
+          if(j + 1 < NB) finish(j + 1, m1, ga1, (int)e >> 16, (int)tot >> 16);
+        }
+      } else {
+#pragma unroll
+        for(int j = 0; j < NB; j++) {
+          int m, ga, incl;
+          mats_block_head<NB>(j, lane, la, prow, hp, gap, prev_old, open, ext, m, ga, incl);
+#pragma unroll
+          for(int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if(lane >= o) incl = fmax2(incl, v);
+          }
+          const int e = __shfl_up_sync(FULL, incl, 1), tot = __shfl_sync(FULL, incl, 31);
+          finish(j, m, ga, e, tot);
+        }
       }
     }
     if(A.score) {
 #pragma unroll
-      for(int o = 16; o > 0; o >>= 1) best = imax(best, __shfl_xor_sync(FULL, best, o));
+      for(int o = 16; o > 0; o >>= 1) best = fmax2(best, __shfl_xor_sync(FULL, best, o));
       if(lane == 0) A.score[p] = best;
     }
   }
@@ -167,9 +228,12 @@ inline int mats_blocks(int64_t max_la)
 }
 
 template <int NB>
-int mats_launch_nb(const MatsArgs &M, size_t smem, int num_sms, cudaStream_t st)
+int mats_launch_nb(const MatsArgs &M, bool pack, size_t smem, int num_sms, cudaStream_t st)
 {
-  void (*kfn)(const MatsArgs) = mats_kernel<NB>;
+  const char *cs_env = getenv("SEQALIGN_MATS_STORES");   /* "stream" = st.global.cs (experiments: no measurable difference) */
+  const bool cs = cs_env && cs_env[0] == 's';
+  void (*kfn)(const MatsArgs) = pack ? (cs ? mats_kernel<NB, true, true> : mats_kernel<NB, false, true>)
+                                     : (cs ? mats_kernel<NB, true, false> : mats_kernel<NB, false, false>);
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -180,21 +244,21 @@ int mats_launch_nb(const MatsArgs &M, size_t smem, int num_sms, cudaStream_t st)
   return 0;
 }
 
-inline int mats_launch(int NB, const MatsArgs &M, int ncodes, int num_sms, size_t smem_optin, cudaStream_t st)
+inline int mats_launch(int NB, bool pack, const MatsArgs &M, int ncodes, int num_sms, size_t smem_optin, cudaStream_t st)
 {
   const size_t smem = mats_smem_bytes(NB, ncodes);
   if(smem > smem_optin) return -1;
   switch(NB) {
-    case 1: return mats_launch_nb<1>(M, smem, num_sms, st);
-    case 2: return mats_launch_nb<2>(M, smem, num_sms, st);
-    case 3: return mats_launch_nb<3>(M, smem, num_sms, st);
-    case 4: return mats_launch_nb<4>(M, smem, num_sms, st);
-    case 5: return mats_launch_nb<5>(M, smem, num_sms, st);
-    case 6: return mats_launch_nb<6>(M, smem, num_sms, st);
-    case 8: return mats_launch_nb<8>(M, smem, num_sms, st);
-    case 10: return mats_launch_nb<10>(M, smem, num_sms, st);
-    case 13: return mats_launch_nb<13>(M, smem, num_sms, st);
-    case 16: return mats_launch_nb<16>(M, smem, num_sms, st);
+    case 1: return mats_launch_nb<1>(M, pack, smem, num_sms, st);
+    case 2: return mats_launch_nb<2>(M, pack, smem, num_sms, st);
+    case 3: return mats_launch_nb<3>(M, pack, smem, num_sms, st);
+    case 4: return mats_launch_nb<4>(M, pack, smem, num_sms, st);
+    case 5: return mats_launch_nb<5>(M, pack, smem, num_sms, st);
+    case 6: return mats_launch_nb<6>(M, pack, smem, num_sms, st);
+    case 8: return mats_launch_nb<8>(M, pack, smem, num_sms, st);
+    case 10: return mats_launch_nb<10>(M, pack, smem, num_sms, st);
+    case 13: return mats_launch_nb<13>(M, pack, smem, num_sms, st);
+    case 16: return mats_launch_nb<16>(M, pack, smem, num_sms, st);
   }
   return -1;
 }

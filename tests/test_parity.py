@@ -311,7 +311,7 @@ def test_matrices(engine, big, name):
 
 
 @pytest.mark.parametrize("name", ["sw_cli", "nw_default", "linear_gap", "wild_n", "mutations", "blosum62", "pam30"])
-def test_batch_matrices(engine, big, name):
+def test_batch_matrices(engine, big, name, monkeypatch):
     """MODE_MATS: aligner_align() for a whole batch (row-per-step kernel with the gap_b prefix scan):
     all three matrices of every pair, element for element, against the oracle's fill; widths
     around the 32-column blocks, empty sequences"""
@@ -326,15 +326,18 @@ def test_batch_matrices(engine, big, name):
     o = orc_from_scoring(sc)
     engine.set_scoring(sc)
     engine.force_general(0)
-    engine.submit(SW, MODE_MATS, sa, sb)
-    assert engine.last_kernel == "mats_sw"
-    scores = engine.scores()
-    for i, (a, b) in enumerate(zip(sa, sb)):
-        m, ga, gb = engine.matrices(i, len(a), len(b))
-        rc, em, ega, egb = orc_fill(o, a, b, True)
-        assert rc == 0
-        assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, i, a, b)
-        assert scores[i] == em.max()
+    for nopack in ("", "1"):     # packed 16-bit prefix scans / plain int32 scans
+        if nopack:
+            monkeypatch.setenv("SEQALIGN_MATS_NOPACK", "1")
+        engine.submit(SW, MODE_MATS, sa, sb)
+        assert engine.last_kernel == ("mats_sw" if nopack else "mats_sw_packed")
+        scores = engine.scores()
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            m, ga, gb = engine.matrices(i, len(a), len(b))
+            rc, em, ega, egb = orc_fill(o, a, b, True)
+            assert rc == 0
+            assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, nopack, i, a, b)
+            assert scores[i] == em.max()
 
 
 def test_batch_matrices_rejects_other_shapes(engine):
