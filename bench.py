@@ -313,7 +313,9 @@ def main():
     checksum = int(d_score.sum().item())
 
     # ---- end-to-end arm (host buffers through the C-ABI) ----------------------
-    run_host_steps(0, args.warmup)
+    # warm-up: enough submissions that every engine of the pipeline has made its first call
+    # (device / pinned allocations happen there), at least the W the caller asked for
+    run_host_steps(0, max(args.warmup, 2 * E2E_DEPTH))
     barrier()
     t0 = time.perf_counter()
     e2e_checksum = run_host_steps(args.warmup, args.steps)
