@@ -945,10 +945,13 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   if(n == 0) return 0;
   cudaStream_t st = eng->stream;
   const int64_t total_a = h_off_a[n], total_b = h_off_b[n];
+  bool uniform_batch = true;   /* every pair la0 x lb0: the device can make the offsets itself */
+  const int64_t la0 = h_off_a[1] - h_off_a[0], lb0 = h_off_b[1] - h_off_b[0];
   for(size_t i = 0; i < n; i++) {
     const int64_t la = h_off_a[i + 1] - h_off_a[i], lb = h_off_b[i + 1] - h_off_b[i];
     if(la < 0 || lb < 0 || la > (1 << 30) || lb > (1 << 30))
       return fail(eng, SEQALIGN_ERR_ARG, "bad offsets / sequence too long");
+    uniform_batch = uniform_batch && la == la0 && lb == lb0;
   }
   TRY(ensure_dev(eng, eng->d_seq_a, (size_t)total_a + 32));
   TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
@@ -977,8 +980,17 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     const char *env = getenv("SEQALIGN_CHUNKS");
     if(env && atoi(env) >= 1 && atoi(env) <= seqalign_batch::MAX_CHUNKS) nchunks = atoi(env);
     if((size_t)nchunks > n) nchunks = (int)n;
-    CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
-    CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    if(uniform_batch && n >= 4096) {
+      int ogrid = (int)((n + 256) / 256);
+      if(ogrid > eng->num_sms * 8) ogrid = eng->num_sms * 8;
+      SA_LAUNCH(uniform_offsets_kernel, ogrid, 256, 0, cs, (int64_t *)eng->d_off_a.p, (int64_t *)eng->d_off_b.p,
+                (int64_t)n, la0, lb0);
+      CU_TRY(cudaGetLastError());
+      eng->last_launches++;
+    } else {
+      CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+      CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    }
     size_t bounds[seqalign_batch::MAX_CHUNKS + 1];
     for(int c = 0; c <= nchunks; c++) bounds[c] = n * (size_t)c / (size_t)nchunks;
     for(int c = 0; c < nchunks; c++) {

@@ -48,6 +48,18 @@ struct ScoreParams {
 enum { META_PRES_A = 0, META_PRES_B = 4, META_MAX_LA = 8, META_MAX_LB = 9,
        META_CELLS = 10, META_MAX_CELLS = 11, META_MIN_LA = 12, META_MIN_LB = 13, META_WORDS = 16 };
 
+/* offsets of a batch whose sequences all have the same length: off[i] = i*len.
+ * Such a batch (every BASELINE config) does not ship its offset arrays over
+ * PCIe -- 16 bytes per pair, 5 % of a 150 bp batch -- they are made here. */
+__global__ void __launch_bounds__(256)
+uniform_offsets_kernel(int64_t *__restrict__ off_a, int64_t *__restrict__ off_b, int64_t n, int64_t la, int64_t lb)
+{
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+    off_a[i] = i * la;
+    off_b[i] = i * lb;
+  }
+}
+
 /* ---------------------------------------------------------------------------
  * scan_kernel: which byte values occur in seq_a / seq_b (256-bit sets), the
  * longest sequences and the cell count.  The host needs the alphabet to turn

@@ -117,6 +117,24 @@ def test_fast16_tight_shapes(engine, big, la):
     engine.force_general(0)
 
 
+def test_uniform_batch_offsets_made_on_device(engine, big):
+    """a host batch of >= 4096 equal-shaped pairs does not ship its offset arrays: the engine
+    generates them on the device; results must equal the ragged path's (one pair trimmed)"""
+    n, la, lb = 4200, (150 if big else 7), (150 if big else 6)
+    a, oa, b, ob = synthetic_batch(31, n, la, lb)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    es, ex, ey = orc_batch_sw(orc_from_scoring(sc), a, oa, b, ob)
+    engine.set_scoring(sc)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s, x, y = engine.ends()
+    assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
+    # same sequences, last pair one base shorter: not uniform any more, offsets travel as before
+    ob2 = ob.copy(); ob2[-1] -= 1
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob2)
+    s2, _, _ = engine.ends()
+    assert np.array_equal(s2[:-1], es[:-1])
+
+
 def test_protein_config_sample(engine, big):
     """BASELINE config 4 shape: SW, protein 400x400, BLOSUM62"""
     n, L = (400, 400) if big else (2, 70)
