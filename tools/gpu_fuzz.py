@@ -51,13 +51,20 @@ while time.time() < t_end:
     sc, desc, alpha = model()
     maxlen = int([20, 60, 150, 300, 512, 700][int(rng.integers(0, 6))])
     n = int(rng.integers(3, 400 if maxlen <= 150 else 60))
-    sa, sb = ragged_batch(int(rng.integers(0, 1 << 30)), n, maxlen, maxlen, alphabet=alpha, min_len=int(rng.integers(0, 2)))
+    uniform = rng.random() < 0.15 and maxlen <= 512     # one shape for the whole batch: the packed 16-bit kernel's case
+    if uniform:
+        la_u, lb_u = int(rng.integers(1, maxlen + 1)), int(rng.integers(1, maxlen + 1))
+        ua, uoa, ub, uob = synthetic_batch(int(rng.integers(0, 1 << 30)), n, la_u, lb_u, kind="protein" if alpha == PROT else "dna")
+        sa = [ua[i * la_u:(i + 1) * la_u].tobytes() for i in range(n)]; sb = [ub[i * lb_u:(i + 1) * lb_u].tobytes() for i in range(n)]
+    else:
+        sa, sb = ragged_batch(int(rng.integers(0, 1 << 30)), n, maxlen, maxlen, alphabet=alpha, min_len=int(rng.integers(0, 2)))
     a, oa = seqalign.pack(sa); b, ob = seqalign.pack(sb)
     o = orc_from_scoring(sc)
     eng.set_scoring(sc)
     algo = SW if rng.random() < 0.6 else NW
     if unsafe(sc, algo): algo = SW
     mode = [MODE_SCORE, MODE_ALIGN, MODE_HITS, MODE_MATS, MODE_SCORE_ONLY][int(rng.integers(0, 5))]
+    if uniform and rng.random() < 0.7: algo, mode = SW, MODE_SCORE_ONLY
     if algo == NW and mode in (MODE_HITS, MODE_MATS): mode = MODE_ALIGN
     eng.force_general(1 if rng.random() < 0.1 and mode in (MODE_SCORE, MODE_ALIGN) else 0)
     eng.set_hit_limits(8, 1)
