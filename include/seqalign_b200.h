@@ -200,7 +200,8 @@ const char *seqalign_batch_last_kernel(const seqalign_batch_t *eng);
 /* kernel selection knob for tests: 0 = automatic; 1 = general kernel only;
  * 2 = specialised kernel with per-column end-cell keys; 3 = specialised
  * kernel without end-cell tracking (x_end/y_end come back 0; packed 16-bit
- * kernel when the batch qualifies); 4 = like 3 but int32 arithmetic only. */
+ * kernel when the batch qualifies); 4 = like 3 but int32 arithmetic only;
+ * 5 = automatic, but int32 arithmetic only. */
 void seqalign_batch_force_general(seqalign_batch_t *eng, int on);
 
 #ifdef __cplusplus

@@ -76,7 +76,7 @@ struct seqalign_batch {
     int64_t max_lb = 0;
   } spec;
   int spec_hits = 0, spec_misses = 0;
-  int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only */
+  int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only, 5 = auto but int32 only */
 
   /* inputs on device */
   DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
@@ -458,7 +458,9 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
   FastPlan plan;
   const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
-  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb && eng->force_mode != 4;
+  /* force modes 2, 4 and 5 keep to the int32 kernels */
+  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb && eng->force_mode != 4 &&
+                       eng->force_mode != 2 && eng->force_mode != 5;
   if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &plan)) {
     if(eng->force_mode == 2 && plan.track == TRACK_TREE) { plan.track = TRACK_COLUMN; plan.name = "fast_sw_score_endcol"; }
     const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);

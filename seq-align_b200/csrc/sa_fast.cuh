@@ -67,6 +67,7 @@ struct FastPlan {
   int track = 0;
   bool prof32 = false;
   bool s16 = false;   /* two pairs per register (fast16_kernel) */
+  bool s16_ends = false; /* ... with the SW end cell tracked in 16-bit keys */
   bool dir = false;   /* also write traceback flag bytes */
   bool hits = false;  /* ... and int16 match scores (multi-hit stage) */
   size_t smem = 0;
@@ -570,7 +571,15 @@ __device__ __forceinline__ void fast16_load_rows(unsigned pl, unsigned ph, unsig
   }
 }
 
-template <int G, int K>
+/* ENDS: also the SW end cell (x_end, y_end) under the reference's hit order.
+ * Every cell's match score gets the column index appended, key = M* x 32 +
+ * (31 - j), by one packed IMAD (scores below 1024 leave the room inside int16);
+ * the row's best key comes out of the same max3 tree as before, and the ROW is
+ * tracked once per row step (did the lane's best key grow?) instead of once
+ * per cell.  A larger key is a higher score or, at equal score, a smaller
+ * column; a later row only replaces an equal score if its column is smaller:
+ * that is (score desc, x asc, y asc), smith_waterman.c:71-86. */
+template <int G, int K, bool ENDS>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast16_kernel(const FastArgs A)
 {
@@ -716,7 +725,9 @@ fast16_kernel(const FastArgs A)
     unsigned hp[K], ga[K];
 #pragma unroll
     for(int j = 0; j < K; j++) { hp[j] = 0; ga[j] = BB; }
-    unsigned best = BB, hd = 0, out_h = 0, out_gb = BB;
+    unsigned best = ENDS ? BB * 32u : BB, hd = 0, out_h = 0, out_gb = BB;
+    int ylo = 0, yhi = 0;
+    const unsigned mul_key = (unsigned)A.mul_key;
 
     int maxlb = lb;
 #pragma unroll
@@ -755,7 +766,7 @@ fast16_kernel(const FastArgs A)
         } else {
           fast16_load_rows<KW, 1>(pl, ph, wl, wh, dsm);
         }
-        unsigned d = hd, kprev = BB;
+        unsigned d = hd, kprev = ENDS ? 0u : BB, rowkey = 0;
 #pragma unroll
         for(int j = 0; j < K; j++) {
           const unsigned sub = pack_sub2_dyn(wl[j / 4], wh[j / 4], j & 3);
@@ -763,12 +774,28 @@ fast16_kernel(const FastArgs A)
           ga[j] = addmax_s16x2(ga[j], EXT2, hp[j]);
           gb = addmax_s16x2(gb, EXT2, hl);
           const unsigned h = max3_s16x2(m, ga[j], gb);
-          if(j & 1) best = max3_s16x2(best, kprev, m);
-          else if(j == K - 1) best = max3_s16x2(best, m, m);
-          kprev = m;
+          if constexpr(ENDS) {
+            const unsigned kk = m * mul_key + (unsigned)((31 - j) * 0x10001);   /* both halves: M* x 32 + (31 - j) */
+            if(j & 1) rowkey = max3_s16x2(rowkey, kprev, kk);
+            else if(j == K - 1) rowkey = max3_s16x2(rowkey, kk, kk);
+            kprev = kk;
+          } else {
+            if(j & 1) best = max3_s16x2(best, kprev, m);
+            else if(j == K - 1) best = max3_s16x2(best, m, m);
+            kprev = m;
+          }
           d = hp[j];
           hl = h * mul_one + OPENC;   /* packed H* + open, see header */
           hp[j] = hl;
+        }
+        if constexpr(ENDS) {
+          /* once per row: where the lane's best key grew, this row is its row */
+          const unsigned nb = max3_s16x2(best, rowkey, rowkey);
+          const unsigned grew = nb ^ best;
+          const int y = s - lig + 1;
+          if(grew & 0xffffu) ylo = y;
+          if(grew >> 16) yhi = y;
+          best = nb;
         }
         out_h = hl;
         out_gb = gb;
@@ -776,21 +803,44 @@ fast16_kernel(const FastArgs A)
       }
     }
 
+    if constexpr(ENDS) {
+      /* per half: (score, x, y) of the lane, then the group's best under the hit order */
+      int sv[2], sx[2], sy[2];
 #pragma unroll
-    for(int o = G / 2; o > 0; o >>= 1) {
-      const unsigned v = __shfl_xor_sync(FULL, best, o);
-      best = max3_s16x2(best, v, v);
-    }
-    if(lig == 0) {
-      if(have_lo) {
-        A.score[plo] = (int)(best & 0xffffu) - (int)B;
-        if(A.xend) A.xend[plo] = 0;
-        if(A.yend) A.yend[plo] = 0;
+      for(int hsel = 0; hsel < 2; hsel++) {
+        const int key = (int)((best >> (16 * hsel)) & 0xffffu);
+        sv[hsel] = (key >> 5) - (int)B;
+        sx[hsel] = sv[hsel] > 0 ? xf + 31 - (key & 31) : 0;
+        sy[hsel] = sv[hsel] > 0 ? (hsel ? yhi : ylo) : 0;
+#pragma unroll
+        for(int o = G / 2; o > 0; o >>= 1) {
+          const int v2 = __shfl_xor_sync(FULL, sv[hsel], o);
+          const int x2 = __shfl_xor_sync(FULL, sx[hsel], o);
+          const int y2 = __shfl_xor_sync(FULL, sy[hsel], o);
+          if(hit_better(v2, x2, y2, sv[hsel], sx[hsel], sy[hsel])) { sv[hsel] = v2; sx[hsel] = x2; sy[hsel] = y2; }
+        }
       }
-      if(have_hi) {
-        A.score[phi] = (int)(best >> 16) - (int)B;
-        if(A.xend) A.xend[phi] = 0;
-        if(A.yend) A.yend[phi] = 0;
+      if(lig == 0) {
+        if(have_lo) { A.score[plo] = sv[0]; if(A.xend) A.xend[plo] = sx[0]; if(A.yend) A.yend[plo] = sy[0]; }
+        if(have_hi) { A.score[phi] = sv[1]; if(A.xend) A.xend[phi] = sx[1]; if(A.yend) A.yend[phi] = sy[1]; }
+      }
+    } else {
+#pragma unroll
+      for(int o = G / 2; o > 0; o >>= 1) {
+        const unsigned v = __shfl_xor_sync(FULL, best, o);
+        best = max3_s16x2(best, v, v);
+      }
+      if(lig == 0) {
+        if(have_lo) {
+          A.score[plo] = (int)(best & 0xffffu) - (int)B;
+          if(A.xend) A.xend[plo] = 0;
+          if(A.yend) A.yend[plo] = 0;
+        }
+        if(have_hi) {
+          A.score[phi] = (int)(best >> 16) - (int)B;
+          if(A.xend) A.xend[phi] = 0;
+          if(A.yend) A.yend[phi] = 0;
+        }
       }
     }
 
@@ -853,9 +903,11 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   const bool fits8 = lo >= -127 && hi <= 127 && (long)padsub - sp.open >= -127 && (long)padsub - sp.open <= 127;
   /* packed 16-bit kernel: SW score only, one shape for the whole batch, and
    * every biased value (score + |open|) inside int16 */
-  const bool s16 = sp.is_sw && !want_ends && !want_dir && uniform && fits8 &&
-                   shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open < 32000 && sp.open > -16000 &&
-                   ft.min_sub > -16000;
+  const long best_biased = shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open;   /* largest M + B */
+  /* ... with the end cell: the 16-bit key is (M + B) x 32 + column, so M + B must stay below 1024 */
+  const bool s16_ends = want_ends && best_biased < 1024 && max_lb <= 32767;
+  const bool s16 = sp.is_sw && (!want_ends || s16_ends) && !want_dir && uniform && fits8 &&
+                   best_biased < 32000 && sp.open > -16000 && ft.min_sub > -16000;
   int G = 0, K = 0;
   if(s16) {
     /* the packed kernel has extra shapes that fit common read lengths tightly */
@@ -872,6 +924,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   if(!prof32 && !fits8) return false;
   if(s16) prof32 = false;
   plan->s16 = s16;
+  plan->s16_ends = s16 && want_ends;
   plan->dir = want_dir;
   plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
@@ -907,7 +960,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
     plan->name = sp.is_sw ? "fast_sw_dir" : "fast_nw_dir";
     return true;
   }
-  plan->name = !sp.is_sw ? "fast_nw_score" : s16 ? "fast16_sw_score"
+  plan->name = !sp.is_sw ? "fast_nw_score" : (s16 && want_ends) ? "fast16_sw_score_end" : s16 ? "fast16_sw_score"
              : plan->track == TRACK_NONE ? "fast_sw_score" : plan->track == TRACK_TREE ? "fast_sw_score_end" : "fast_sw_score_endcol";
   return true;
 }
@@ -957,7 +1010,7 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
 #define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
-    void (*kfn)(const FastArgs) = fast16_kernel<g, k>;                                        \
+    void (*kfn)(const FastArgs) = plan.s16_ends ? fast16_kernel<g, k, true> : fast16_kernel<g, k, false>; \
     /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
     const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
     const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \

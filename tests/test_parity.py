@@ -89,7 +89,13 @@ def test_headline_config_sample(engine, big):
     a, oa, b, ob = synthetic_batch(2, n, 150, 150)
     sc = scoring_from_spec(SPECS["sw_cli"])
     k = _score_check(engine, sc, SW, a, oa, b, ob, general=False)
-    assert k == "fast_sw_score_end"
+    assert k == "fast16_sw_score_end"     # uniform batch, scores below 1024: end cells from the packed kernel
+    engine.force_general(5)               # the int32 tree kernel on the same batch
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast_sw_score_end"
+    es, ex, ey = orc_batch_sw(orc_from_scoring(sc), a, oa, b, ob)
+    s5, x5, y5 = engine.ends()
+    assert np.array_equal(s5, es) and np.array_equal(x5, ex) and np.array_equal(y5, ey)
     engine.force_general(3)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
     assert engine.last_kernel == "fast16_sw_score"
@@ -115,6 +121,15 @@ def test_fast16_tight_shapes(engine, big, la):
     assert engine.last_kernel == "fast16_sw_score"
     assert np.array_equal(engine.scores(), es)
     engine.force_general(0)
+    # with end cells: the same shapes through the 16-bit keys (ties between equal scores are
+    # frequent on unrelated pairs: x ascending first, then y)
+    for related in (True, False):
+        a, oa, b, ob = synthetic_batch(1900 + la, n, la, lb, related=related)
+        es, ex, ey = orc_batch_sw(orc_from_scoring(sc), a, oa, b, ob)
+        engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+        assert engine.last_kernel == "fast16_sw_score_end"
+        s, x, y = engine.ends()
+        assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey), (la, related)
 
 
 def test_uniform_batch_offsets_made_on_device(engine, big):
@@ -475,7 +490,12 @@ def test_full_size_invariants(engine, big):
     engine.force_general(False)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
     s, x, y = engine.ends()
+    assert engine.last_kernel == "fast16_sw_score_end"
+    engine.force_general(5)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    s5, x5, y5 = engine.ends()
     assert engine.last_kernel == "fast_sw_score_end"
+    assert np.array_equal(s, s5) and np.array_equal(x, x5) and np.array_equal(y, y5)
     engine.force_general(True)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
     s2, x2, y2 = engine.ends()

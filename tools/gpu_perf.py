@@ -29,7 +29,8 @@ def timeit(tag, name, algo, force, a, oa, b, ob, cells, reps=4, check=None):
 
 A, OA, B, OB = synthetic_batch(2, 100000, 150, 150)
 c = 100000 * 22500.0
-ref = timeit("dna150 auto(end,tree)", "sw_cli", seqalign.SW, 0, A, OA, B, OB, c)
+ref = timeit("dna150 auto (end cell, packed 16-bit keys)", "sw_cli", seqalign.SW, 0, A, OA, B, OB, c)
+timeit("dna150 end cell, int32 tree", "sw_cli", seqalign.SW, 5, A, OA, B, OB, c, check=ref)
 timeit("dna150 end,column", "sw_cli", seqalign.SW, 2, A, OA, B, OB, c, check=ref)
 timeit("dna150 score-only s16x2", "sw_cli", seqalign.SW, 3, A, OA, B, OB, c, check=ref)
 timeit("dna150 score-only int32", "sw_cli", seqalign.SW, 4, A, OA, B, OB, c, check=ref)
@@ -39,6 +40,7 @@ timeit("dna150 libdefault sw", "nw_default", seqalign.SW, 0, A, OA, B, OB, c)
 PA, POA, PB, POB = synthetic_batch(4, 50000, 400, 400, kind="protein")
 c4 = 50000 * 160000.0
 ref = timeit("prot400 auto", "blosum62", seqalign.SW, 0, PA, POA, PB, POB, c4)
+timeit("prot400 end cell, int32 tree", "blosum62", seqalign.SW, 5, PA, POA, PB, POB, c4, check=ref)
 timeit("prot400 score-only s16x2", "blosum62", seqalign.SW, 3, PA, POA, PB, POB, c4, check=ref)
 timeit("prot400 score-only int32", "blosum62", seqalign.SW, 4, PA, POA, PB, POB, c4, check=ref)
 for L in (64, 100, 128, 250, 300, 512):
