@@ -615,7 +615,9 @@ fast16_kernel(const FastArgs A)
   const unsigned B = (unsigned)(-open);
   const unsigned BB = B | (B << 16);
   const unsigned EXT2 = ((unsigned)ext & 0xffffu) | ((unsigned)ext << 16);
-  const unsigned OPENC = (((unsigned)(open - 1) & 0xffffu) << 16) | ((unsigned)open & 0xffffu);
+  /* open < 0: the low half always carries (H* >= B = -open), the -1 in the high half absorbs it.
+   * open == 0 (gap_open = gap_extend = 0): nothing to add and no carry to absorb */
+  const unsigned OPENC = open == 0 ? 0u : ((((unsigned)(open - 1) & 0xffffu) << 16) | ((unsigned)open & 0xffffu));
   const unsigned mul_one = (unsigned)A.mul_one;
   const int64_t nsets = (A.npairs + NP - 1) / NP;
 

@@ -237,6 +237,7 @@ SPECS = {
     "free_start": dict(init=[1, -1, -4, -1, 1, 0, 0, 0, 0, 0]),
     "free_end": dict(init=[1, -1, -4, -1, 0, 1, 0, 0, 0, 0]),
     "linear_gap": dict(init=[2, -3, 0, -2, 0, 0, 0, 0, 0, 0]),
+    "free_gaps": dict(init=[3, -2, 0, 0, 0, 0, 0, 0, 0, 0]),      # gaps cost nothing (found by tools/gpu_fuzz.py: open == 0)
     "no_gaps_a": dict(init=[1, -2, -4, -1, 0, 0, 1, 0, 0, 0]),
     "no_gaps_b": dict(init=[1, -2, -4, -1, 0, 0, 0, 1, 0, 0]),
     "no_mismatch": dict(init=[1, -2, -4, -1, 0, 0, 0, 0, 1, 0]),

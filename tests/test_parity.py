@@ -132,6 +132,27 @@ def test_fast16_tight_shapes(engine, big, la):
         assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey), (la, related)
 
 
+@pytest.mark.parametrize("name", ["free_gaps", "linear_gap", "nw_default", "blosum62"])
+def test_fast16_gap_models(engine, big, name):
+    """packed kernel under gap models at the edges of its "+open" trick: gap_open = gap_extend = 0
+    (nothing to add, no carry between the halves -- the fuzzer's find), linear gaps, protein tables;
+    scores alone and with end cells"""
+    n, la, lb = (301, 150, 140) if big else (7, 30, 26)
+    a, oa, b, ob = synthetic_batch(77, n, la, lb, kind="protein" if name == "blosum62" else "dna")
+    sc = scoring_from_spec(SPECS[name])
+    es, ex, ey = orc_batch_sw(orc_from_scoring(sc), a, oa, b, ob)
+    engine.set_scoring(sc)
+    engine.force_general(3)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast16_sw_score"
+    assert np.array_equal(engine.scores(), es)
+    engine.force_general(0)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast16_sw_score_end"
+    s, x, y = engine.ends()
+    assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
+
+
 def test_uniform_batch_offsets_made_on_device(engine, big):
     """a host batch of >= 4096 equal-shaped pairs does not ship its offset arrays: the engine
     generates them on the device; results must equal the ragged path's (one pair trimmed)"""
