@@ -148,7 +148,8 @@ def test_fast16_gap_models(engine, big, name):
     assert np.array_equal(engine.scores(), es)
     engine.force_general(0)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
-    assert engine.last_kernel == "fast16_sw_score_end"
+    # 16-bit keys need (score + |open|) < 1024: 140 x 11 with BLOSUM62 is past that, the int32 tree kernel takes over
+    assert engine.last_kernel == ("fast_sw_score_end" if name == "blosum62" and big else "fast16_sw_score_end")
     s, x, y = engine.ends()
     assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
 
