@@ -64,7 +64,7 @@ while time.time() < t_end:
     algo = SW if rng.random() < 0.6 else NW
     if unsafe(sc, algo): algo = SW
     mode = [MODE_SCORE, MODE_ALIGN, MODE_HITS, MODE_MATS, MODE_SCORE_ONLY][int(rng.integers(0, 5))]
-    if uniform and rng.random() < 0.7: algo, mode = SW, MODE_SCORE_ONLY
+    if uniform and rng.random() < 0.9: algo, mode = SW, (MODE_SCORE_ONLY if rng.random() < 0.5 else MODE_SCORE)
     if algo == NW and mode in (MODE_HITS, MODE_MATS): mode = MODE_ALIGN
     eng.force_general(1 if rng.random() < 0.1 and mode in (MODE_SCORE, MODE_ALIGN) else 0)
     eng.set_hit_limits(8, 1)
