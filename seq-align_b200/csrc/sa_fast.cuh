@@ -580,7 +580,7 @@ __device__ __forceinline__ void fast16_load_rows(unsigned pl, unsigned ph, unsig
  * column; a later row only replaces an equal score if its column is smaller:
  * that is (score desc, x asc, y asc), smith_waterman.c:71-86. */
 template <int G, int K, bool ENDS>
-__global__ void __launch_bounds__(FAST_WARPS * 32, (K <= 19 && !ENDS) ? 6 : 5)
+__global__ void __launch_bounds__(FAST_WARPS * 32)
 fast16_kernel(const FastArgs A)
 {
   constexpr int NG = 32 / G;              /* couples per warp */
@@ -598,12 +598,11 @@ fast16_kernel(const FastArgs A)
   uint8_t *s_lut = dsm + 64;
   int8_t *s_tab8 = (int8_t *)(dsm + 64 + 256);
   const int tab_bytes = (n * tw + 15) & ~15;
-  /* seq_a is not staged: it is read once per pair set, straight from global
-   * memory, while the profile is built (the shared memory buys a sixth CTA) */
-  const int warp_bytes = 2 * n * PSTRIDE + 2 * NP * A.b_stage;
+  const int warp_bytes = 2 * n * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
   unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
   unsigned char *s_prof = wbase;                           /* [half][code][PSTRIDE] */
-  unsigned char *s_b = wbase + 2 * n * PSTRIDE;            /* [stage][pair][b_stage] */
+  unsigned char *s_a = wbase + 2 * n * PSTRIDE;            /* [stage][pair][a_stage] */
+  unsigned char *s_b = s_a + 2 * NP * A.a_stage;
   uint64_t *bar = s_bar + wib * 2;
 
   for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
@@ -631,6 +630,7 @@ fast16_kernel(const FastArgs A)
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;   /* does not fit the plan: skipped, see below */
+        if(ea > oa) bytes += (uint32_t)(((ea + 15) & ~(int64_t)15) - (oa & ~(int64_t)15));
         if(eb > ob) bytes += (uint32_t)(((eb + 15) & ~(int64_t)15) - (ob & ~(int64_t)15));
       }
       mbar_expect_tx(&bar[st], bytes);
@@ -640,7 +640,9 @@ fast16_kernel(const FastArgs A)
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;
-        const int64_t b0 = ob & ~(int64_t)15;
+        const int64_t a0 = oa & ~(int64_t)15, b0 = ob & ~(int64_t)15;
+        if(ea > oa)
+          bulk_g2s(s_a + (st * NP + g) * A.a_stage, A.seq_a + a0, (uint32_t)(((ea + 15) & ~(int64_t)15) - a0), &bar[st]);
         if(eb > ob)
           bulk_g2s(s_b + (st * NP + g) * A.b_stage, A.seq_b + b0, (uint32_t)(((eb + 15) & ~(int64_t)15) - b0), &bar[st]);
       }
@@ -664,13 +666,11 @@ fast16_kernel(const FastArgs A)
     /* this group's couple: pair plo in the low halves, phi in the high halves */
     const int64_t plo = t * NP + 2 * grp, phi = plo + 1;
     const bool have_lo = plo < A.npairs, have_hi = phi < A.npairs;
-    int la = 0, lb = 0, shb_lo = 0, shb_hi = 0;
-    const uint8_t *ra_lo = A.seq_a, *ra_hi = A.seq_a;   /* seq_a of the two pairs, in global memory */
+    int la = 0, lb = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
     if(have_lo) {
       const int64_t oa = A.off_a[plo], ob = A.off_b[plo];
       la = (int)(A.off_a[plo + 1] - oa); lb = (int)(A.off_b[plo + 1] - ob);   /* uniform batch: same for phi */
-      shb_lo = (int)(ob & 15);
-      ra_lo = ra_hi = A.seq_a + oa;
+      sha_lo = (int)(oa & 15); shb_lo = (int)(ob & 15);
     }
     if(have_hi) {
       /* speculative launches only: shapes the plan did not foresee become empty pairs */
@@ -678,12 +678,14 @@ fast16_kernel(const FastArgs A)
       if(la_hi != la || lb_hi != lb) { la = 0; lb = 0; }
     }
     if(la > G * K || lb > A.max_lb) { la = 0; lb = 0; }
-    if(have_hi) { ra_hi = A.seq_a + A.off_a[phi]; shb_hi = (int)(A.off_b[phi] & 15); }
+    if(have_hi) { sha_hi = (int)(A.off_a[phi] & 15); shb_hi = (int)(A.off_b[phi] & 15); }
     mbar_wait(&bar[stage], stage ? phase1 : phase0);
     if(stage) phase1 ^= 1; else phase0 ^= 1;
 
     const int slot_lo = stage * NP + 2 * grp, slot_hi = have_hi ? slot_lo + 1 : slot_lo;
+    unsigned char *ra_lo = s_a + slot_lo * A.a_stage + sha_lo;
     unsigned char *rb_lo = s_b + slot_lo * A.b_stage + shb_lo;
+    unsigned char *ra_hi = s_a + slot_hi * A.a_stage + (have_hi ? sha_hi : sha_lo);
     unsigned char *rb_hi = s_b + slot_hi * A.b_stage + (have_hi ? shb_hi : shb_lo);
 
     /* seq_b of both pairs: raw bytes -> codes, in place (a missing high pair aliases the low one) */
@@ -700,7 +702,7 @@ fast16_kernel(const FastArgs A)
     const int xf = lig * K + 1;
 #pragma unroll
     for(int half = 0; half < 2; half++) {
-      const uint8_t *ra = half ? ra_hi : ra_lo;
+      const unsigned char *ra = half ? ra_hi : ra_lo;   /* seq_a stays raw in shared memory */
       int acode[K];
 #pragma unroll
       for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : n;
@@ -934,7 +936,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
     /* exact sizes (a fifth CTA per SM depends on them): a bulk copy brings at
      * most floor16(len + 30) bytes; the packed kernel also reads seq_b codes one
      * row ahead in every lane, up to G + 1 bytes past the end of the sequence */
-    plan->a_stage = 0;   /* the packed kernel reads seq_a from global memory */
+    plan->a_stage = (int)((G * K + 15 + 15) & ~15);
     plan->b_stage = (int)((max_lb + 15 + 15 + G + 1) & ~(int64_t)15);
   }
   plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
