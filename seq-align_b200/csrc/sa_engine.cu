@@ -1337,11 +1337,12 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
     const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
     /* the scan runs on the side stream, next to the DP kernel */
     cudaStream_t cs = eng->copy_stream;
+    /* the DP kernel goes first: the scan's handful of launches would otherwise sit in front of it */
     CU_TRY(cudaEventRecord(eng->ev_copy[0], st));
-    CU_TRY(cudaStreamWaitEvent(cs, eng->ev_copy[0], 0));
-    TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, approx_bytes, cs));
     TRY(launch_fast_score(eng, eng->spec.plan, sp, db, eng->spec.max_lb, (int32_t *)d_score,
                           (int32_t *)d_x_end, (int32_t *)d_y_end, st, eng->ev0, eng->ev1));
+    CU_TRY(cudaStreamWaitEvent(cs, eng->ev_copy[0], 0));
+    TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, approx_bytes, cs));
     TRY(scan_collect(eng, n, cs, &bm));
     CU_TRY(cudaStreamSynchronize(st));
     uint64_t pres[8];

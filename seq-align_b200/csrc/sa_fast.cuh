@@ -967,12 +967,31 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   return true;
 }
 
-/* persistent grid: exactly as many CTAs as are resident at once */
+/* Shared-memory opt-in and resident CTAs per SM of a kernel, asked from the
+ * runtime once per (kernel, shared memory, device, host thread) and remembered:
+ * the two runtime calls cost several microseconds on every launch otherwise. */
+struct FastKernelInfo { const void *fn; size_t smem; int device; int per_sm; };
+template <class KF>
+int fast_per_sm(KF kfn, size_t smem)
+{
+  thread_local std::vector<FastKernelInfo> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for(const FastKernelInfo &k : cache)
+    if(k.fn == (const void *)kfn && k.smem == smem && k.device == dev) return k.per_sm;
+  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  int per_sm = 1;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, FAST_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cache.push_back({(const void *)kfn, smem, dev, per_sm});
+  return per_sm;
+}
+
+/* persistent grid: exactly as many CTAs as are resident at once; -1 if the kernel cannot take this much shared memory */
 template <class KF>
 int fast_grid(KF kfn, size_t smem, int num_sms, int64_t need)
 {
-  int per_sm = 1;
-  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, FAST_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int per_sm = fast_per_sm(kfn, smem);
+  if(per_sm < 0) return -1;
   int64_t grid = (int64_t)num_sms * per_sm;
   if(grid > need) grid = need;
   return grid < 1 ? 1 : (int)grid;
@@ -997,8 +1016,9 @@ int fast_launch_gkp(const FastPlan &plan, const FastArgs &F, int num_sms, int64_
   else if(plan.track == TRACK_TREE) kfn = fast_score_kernel<G, K, true, TRACK_TREE, P32, false>;
   else kfn = fast_score_kernel<G, K, true, TRACK_COLUMN, P32, false>;
   if(!kfn) return -1;
-  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
-  SA_LAUNCH(kfn, fast_grid(kfn, plan.smem, num_sms, need), FAST_WARPS * 32, plan.smem, st, F);
+  const int grid = fast_grid(kfn, plan.smem, num_sms, need);
+  if(grid < 0) return -1;
+  SA_LAUNCH(kfn, grid, FAST_WARPS * 32, plan.smem, st, F);
   return 0;
 }
 
@@ -1016,8 +1036,9 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
     /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
     const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
     const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \
-    if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16) != cudaSuccess) return -1; \
-    SA_LAUNCH(kfn, fast_grid(kfn, smem16, num_sms, need), FAST_WARPS * 32, smem16, st, F);    \
+    const int grid16 = fast_grid(kfn, smem16, num_sms, need);                                 \
+    if(grid16 < 0) return -1;                                                                 \
+    SA_LAUNCH(kfn, grid16, FAST_WARPS * 32, smem16, st, F);                                   \
     return 0;                                                                                 \
   }
 #define SA_FAST_CASE(g, k)                                                                    \
