@@ -176,7 +176,16 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
   if(n == 0) return;
   int batch_ok = !opt.print_matrices && !wait_on_keystroke;
   size_t cap = HIT_CAP;
-  if(batch_ok) {
+  /* --maxhits 1: only the first fetch matters, and that is what align mode delivers (best cell
+   * under the hit order + traceback, one fill pass, every scoring shape): no candidate sort */
+  const int first_only = batch_ok && opt.max_hits_set && opt.max_hits == 1;
+  if(first_only) {
+    const double t0 = sa_now();
+    const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+    sa_t_align += sa_now() - t0;
+    if(rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0;
+    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+  } else if(batch_ok) {
     /* empty sequences are reported at print time; the engine sees them as pairs without hits */
     int min_all = 0, have = 0;
     for(size_t i = 0; i < n; i++) {
@@ -198,6 +207,16 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
     if(!batch_ok) { align_single(a[i], b[i], na, nb); continue; }
     if(rejects_pair(a[i], b[i], na, nb)) continue;
     const int min_score = pair_min_score(la[i], lb[i]);
+    if(first_only) {
+      print_header(a[i], b[i], na, nb, la[i], lb[i], NULL);
+      alignment_ensure_capacity(result, la[i] + lb[i]);
+      const int got = seqalign_batch_alignment(eng, i, result);
+      if(got < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+      if(got == 1 && result->score >= min_score) print_hit(a[i], b[i], la[i], lb[i], 0);
+      fputs("==\n", stdout);
+      alignment_index++;
+      continue;
+    }
     const size_t nh = seqalign_batch_hit_count(eng, i);
     const size_t want = opt.max_hits_set ? opt.max_hits : (size_t)-1;
     /* the device list is complete unless it is full and the caller wants more */

@@ -47,5 +47,27 @@ for tool, args in (("needleman_wunsch", ["--printscores"]), ("smith_waterman", [
                    same_stdout_as_reference=out_small == out_ref, first_pair_same=out_small.split(b"\n\n")[0] == out_ref.split(b"\n\n")[0])
     print(json.dumps(row), flush=True)
     rows.append(row)
+# BASELINE config 4 through the tool: 50k protein pairs 400x400, BLOSUM62, first hit only
+NP, NPREF, LP = 50000, 300, 400
+pa, _, pb, _ = synthetic_batch(4, NP, LP, LP, kind="protein")
+def writep(path, n):
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(">a%d\n%s\n>b%d\n%s\n" % (i, pa[i * LP:(i + 1) * LP].tobytes().decode(), i, pb[i * LP:(i + 1) * LP].tobytes().decode()))
+bigp, smallp = os.path.join(td, "bigp.fa"), os.path.join(td, "smallp.fa")
+writep(bigp, NP); writep(smallp, NPREF)
+args = ["--scoring", "BLOSUM62", "--maxhits", "1", "--minscore", "1"]
+ours, ref = os.path.join(ROOT, "bin", "smith_waterman"), os.path.join(ROOT, "tests", "integration", "_ref_own", "smith_waterman")
+run(ours, args, smallp)
+t_big, out_big = run(ours, args, bigp)
+row = dict(tool="smith_waterman", args=args, config="BASELINE config 4", pairs=NP, seconds=round(t_big, 3), pairs_per_s=round(NP / t_big),
+           gcups=round(NP * LP * LP / t_big / 1e9, 1), stdout_mb=round(len(out_big) / 1e6, 1), phases=last_timing)
+if os.path.exists(ref):
+    t_ref, out_ref = run(ref, args, smallp)
+    t_s, out_s = run(ours, args, smallp)
+    row.update(ref_pairs=NPREF, ref_seconds=round(t_ref, 3), ref_pairs_per_s=round(NPREF / t_ref, 1), ref_gcups=round(NPREF * LP * LP / t_ref / 1e9, 3),
+               speedup_whole_process=round((NP / t_big) / (NPREF / t_ref), 1), first_pair_same=out_s.split(b"==\n")[0] == out_ref.split(b"==\n")[0])
+print(json.dumps(row), flush=True)
+rows.append(row)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gpu_cli.json"), "w"), indent=1)
