@@ -16,8 +16,18 @@ A step = one pass of the hot path over one batch:
   e2e   : the same batch through the host-buffer C-ABI call
           (seqalign_batch_submit_packed from pinned host memory: H2D copies,
           kernels, D2H of the scores inside the timed region).
+          E2E_DEPTH batches are in flight (one engine and host thread each), so
+          the PCIe copy of one step overlaps the kernel of another.
 Between timed steps the input rotates over NB distinct batches whose total
 size exceeds L2 (126 MB), so no step re-reads a cached batch.
+
+roofline : HBM, as the contract asks (algorithmic bytes of the DP kernel /
+           its CUDA-event time / measured copy bandwidth) -- 0.9 %: score-only
+           moves 0.0135 B/cell.  roofline.issue is the roof that binds this
+           kernel (ALU-pipe issue, from the DPX rate microbenchmarked live);
+           roofline.materialise is the HBM roofline of the one mode of the path
+           that HBM does bind (all three matrices of every pair, 12 B/cell),
+           measured on half of the step's pairs.
 
 --impl reference times the reference's own CPU fill (oracle/_ref/ref_batch,
 the unmodified seq-align sources compiled by oracle/Makefile; aligner_align +
