@@ -29,6 +29,7 @@ static scoring_t scoring;
 static sw_aligner_t *sw;
 static alignment_t *result;
 static seqalign_batch_t *eng;
+static seqalign_batch_t *mats_eng;   /* --printmatrices: the batch's matrices live on a second engine */
 static size_t alignment_index = 0;
 static int wait_on_keystroke = 0;
 static sa_reader *prompt_input = NULL;
@@ -174,8 +175,21 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
                         char *const *name_a, char *const *name_b, size_t n)
 {
   if(n == 0) return;
-  int batch_ok = !opt.print_matrices && !wait_on_keystroke;
+  int batch_ok = !wait_on_keystroke;
   size_t cap = HIT_CAP;
+  /* --printmatrices: all three matrices of every pair from the batch materialise mode
+   * (device resident, copied out pair by pair while printing); the single-pair API remains
+   * the way out for scoring shapes that mode does not take */
+  int with_mats = 0;
+  if(batch_ok && opt.print_matrices) {
+    if(!mats_eng) {
+      mats_eng = seqalign_batch_create(0);
+      if(mats_eng) seqalign_batch_set_scoring(mats_eng, &scoring);
+    }
+    with_mats = mats_eng && n > 1 &&
+                seqalign_batch_submit(mats_eng, SEQALIGN_SW, SEQALIGN_MODE_MATS, a, la, b, lb, n) == SEQALIGN_OK;
+    if(!with_mats) batch_ok = 0;
+  }
   /* --maxhits 1: only the first fetch matters, and that is what align mode delivers (best cell
    * under the hit order + traceback, one fill pass, every scoring shape): no candidate sort */
   const int first_only = batch_ok && opt.max_hits_set && opt.max_hits == 1;
@@ -207,29 +221,52 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
     if(!batch_ok) { align_single(a[i], b[i], na, nb); continue; }
     if(rejects_pair(a[i], b[i], na, nb)) continue;
     const int min_score = pair_min_score(la[i], lb[i]);
+    aligner_t tmp;
+    aligner_t *mats = NULL;
+    if(with_mats) {
+      /* an aligner_t exactly as aligner_align() would leave it, for alignment_print_matrices */
+      memset(&tmp, 0, sizeof(tmp));
+      const size_t cells = (la[i] + 1) * (lb[i] + 1);
+      tmp.scoring = &scoring; tmp.seq_a = a[i]; tmp.seq_b = b[i];
+      tmp.score_width = la[i] + 1; tmp.score_height = lb[i] + 1; tmp.capacity = cells;
+      tmp.match_scores = malloc(cells * sizeof(score_t));
+      tmp.gap_a_scores = malloc(cells * sizeof(score_t));
+      tmp.gap_b_scores = malloc(cells * sizeof(score_t));
+      if(!tmp.match_scores || !tmp.gap_a_scores || !tmp.gap_b_scores ||
+         seqalign_batch_matrices(mats_eng, i, tmp.match_scores, tmp.gap_a_scores, tmp.gap_b_scores) != SEQALIGN_OK) {
+        fprintf(stderr, "Error: %s\n", seqalign_batch_error(mats_eng));
+        exit(EXIT_FAILURE);
+      }
+      mats = &tmp;
+    }
+    size_t nh = 0;
+    const size_t want = opt.max_hits_set ? opt.max_hits : (size_t)-1;
+    if(!first_only) {
+      nh = seqalign_batch_hit_count(eng, i);
+      /* the device list is complete unless it is full and the caller wants more */
+      if(nh == cap && want > cap) {
+        seqalign_batch_hit(eng, i, nh - 1, result);
+        if(result->score >= min_score) {
+          if(mats) { free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores); }
+          align_single(a[i], b[i], na, nb);
+          continue;
+        }
+      }
+    }
+    print_header(a[i], b[i], na, nb, la[i], lb[i], mats);
+    if(mats) { free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores); }
     if(first_only) {
-      print_header(a[i], b[i], na, nb, la[i], lb[i], NULL);
       alignment_ensure_capacity(result, la[i] + lb[i]);
       const int got = seqalign_batch_alignment(eng, i, result);
       if(got < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
       if(got == 1 && result->score >= min_score) print_hit(a[i], b[i], la[i], lb[i], 0);
-      fputs("==\n", stdout);
-      alignment_index++;
-      continue;
-    }
-    const size_t nh = seqalign_batch_hit_count(eng, i);
-    const size_t want = opt.max_hits_set ? opt.max_hits : (size_t)-1;
-    /* the device list is complete unless it is full and the caller wants more */
-    if(nh == cap && want > cap) {
-      seqalign_batch_hit(eng, i, nh - 1, result);
-      if(result->score >= min_score) { align_single(a[i], b[i], na, nb); continue; }
-    }
-    print_header(a[i], b[i], na, nb, la[i], lb[i], NULL);
-    size_t hit_index = 0;
-    for(size_t h = 0; h < nh && hit_index < want; h++) {
-      if(seqalign_batch_hit(eng, i, h, result) != 1) break;
-      if(result->score < min_score) break;
-      print_hit(a[i], b[i], la[i], lb[i], hit_index++);
+    } else {
+      size_t hit_index = 0;
+      for(size_t h = 0; h < nh && hit_index < want; h++) {
+        if(seqalign_batch_hit(eng, i, h, result) != 1) break;
+        if(result->score < min_score) break;
+        print_hit(a[i], b[i], la[i], lb[i], hit_index++);
+      }
     }
     fputs("==\n", stdout);
     alignment_index++;
@@ -281,6 +318,7 @@ int main(int argc, char **argv)
   smith_waterman_free(sw);
   alignment_free(result);
   seqalign_batch_destroy(eng);
+  if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);
   sa_timing_report();
   return EXIT_SUCCESS;

@@ -144,6 +144,11 @@ CASES = [
      {"@fa": T(fasta(SW8[:2]) + ">e1\n\n>e2\nACGT\n" + fasta(SW8[2:4], tag="z"))}, None, True),
     ("smith_waterman", ["--nogaps", "--minscore", "3", "--maxhits", "3", "--file", "@fa"], {"@fa": T(fasta(SW8[:3]))}, None, True),
     ("smith_waterman", ["--gapopen", "0", "--minscore", "6", "--file", "@fa"], {"@fa": T(fasta(SW8[:5]))}, None, True),
+    # --printmatrices over several pairs: the batch materialise mode behind alignment_print_matrices
+    ("smith_waterman", ["--printmatrices", "--minscore", "3", "--maxhits", "2", "--file", "@fa"],
+     {"@fa": T(fasta([(a[:14], b[:11]) for a, b in SW8[:4]]))}, None, True),
+    ("smith_waterman", ["--printmatrices", "--maxhits", "1", "--minscore", "1", "--scoring", "BLOSUM62", "--file", "@fa"],
+     {"@fa": T(fasta([(a[:9], b[:12]) for a, b in SWP4[:3]]))}, None, True),
     ("lcs", ["abcabcdabcdexabcd"], {}, None, False),
 ]
 
