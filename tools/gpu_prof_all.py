@@ -11,7 +11,10 @@ A, OA, B, OB = synthetic_batch(2, 100000, 150, 150)
 eng.set_scoring(specs["sw_cli"]())
 eng.force_general(3); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, A, OA, B, OB); print(eng.last_kernel, eng.last_kernel_ms)
 eng.force_general(0); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, A, OA, B, OB); print(eng.last_kernel, eng.last_kernel_ms)
+eng.force_general(5); eng.submit_packed(seqalign.SW, seqalign.MODE_SCORE, A, OA, B, OB); print(eng.last_kernel, eng.last_kernel_ms)
+eng.force_general(0)
 n = 20000
+eng.submit_packed(seqalign.SW, seqalign.MODE_MATS, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); print(eng.last_kernel, eng.last_kernel_ms)
 eng.submit_packed(seqalign.SW, seqalign.MODE_ALIGN, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); print(eng.last_kernel, eng.last_kernel_ms, eng.last_walk_ms)
 eng.set_hit_limits(8, 60)
 eng.submit_packed(seqalign.SW, seqalign.MODE_HITS, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1]); print(eng.last_kernel, eng.last_kernel_ms)
