@@ -1,8 +1,12 @@
 /*
  * sa_fast.cuh -- sm_100a kernels of the batch alignment engine (part 2):
- * the score-only fill for the common scoring shape (affine gaps with
- * gap_open <= 0, no gap/mismatch restrictions, no free end gaps).  This is
- * the kernel behind the headline metric (batched 150x150 DNA SW).
+ * the fill for the common scoring shape (affine gaps with gap_open <= 0, no
+ * gap/mismatch restrictions, no free end gaps) and pairs up to 512 columns:
+ * fast_score_kernel (int32: score, SW end cell, traceback flag bytes, int16
+ * match scores for the multi-hit stage) and fast16_kernel (two pairs per
+ * register in packed 16-bit lanes: score, optionally the SW end cell).
+ * fast16_kernel is the kernel behind the headline metric (batched 150x150
+ * DNA SW).
  *
  * Same recurrence as alignment_fill_matrices (reference
  * src/alignment.c:89-167) and the general kernel, restated for speed:

@@ -23,7 +23,10 @@
  *                      Stability inside a 32-key tile comes from
  *                      __match_any_sync ranks, across tiles from the warp
  *                      processing them in order.
- *   hits_walk_kernel   one thread per pair: the sequential part (mask).
+ *   hits_walk_kernel   one warp per pair: the sequential part (mask).  All
+ *                      lanes follow the same walk (no divergence, lane 0
+ *                      writes); together they skip marked candidates 32 at a
+ *                      time.
  */
 #ifndef SA_HITS_CUH
 #define SA_HITS_CUH
