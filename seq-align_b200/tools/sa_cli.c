@@ -435,8 +435,14 @@ static size_t rd_line(sa_reader *r, sa_str *s)
   }
 }
 
+/* A line that starts with white space: the reference means to skip it, and does when it reads
+ * stdin unbuffered (--stdin); through its buffered reader (--file, --files) the skip has no effect
+ * and only the leading white space goes -- the rest of the line is read as a sequence (observed on
+ * the reference's tools; seq_file.h:303,316 call a skipline that does not move the buffer).  Both
+ * behaviours are kept, each where the reference shows it. */
 static void rd_skipline(sa_reader *r)
 {
+  if(r->fd < 0) return;
   int c;
   while((c = rd_getc(r)) != -1 && c != '\n') {}
 }

@@ -94,6 +94,10 @@ CASES = [
      {"@f1": T("".join(">x%d\n%s\n" % (i, a) for i, (a, b) in enumerate(P5))), "@f2": T("".join(b + "\n" for a, b in P5))}, None, False),
     ("needleman_wunsch", ["--printscores", "--pretty", "--stdin"], {}, plain(P5), False),
     ("needleman_wunsch", ["--printscores", "--file", "-"], {}, fasta(P5), False),
+    # lines that start with white space: skipped on --stdin, read (minus the white space) through --file
+    ("needleman_wunsch", ["--printscores", "--file", "@ws"], {"@ws": T("AAAA\n  indented line\nCCCC\n\tACGT x\nGGGG\nTTTT\n")}, None, False),
+    ("needleman_wunsch", ["--printscores", "--stdin"], {}, "AAAA\n  indented line\nCCCC\n\tACGT x\nGGGG\nTTTT\n", False),
+    ("needleman_wunsch", ["--printscores", "--file", "@ws"], {"@ws": T("\n\n  ACGTAC\nACGTTC\n")}, None, False),
     ("needleman_wunsch", ["--printscores", "--file", "@a", "--file", "@b", "ACGTAC", "ACTTAC"],
      {"@a": T(fasta(P5[:2])), "@b": T(plain(P5[2:]))}, None, False),
     ("needleman_wunsch", ["--substitution_matrix", "@m", "--printscores", "--file", "@fa"],
@@ -105,6 +109,13 @@ CASES = [
     ("needleman_wunsch", ["--substitution_pairs", "@p", "--match", "2", "--mismatch", "-4", "--printscores", "--pretty", "ACGGTCA", "ACAGTTA"],
      {"@p": T(PAIRS_SEP)}, None, False),
     ("needleman_wunsch", ["--scoring", "BLOSUM62", "--printscores", "--file", "@fa"], {"@fa": T(fasta(PROT6))}, None, False),
+    # the reference's own NCBI matrix files (scoring/*.txt), embedded as fixtures
+    ("needleman_wunsch", ["--substitution_matrix", "@b62", "--printscores", "--pretty", "--file", "@fa"],
+     {"@b62": T(open("/root/reference/scoring/BLOSUM62.txt").read()), "@fa": T(fasta(PROT6[:3]))}, None, False),
+    ("smith_waterman", ["--substitution_matrix", "@nuc", "--gapopen", "-6", "--minscore", "8", "--maxhits", "2", "ACGTNRYACGTTAGC", "ACGTACGTCAGC"],
+     {"@nuc": T(open("/root/reference/scoring/NUC.4.4.txt").read())}, None, False),
+    ("needleman_wunsch", ["--substitution_matrix", "@p250", "--printscores", "HEAGAWGHEE", "PAWHEAE"],
+     {"@p250": T(open("/root/reference/scoring/PAM250.txt").read(), gz=True)}, None, False),
     ("needleman_wunsch", ["--scoring", "PAM70", "--freestartgap", "--freeendgap", "--printscores", "--pretty", "--file", "@fa"],
      {"@fa": T(fasta(PROT6))}, None, False),
     ("needleman_wunsch", ["--printscores", "--file", "@odd"], {"@odd": T(fasta(P5[:2]) + ">lonely\nACGT\n")}, None, False),
