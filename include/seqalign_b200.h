@@ -171,6 +171,23 @@ int seqalign_shared_free(int device, void *d_ptr);
 int seqalign_shared_open(int device, const seqalign_ipc_handle_t *handle, void **d_ptr);
 int seqalign_shared_close(int device, void *d_ptr);
 
+/* The same without waiting: when the engine has a plan to guess from (the
+ * previous run's: same scoring, algorithm and outputs) the kernels are only
+ * ENQUEUED on `stream` and the call returns; up to 4 runs may be outstanding,
+ * so a caller that streams batches keeps the GPU busy across the host's launch
+ * and synchronisation latency.  seqalign_batch_run_device_wait() completes the
+ * OLDEST outstanding run: its results are in its d_score when it returns (a run
+ * whose batch did not fit the guessed plan -- and every run enqueued after it
+ * -- is redone right there).  Without a plan to guess from (first run, new
+ * scoring) the call is the blocking one and wait() has nothing to do.  Any
+ * other entry point of the engine first waits for everything outstanding. */
+int seqalign_batch_run_device_async(seqalign_batch_t *eng, int algo,
+                                    const void *d_seq_a, const void *d_off_a,
+                                    const void *d_seq_b, const void *d_off_b,
+                                    size_t n, void *d_score, void *d_x_end,
+                                    void *d_y_end, void *stream);
+int seqalign_batch_run_device_wait(seqalign_batch_t *eng);
+
 /* seqalign_batch_run_device launches speculatively with the previous run's
  * plan (same scoring, algorithm and outputs) and verifies against this
  * batch's scan afterwards; these count how often the guess held / was redone. */

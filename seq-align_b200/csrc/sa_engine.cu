@@ -76,6 +76,17 @@ struct seqalign_batch {
     int64_t max_lb = 0;
   } spec;
   int spec_hits = 0, spec_misses = 0;
+  /* device-resident runs launched ahead of their verification (seqalign_batch_run_device_async) */
+  struct Pending {
+    int slot, algo;
+    const void *a, *oa, *b, *ob;
+    size_t n;
+    void *ds, *dx, *dy;
+    void *stream;
+  };
+  enum { MAX_PENDING = 4 };
+  Pending pend[MAX_PENDING];
+  int pend_head = 0, pend_count = 0;
   int force_mode = 0; /* 0 auto, 1 general kernel, 2 fast + per-column keys, 3 fast without end cell, 4 = 3 but int32 only, 5 = auto but int32 only */
 
   /* inputs on device */
@@ -933,6 +944,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
 int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
                   const char *h_b, const int64_t *h_off_b, size_t n)
 {
+  while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));   /* runs launched ahead finish first */
   eng->err.clear();
   eng->n = 0;
   eng->last_launches = 0;
@@ -1182,6 +1194,7 @@ seqalign_batch_t *seqalign_batch_create(int device)
 void seqalign_batch_destroy(seqalign_batch_t *eng)
 {
   if(!eng) return;
+  while(eng->pend_count > 0) { if(seqalign_batch_run_device_wait(eng) != 0) break; }
   cudaSetDevice(eng->device);
   DevBuf *d[] = {&eng->d_seq_a, &eng->d_seq_b, &eng->d_off_a, &eng->d_off_b, &eng->d_meta, &eng->d_counter,
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
@@ -1211,6 +1224,7 @@ const char *seqalign_batch_error(const seqalign_batch_t *eng) { return eng ? eng
 
 int seqalign_batch_set_scoring(seqalign_batch_t *eng, const scoring_t *scoring)
 {
+  if(eng) while(eng->pend_count > 0) { if(seqalign_batch_run_device_wait(eng) != 0) break; }
   if(!eng || !scoring) return SEQALIGN_ERR_ARG;
   if(!eng->have_scoring || memcmp(eng->scoring, scoring, sizeof(scoring_t)) != 0) {
     memcpy(eng->scoring, scoring, sizeof(scoring_t));
@@ -1303,12 +1317,126 @@ int seqalign_batch_alignment(seqalign_batch_t *eng, size_t i, alignment_t *out)
   return 1;
 }
 
+static bool can_speculate(const seqalign_batch *eng, int algo, bool want_ends)
+{
+  return eng->spec.valid && eng->spec.version == eng->scoring_version && eng->spec.algo == algo &&
+         eng->spec.want_ends == want_ends && eng->tables_valid && eng->tables_version == eng->scoring_version &&
+         eng->spec.plan.tab32 == eng->dev_tab32 && eng->spec.plan.tab8 == eng->dev_tab8 &&
+         eng->force_mode == 0 && !getenv("SEQALIGN_NO_SPECULATION");
+}
+
+/* does the batch whose scan is in `bm` fit the plan it was launched with? */
+static bool speculation_held(seqalign_batch *eng, int algo, bool want_ends, const BatchMeta &bm)
+{
+  const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
+  uint64_t pres[8];
+  bool subset = true;
+  for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
+  for(int i = 0; i < 8; i++) subset = subset && (pres[i] & ~eng->tables_pres[i]) == 0;
+  FastPlan now;
+  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
+  const FastPlan &old = eng->spec.plan;
+  /* (a larger shape than needed, or int32 where 16 bits would do, is still exact) */
+  return subset && bm.max_lb <= eng->spec.max_lb &&
+         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &now) &&
+         now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) &&
+         (old.track != TRACK_TREE || bm.max_lb <= 2047);
+}
+
+int seqalign_batch_run_device_wait(seqalign_batch_t *eng)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  if(eng->pend_count == 0) return 0;
+  CU_TRY(cudaSetDevice(eng->device));
+  const seqalign_batch::Pending p = eng->pend[eng->pend_head];
+  eng->pend_head = (eng->pend_head + 1) % seqalign_batch::MAX_PENDING;
+  eng->pend_count--;
+  CU_TRY(cudaEventSynchronize(eng->ev_scan[p.slot]));
+  BatchMeta bm;
+  scan_decode(eng, p.n, p.slot, &bm);
+  CU_TRY(cudaEventSynchronize(eng->ev_k1[p.slot]));
+  const bool want_ends = (p.dx != nullptr || p.dy != nullptr);
+  if(eng->spec.valid && speculation_held(eng, p.algo, want_ends, bm)) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, eng->ev_k0[p.slot], eng->ev_k1[p.slot]));
+    eng->last_ms = ms;
+    eng->spec_hits++;
+    return 0;
+  }
+  /* wrong guess: this run and everything launched after it with the same plan is redone, in order */
+  eng->spec_misses++;
+  eng->spec.valid = false;
+  seqalign_batch::Pending redo[seqalign_batch::MAX_PENDING + 1];
+  int nredo = 0;
+  redo[nredo++] = p;
+  while(eng->pend_count > 0) {
+    redo[nredo] = eng->pend[eng->pend_head];
+    eng->pend_head = (eng->pend_head + 1) % seqalign_batch::MAX_PENDING;
+    eng->pend_count--;
+    CU_TRY(cudaEventSynchronize(eng->ev_k1[redo[nredo].slot]));
+    CU_TRY(cudaEventSynchronize(eng->ev_scan[redo[nredo].slot]));
+    nredo++;
+  }
+  for(int i = 0; i < nredo; i++)
+    TRY(seqalign_batch_run_device(eng, redo[i].algo, redo[i].a, redo[i].oa, redo[i].b, redo[i].ob, redo[i].n,
+                                  redo[i].ds, redo[i].dx, redo[i].dy, redo[i].stream));
+  return 0;
+}
+
+static int drain_pending(seqalign_batch *eng)
+{
+  while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));
+  return 0;
+}
+
+int seqalign_batch_run_device_async(seqalign_batch_t *eng, int algo,
+                                    const void *d_seq_a, const void *d_off_a,
+                                    const void *d_seq_b, const void *d_off_b,
+                                    size_t n, void *d_score, void *d_x_end, void *d_y_end, void *stream)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
+  const bool want_ends = (d_x_end != nullptr || d_y_end != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
+  if(n == 0 || !can_speculate(eng, algo, want_ends)) {
+    /* nothing to guess from yet (first run, new scoring, ...): the blocking call, which also learns the plan */
+    TRY(drain_pending(eng));
+    return seqalign_batch_run_device(eng, algo, d_seq_a, d_off_a, d_seq_b, d_off_b, n, d_score, d_x_end, d_y_end, stream);
+  }
+  if(eng->pend_count == seqalign_batch::MAX_PENDING) TRY(seqalign_batch_run_device_wait(eng));
+  if(!can_speculate(eng, algo, want_ends)) {   /* the wait may have found a wrong guess */
+    TRY(drain_pending(eng));
+    return seqalign_batch_run_device(eng, algo, d_seq_a, d_off_a, d_seq_b, d_off_b, n, d_score, d_x_end, d_y_end, stream);
+  }
+  eng->err.clear();
+  CU_TRY(cudaSetDevice(eng->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : eng->stream;
+  const int slot = (eng->pend_head + eng->pend_count) % seqalign_batch::MAX_PENDING;
+  DevBatch db;
+  db.a = (const uint8_t *)d_seq_a; db.b = (const uint8_t *)d_seq_b;
+  db.off_a = (const int64_t *)d_off_a; db.off_b = (const int64_t *)d_off_b;
+  db.n = n;
+  const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
+  cudaStream_t cs = eng->copy_stream;
+  CU_TRY(cudaEventRecord(eng->ev_copy[slot], st));
+  TRY(launch_fast_score(eng, eng->spec.plan, sp, db, eng->spec.max_lb, (int32_t *)d_score,
+                        (int32_t *)d_x_end, (int32_t *)d_y_end, st, eng->ev_k0[slot], eng->ev_k1[slot]));
+  CU_TRY(cudaStreamWaitEvent(cs, eng->ev_copy[slot], 0));
+  TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, (int64_t)n * 256, cs, slot));
+  CU_TRY(cudaEventRecord(eng->ev_scan[slot], cs));
+  seqalign_batch::Pending &q = eng->pend[slot];
+  q.slot = slot; q.algo = algo; q.a = d_seq_a; q.oa = d_off_a; q.b = d_seq_b; q.ob = d_off_b; q.n = n;
+  q.ds = d_score; q.dx = want_ends ? d_x_end : nullptr; q.dy = want_ends ? d_y_end : nullptr; q.stream = stream;
+  eng->pend_count++;
+  return 0;
+}
+
 int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
                               const void *d_seq_a, const void *d_off_a,
                               const void *d_seq_b, const void *d_off_b,
                               size_t n, void *d_score, void *d_x_end, void *d_y_end, void *stream)
 {
   if(!eng) return SEQALIGN_ERR_ARG;
+  if(eng->pend_count > 0) TRY(drain_pending(eng));
   eng->err.clear();
   eng->last_launches = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
@@ -1330,10 +1458,7 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
    * the scan result is checked afterwards and the batch is redone the slow
    * way if the guess was wrong (the kernels turn pairs that do not fit the
    * plan into empty ones, so a wrong guess is harmless). */
-  if(eng->spec.valid && eng->spec.version == eng->scoring_version && eng->spec.algo == algo &&
-     eng->spec.want_ends == want_ends && eng->tables_valid && eng->tables_version == eng->scoring_version &&
-     eng->spec.plan.tab32 == eng->dev_tab32 && eng->spec.plan.tab8 == eng->dev_tab8 &&
-     eng->force_mode == 0 && !getenv("SEQALIGN_NO_SPECULATION")) {
+  if(can_speculate(eng, algo, want_ends)) {
     const ScoreParams sp = make_params(eng->scoring, algo == SEQALIGN_SW, eng->ft.ncodes);
     /* the scan runs on the side stream, next to the DP kernel */
     cudaStream_t cs = eng->copy_stream;
@@ -1345,18 +1470,7 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
     TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, approx_bytes, cs));
     TRY(scan_collect(eng, n, cs, &bm));
     CU_TRY(cudaStreamSynchronize(st));
-    uint64_t pres[8];
-    bool subset = true;
-    for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
-    for(int i = 0; i < 8; i++) subset = subset && (pres[i] & ~eng->tables_pres[i]) == 0;
-    FastPlan now;
-    const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
-    const FastPlan &old = eng->spec.plan;
-    if(subset && bm.max_lb <= eng->spec.max_lb &&
-       fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &now) &&
-       now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) &&
-       (old.track != TRACK_TREE || bm.max_lb <= 2047)) {
-      /* (a larger shape than needed, or int32 where 16 bits would do, is still exact) */
+    if(speculation_held(eng, algo, want_ends, bm)) {
       CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
       eng->last_ms = ms;
       eng->spec_hits++;
@@ -1406,6 +1520,7 @@ int seqalign_fill_matrices(seqalign_batch_t *eng, const char *seq_a, size_t len_
                            int32_t *match, int32_t *gap_a, int32_t *gap_b)
 {
   if(!eng) return SEQALIGN_ERR_ARG;
+  while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));
   eng->err.clear();
   eng->last_launches = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");

@@ -138,6 +138,8 @@ def load():
     L.seqalign_batch_size.argtypes = [vp]
     L.seqalign_batch_alignment.argtypes = [vp, sz, vp]
     L.seqalign_batch_run_device.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.seqalign_batch_run_device_async.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.seqalign_batch_run_device_wait.argtypes = [vp]
     L.seqalign_fill_matrices.argtypes = [vp, vp, sz, vp, sz, ctypes.c_int, vp, vp, vp]
     L.seqalign_batch_unknown_pair.argtypes = [vp, vp, vp]
     L.seqalign_batch_last_kernel_ms.restype = ctypes.c_double
@@ -370,6 +372,16 @@ class BatchAligner:
         self._check(self._L.seqalign_batch_run_device(self._h, algo, d_seq_a, d_off_a, d_seq_b, d_off_b,
                                                        n, d_score, d_xend or None, d_yend or None,
                                                        stream or None))
+
+    def run_device_async(self, algo, d_seq_a, d_off_a, d_seq_b, d_off_b, n, d_score, d_xend=0, d_yend=0, stream=0):
+        """run_device without waiting (up to 4 outstanding); pair every call with run_device_wait()"""
+        self._check(self._L.seqalign_batch_run_device_async(self._h, algo, d_seq_a, d_off_a, d_seq_b, d_off_b,
+                                                             n, d_score, d_xend or None, d_yend or None,
+                                                             stream or None))
+
+    def run_device_wait(self):
+        """completes the oldest outstanding run_device_async"""
+        self._check(self._L.seqalign_batch_run_device_wait(self._h))
 
     def fill_matrices(self, a, b, is_sw):
         a = a.encode() if isinstance(a, str) else bytes(a)

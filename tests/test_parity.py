@@ -681,6 +681,55 @@ def test_device_resident_api(big):
     eng.close()
 
 
+def test_device_resident_async(big):
+    """seqalign_batch_run_device_async / _wait: several runs enqueued before any is verified.
+    The stream mixes batches that fit the guessed plan with ones that do not (new alphabet, larger
+    shape, ragged): a wrong guess redoes that run and everything enqueued after it; every result
+    must equal the oracle's whatever the order of events"""
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    o = orc_from_scoring(sc)
+    eng = seqalign.BatchAligner(0, sc)
+    n, L = (2000, 150) if big else (6, 30)
+    withn = ragged_batch(8, n, L, L, alphabet=b"ACGTN")
+    batches = [synthetic_batch(20 + k, n, L, L) for k in range(5)]
+    batches += [seqalign.pack(withn[0]) + seqalign.pack(withn[1])]            # wrong guess in the middle of a queue
+    batches += [synthetic_batch(30 + k, n, L, L) for k in range(3)]
+    batches += [synthetic_batch(40, n, L + 30, L + 11)]                       # larger shape
+    batches += [synthetic_batch(41 + k, n, L - 5, L - 9) for k in range(4)]   # smaller: fits the larger plan
+    for want_ends in (False, True):
+        for depth in (1, 2, 4, 6):
+            pending, checked = [], 0
+            for k, (a, oa, b, ob) in enumerate(batches):
+                m = len(oa) - 1
+                out = [np.zeros(m, dtype=np.int32) for _ in range(3)]
+                keep, (pa, poa, pb, pob, ps, px, py) = _device_arrays(big, [a, oa, b, ob] + out)
+                eng.run_device_async(SW, pa, poa, pb, pob, m, ps, px if want_ends else 0, py if want_ends else 0)
+                pending.append((k, keep, m))
+                while len(pending) > depth or (k == len(batches) - 1 and pending):
+                    eng.run_device_wait()
+                    kk, kp, mm = pending.pop(0)
+                    es, ex, ey = orc_batch_sw(o, *batches[kk])
+                    assert np.array_equal(_device_result(big, kp[4], mm), es), (want_ends, depth, kk, eng.last_kernel)
+                    if want_ends:
+                        assert np.array_equal(_device_result(big, kp[5], mm), ex) and np.array_equal(_device_result(big, kp[6], mm), ey)
+                    checked += 1
+            assert checked == len(batches)
+            eng.run_device_wait()      # nothing outstanding: a no-op
+    hits, misses = eng.speculation_stats()
+    assert hits >= 40 and misses >= 8, (hits, misses)
+    # a blocking entry point with runs outstanding waits for them first
+    a, oa, b, ob = batches[0]
+    m = len(oa) - 1
+    out = [np.zeros(m, dtype=np.int32) for _ in range(3)]
+    keep, (pa, poa, pb, pob, ps, px, py) = _device_arrays(big, [a, oa, b, ob] + out)
+    eng.run_device(SW, pa, poa, pb, pob, m, ps, 0, 0)
+    eng.run_device_async(SW, pa, poa, pb, pob, m, ps, 0, 0)
+    eng.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    es, _, _ = orc_batch_sw(o, a, oa, b, ob)
+    assert np.array_equal(eng.scores(), es) and np.array_equal(_device_result(big, keep[4], m), es)
+    eng.close()
+
+
 def test_pipelined_aligner(big):
     """several batches in flight (one engine per worker thread), results in order"""
     sc = scoring_from_spec(SPECS["sw_cli"])
