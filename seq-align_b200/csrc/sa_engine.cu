@@ -884,20 +884,36 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   return 0;
 }
 
-/* batch materialise (Smith-Waterman): the three matrices of every pair stay in
- * device memory, seqalign_batch_matrices() copies one pair's planes out */
+/* batch materialise: the three matrices of every pair stay in device memory,
+ * seqalign_batch_matrices() copies one pair's planes out */
 int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
              const int64_t *h_off_a, const int64_t *h_off_b, cudaStream_t st)
 {
   const size_t n = db.n;
   const scoring_t *s = eng->scoring;
-  const ScoreParams sp = make_params(s, true, eng->ft.ncodes);
+  const bool nw = eng->algo == SEQALIGN_NW;
+  const ScoreParams sp = make_params(s, !nw, eng->ft.ncodes);
   const int NB = mats_blocks(bm.max_la);
+  if(nw) {
+    /* the NW rows leave the sentinel of alignment.c:41 out of their maxima: exact only while none of
+     * the reference's own `min + penalty` sums wraps and every real score stays far above MATS_NEG */
+    const long slack = labs((long)s->min_penalty);
+    long pen = labs((long)sp.open);
+    if(labs((long)sp.ext) > pen) pen = labs((long)sp.ext);
+    if(labs((long)s->gap_open) > pen) pen = labs((long)s->gap_open);
+    if(labs((long)eng->ft.min_sub) > pen) pen = labs((long)eng->ft.min_sub);
+    if(labs((long)eng->ft.max_sub) > pen) pen = labs((long)eng->ft.max_sub);
+    if(sp.no_start || slack + sp.open < 0 || slack + sp.ext < 0 || slack + eng->ft.min_sub < 0 ||
+       (long)(bm.max_la + bm.max_lb + 2) * pen > (1L << 27))
+      return fail(eng, SEQALIGN_ERR_ARG,
+                  "batch materialise (NW) needs affine gaps with gap_open <= 0, no free start / end gaps, no gap/mismatch "
+                  "restrictions and len_a <= 511; use aligner_align() for this input");
+  }
   if(eng->force_mode == 1 || sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches || s->gap_open > 0 ||
      s->gap_extend > 0 || eng->ft.any_unknown || NB == 0 || eng->ft.min_sub < -32768 || eng->ft.max_sub > 32767 ||
      (long)bm.max_la * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) > (1L << 28) || sp.open < -(1 << 20))
     return fail(eng, SEQALIGN_ERR_ARG,
-                "batch materialise needs Smith-Waterman with affine gaps (gap_open <= 0, no gap/mismatch "
+                "batch materialise needs affine gaps (gap_open <= 0, no free end gaps, no gap/mismatch "
                 "restrictions) and len_a <= 511; use aligner_align() for this input");
   eng->mat_off.assign(n + 1, 0);
   for(size_t i = 0; i < n; i++)
@@ -924,8 +940,8 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   CU_TRY(cudaEventRecord(eng->ev0, st));
   /* packed 16-bit prefix scans when every scan value (score + x*|ext|) fits */
   const long shortest = (long)(bm.max_la < bm.max_lb ? bm.max_la : bm.max_lb);
-  const bool pack = shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
-  if(mats_launch(NB, pack, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
+  const bool pack = !nw && shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
+  if(mats_launch(NB, pack, nw, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
     return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(eng->ev1, st));
@@ -937,7 +953,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   eng->last_ms = ms;
   memcpy(eng->score.data(), eng->h_res.p, n * 4);
-  eng->last_kernel = pack ? "mats_sw_packed" : "mats_sw";
+  eng->last_kernel = nw ? "mats_nw" : pack ? "mats_sw_packed" : "mats_sw";
   return 0;
 }
 
@@ -952,7 +968,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
   if((algo != SEQALIGN_NW && algo != SEQALIGN_SW) || (mode != SEQALIGN_MODE_SCORE && mode != SEQALIGN_MODE_ALIGN && mode != SEQALIGN_MODE_SCORE_ONLY &&
       mode != SEQALIGN_MODE_HITS && mode != SEQALIGN_MODE_MATS) ||
-     ((mode == SEQALIGN_MODE_HITS || mode == SEQALIGN_MODE_MATS) && algo != SEQALIGN_SW))
+     (mode == SEQALIGN_MODE_HITS && algo != SEQALIGN_SW))
     return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
   eng->algo = algo; eng->mode = mode;
   eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);

@@ -28,8 +28,18 @@
  * blocks; at 12 B/cell the arithmetic has an order of magnitude of slack.
  *
  * Smith-Waterman with the scoring shapes of sa_fast.cuh (affine gaps with
- * gap_open <= 0, no gap / mismatch restrictions), len_a <= 511.  Everything
- * else goes pair by pair through general_kernel<MODE_MATS>.
+ * gap_open <= 0, no gap / mismatch restrictions), len_a <= 511.
+ *
+ * Needleman-Wunsch (template flag NW) runs the same rows without the clamps:
+ * with no restriction flags every interior cell has a real predecessor, so the
+ * INT_MIN-based sentinel `min` of alignment.c:41 only ever shows up in the
+ * border cells (alignment.c:62-80), which are written with its exact value;
+ * inside the kernel the sentinel is MATS_NEG, far below any real score.  The
+ * host admits a batch only if none of the reference's `min + penalty` sums
+ * could wrap (run_mats), so leaving the sentinel out of the maxima is exact.
+ * gap_b is the same scan, seeded by the border column: T[0] = gap_a[y][0].
+ *
+ * Everything else goes pair by pair through general_kernel<MODE_MATS>.
  */
 #ifndef SA_MATS_CUH
 #define SA_MATS_CUH
@@ -79,10 +89,10 @@ struct MatsArgs {
  * the scan input u = max(M, GA) - x*ext.  diag: H[y-1][x-1] comes from the
  * lane before; lane 0 takes it from lane 31 of the block before, which that
  * lane sends instead of its own value (one rotating shuffle, no second one) */
-template <int NB>
+template <int NB, bool NW>
 __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const int16_t *prow, const int (&hp)[NB],
                                                 const int (&gap)[NB], int &prev_old, int open, int ext,
-                                                int &m, int &ga, int &u)
+                                                int bord, int minv, int &m, int &ga, int &u)
 {
   const int x = 32 * j + lane;
   const bool cell = x >= 1 && x <= la;
@@ -90,6 +100,13 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
   const int diag = __shfl_sync(FULL, send, (lane + 31) & 31);
   prev_old = hp[j];
   const int sub = prow[x];
+  if constexpr(NW) {
+    /* column 0 is the border: match = min, gap_a = bord (alignment.c:71-79) */
+    m = cell ? diag + sub : minv;
+    ga = cell ? fmax2(gap[j] + ext, hp[j] + open) : (x == 0 ? bord : minv);
+    u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext : MATS_NEG);
+    return;
+  }
   m = cell ? addmax(diag, sub, 0) : 0;
   ga = cell ? max3(gap[j] + ext, hp[j] + open, 0) : 0;
   u = x <= la ? fmax2(m, ga) - x * ext : 0;          /* x = 0: the border's 0; past len_a: never read by a real cell */
@@ -99,10 +116,11 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
  * CS: streaming stores (st.global.cs) -- an experiment, no measurable difference.
  * PACK: the prefix scans of two neighbouring blocks share their shuffles, the two
  * values packed in the halves of a register (needs every scan value in int16). */
-template <int NB, bool CS, bool PACK>
+template <int NB, bool CS, bool PACK, bool NW = false>
 __global__ void __launch_bounds__(MATS_WARPS * 32)
 mats_kernel(const MatsArgs A)
 {
+  static_assert(!(NW && PACK), "NW scores go negative: int32 scans only");
   constexpr int PW = NB * 32;                         /* profile row width (columns) */
   unsigned char *dsm = SA_DYN_SMEM();
   const ScoreParams &sp = A.sp;
@@ -116,6 +134,7 @@ mats_kernel(const MatsArgs A)
   for(int i = threadIdx.x; i < n * n; i += blockDim.x) s_sub[i] = A.sub[i];
   __syncthreads();
   const int open = sp.open, ext = sp.ext;
+  const int minv = sp.minv;                           /* NW: the value the border cells carry */
 
   for(;;) {
     unsigned long long t = 0;
@@ -141,11 +160,19 @@ mats_kernel(const MatsArgs A)
 
     /* row 0: borders, all three matrices 0 (alignment.c:47-57) */
     int hp[NB], gap[NB];
+    int endv = 0;                  /* NW: H of the newest row at column len_a (its owner lane only) */
 #pragma unroll
     for(int j = 0; j < NB; j++) {
       hp[j] = 0; gap[j] = 0;
       const int x = 32 * j + lane;
-      if(x <= la) { pm[x] = 0; pga[x] = 0; pgb[x] = 0; }
+      if constexpr(NW) {
+        /* NW row 0: match = gap_a = min, gap_b = gap_open + x*ext (alignment.c:62-69) */
+        if(x >= 1 && x <= la) {
+          hp[j] = sp.gap_open + x * ext; gap[j] = MATS_NEG;
+          pm[x] = minv; pga[x] = minv; pgb[x] = hp[j];
+        } else if(x == 0) { pm[0] = 0; pga[0] = 0; pgb[0] = 0; }
+      } else if(x <= la) { pm[x] = 0; pga[x] = 0; pgb[x] = 0; }
+      if(NW && x == la) endv = hp[j];
     }
     int best = 0;
     int codes = 0;
@@ -155,6 +182,7 @@ mats_kernel(const MatsArgs A)
       const int c = __shfl_sync(FULL, codes, (y - 1) & 31);
       const int16_t *prow = s_prof + c * PW;
       const int64_t row = (int64_t)y * W;
+      const int bord = NW ? sp.gap_open + y * ext : 0;   /* NW: gap_a[y][0] (alignment.c:77) */
       int prev_old = 0;            /* this lane's H[y-1] in the block before (lane 31's is the one that travels) */
       int run = MATS_NEG;          /* prefix maximum of u over the blocks before */
 
@@ -164,14 +192,17 @@ mats_kernel(const MatsArgs A)
         const bool cell = x >= 1 && x <= la;
         const int excl = lane == 0 ? run : fmax2(excl_in_block, run);
         run = fmax2(run, total);
-        const int gb = cell ? fmax2(excl + open + (x - 1) * ext, 0) : 0;
+        int gb;
+        if constexpr(NW) gb = cell ? excl + open + (x - 1) * ext : minv;
+        else gb = cell ? fmax2(excl + open + (x - 1) * ext, 0) : 0;
         const int h = max3(m, ga, gb);
         if(x <= la) {
           if(CS) { st_stream(pm + row + x, m); st_stream(pga + row + x, ga); st_stream(pgb + row + x, gb); }
           else { pm[row + x] = m; pga[row + x] = ga; pgb[row + x] = gb; }
         }
         best = fmax2(best, m);
-        hp[j] = cell ? h : 0;
+        hp[j] = (NW ? x <= la : cell) ? h : 0;           /* NW column 0: h = gap_a[y][0] */
+        if(NW && x == la) endv = h;
         gap[j] = ga;
       };
 
@@ -179,8 +210,8 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j += 2) {
           int m0, ga0, u0, m1 = 0, ga1 = 0, u1 = 0;
-          mats_block_head<NB>(j, lane, la, prow, hp, gap, prev_old, open, ext, m0, ga0, u0);
-          if(j + 1 < NB) mats_block_head<NB>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, m1, ga1, u1);
+          mats_block_head<NB, false>(j, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, m0, ga0, u0);
+          if(j + 1 < NB) mats_block_head<NB, false>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, m1, ga1, u1);
           unsigned w = ((unsigned)u0 & 0xffffu) | ((unsigned)u1 << 16);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
@@ -195,7 +226,7 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j++) {
           int m, ga, incl;
-          mats_block_head<NB>(j, lane, la, prow, hp, gap, prev_old, open, ext, m, ga, incl);
+          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, m, ga, incl);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(FULL, incl, o);
@@ -207,9 +238,15 @@ mats_kernel(const MatsArgs A)
       }
     }
     if(A.score) {
+      if constexpr(NW) {
+        /* NW score: max of the three matrices at [len_a][len_b] (needleman_wunsch.c:52-55) = H there */
+        const int v = __shfl_sync(FULL, endv, la & 31);
+        if(lane == 0) A.score[p] = v;
+      } else {
 #pragma unroll
-      for(int o = 16; o > 0; o >>= 1) best = fmax2(best, __shfl_xor_sync(FULL, best, o));
-      if(lane == 0) A.score[p] = best;
+        for(int o = 16; o > 0; o >>= 1) best = fmax2(best, __shfl_xor_sync(FULL, best, o));
+        if(lane == 0) A.score[p] = best;
+      }
     }
   }
 }
@@ -228,12 +265,13 @@ inline int mats_blocks(int64_t max_la)
 }
 
 template <int NB>
-int mats_launch_nb(const MatsArgs &M, bool pack, size_t smem, int num_sms, cudaStream_t st)
+int mats_launch_nb(const MatsArgs &M, bool pack, bool nw, size_t smem, int num_sms, cudaStream_t st)
 {
   const char *cs_env = getenv("SEQALIGN_MATS_STORES");   /* "stream" = st.global.cs (experiments: no measurable difference) */
   const bool cs = cs_env && cs_env[0] == 's';
   void (*kfn)(const MatsArgs) = pack ? (cs ? mats_kernel<NB, true, true> : mats_kernel<NB, false, true>)
                                      : (cs ? mats_kernel<NB, true, false> : mats_kernel<NB, false, false>);
+  if(nw) kfn = mats_kernel<NB, false, false, true>;
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -244,21 +282,21 @@ int mats_launch_nb(const MatsArgs &M, bool pack, size_t smem, int num_sms, cudaS
   return 0;
 }
 
-inline int mats_launch(int NB, bool pack, const MatsArgs &M, int ncodes, int num_sms, size_t smem_optin, cudaStream_t st)
+inline int mats_launch(int NB, bool pack, bool nw, const MatsArgs &M, int ncodes, int num_sms, size_t smem_optin, cudaStream_t st)
 {
   const size_t smem = mats_smem_bytes(NB, ncodes);
   if(smem > smem_optin) return -1;
   switch(NB) {
-    case 1: return mats_launch_nb<1>(M, pack, smem, num_sms, st);
-    case 2: return mats_launch_nb<2>(M, pack, smem, num_sms, st);
-    case 3: return mats_launch_nb<3>(M, pack, smem, num_sms, st);
-    case 4: return mats_launch_nb<4>(M, pack, smem, num_sms, st);
-    case 5: return mats_launch_nb<5>(M, pack, smem, num_sms, st);
-    case 6: return mats_launch_nb<6>(M, pack, smem, num_sms, st);
-    case 8: return mats_launch_nb<8>(M, pack, smem, num_sms, st);
-    case 10: return mats_launch_nb<10>(M, pack, smem, num_sms, st);
-    case 13: return mats_launch_nb<13>(M, pack, smem, num_sms, st);
-    case 16: return mats_launch_nb<16>(M, pack, smem, num_sms, st);
+    case 1: return mats_launch_nb<1>(M, pack, nw, smem, num_sms, st);
+    case 2: return mats_launch_nb<2>(M, pack, nw, smem, num_sms, st);
+    case 3: return mats_launch_nb<3>(M, pack, nw, smem, num_sms, st);
+    case 4: return mats_launch_nb<4>(M, pack, nw, smem, num_sms, st);
+    case 5: return mats_launch_nb<5>(M, pack, nw, smem, num_sms, st);
+    case 6: return mats_launch_nb<6>(M, pack, nw, smem, num_sms, st);
+    case 8: return mats_launch_nb<8>(M, pack, nw, smem, num_sms, st);
+    case 10: return mats_launch_nb<10>(M, pack, nw, smem, num_sms, st);
+    case 13: return mats_launch_nb<13>(M, pack, nw, smem, num_sms, st);
+    case 16: return mats_launch_nb<16>(M, pack, nw, smem, num_sms, st);
   }
   return -1;
 }

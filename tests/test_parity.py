@@ -369,7 +369,8 @@ def test_matrices(engine, big, name):
 def test_batch_matrices(engine, big, name, monkeypatch):
     """MODE_MATS: aligner_align() for a whole batch (row-per-step kernel with the gap_b prefix scan):
     all three matrices of every pair, element for element, against the oracle's fill; widths
-    around the 32-column blocks, empty sequences"""
+    around the 32-column blocks, empty sequences.  SW (packed and plain scans) and NW (borders
+    carrying the reference's INT_MIN-based sentinel, alignment.c:41,62-80)"""
     n, maxlen = (60, 200) if big else (10, 45)
     sa, sb = ragged_batch(5200 + _h(name) % 100, n, maxlen, maxlen, alphabet=_alphabet(name))
     widths = [31, 32, 33, 63, 64, 65] + ([127, 160, 300, 511] if big else [])
@@ -393,6 +394,15 @@ def test_batch_matrices(engine, big, name, monkeypatch):
             assert rc == 0
             assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, nopack, i, a, b)
             assert scores[i] == em.max()
+    engine.submit(NW, MODE_MATS, sa, sb)
+    assert engine.last_kernel == "mats_nw"
+    scores = engine.scores()
+    for i, (a, b) in enumerate(zip(sa, sb)):
+        m, ga, gb = engine.matrices(i, len(a), len(b))
+        rc, em, ega, egb = orc_fill(o, a, b, False)
+        assert rc == 0
+        assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, "nw", i, a, b)
+        assert scores[i] == max(em[-1, -1], ega[-1, -1], egb[-1, -1])
 
 
 def test_batch_matrices_rejects_other_shapes(engine):
@@ -404,6 +414,11 @@ def test_batch_matrices_rejects_other_shapes(engine):
     assert e.value.code == seqalign.ERR_ARG
     with pytest.raises(seqalign.SeqAlignError):
         engine.submit(NW, MODE_MATS, [b"ACGT"], [b"ACGT"])
+    for name in ("free_ends", "free_start", "free_end", "no_mismatch"):   # NW shapes the row kernel does not cover
+        engine.set_scoring(scoring_from_spec(SPECS[name]))
+        with pytest.raises(seqalign.SeqAlignError) as e:
+            engine.submit(NW, MODE_MATS, [b"ACGT"], [b"ACGT"])
+        assert e.value.code == seqalign.ERR_ARG
 
 
 @pytest.mark.parametrize("chunk", range(4))
