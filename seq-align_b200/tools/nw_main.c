@@ -6,8 +6,9 @@
  * the difference is the loop: pairs read from files are aligned as batches
  * (one launch sequence per batch, score + traceback on the device) instead of
  * one needleman_wunsch_align() call per pair.  --stdin keeps the per-pair
- * request/response rhythm the perl wrapper depends on.  --printmatrices needs
- * the three DP matrices on the host and goes through the single-pair API.
+ * request/response rhythm the perl wrapper depends on.  --printmatrices over
+ * several pairs takes the batch materialise mode (SEQALIGN_MODE_MATS, NW rows);
+ * single pairs and scoring shapes that mode refuses go through the single-pair API.
  */
 #define _GNU_SOURCE
 #include <ctype.h>
@@ -25,6 +26,7 @@ static scoring_t scoring;
 static nw_aligner_t *nw;
 static alignment_t *result;
 static seqalign_batch_t *eng;
+static seqalign_batch_t *mats_eng;   /* --printmatrices: the batch's matrices live on a second engine */
 
 /* "Br1:/Br2:" layout of --zam (reference nw_cmdline.c:36-75) */
 static void print_zam(void)
@@ -74,17 +76,50 @@ static void align_single(const char *a, const char *b, const char *name_a, const
   print_pair(name_a, name_b);
 }
 
+/* --printmatrices over a batch: pair i's three matrices from the batch materialise mode, dressed
+ * as the aligner_t aligner_align() would leave behind, for alignment_print_matrices */
+static void print_batch_matrices(size_t i, const char *a, size_t la, const char *b, size_t lb)
+{
+  aligner_t tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  const size_t cells = (la + 1) * (lb + 1);
+  tmp.scoring = &scoring; tmp.seq_a = a; tmp.seq_b = b;
+  tmp.score_width = la + 1; tmp.score_height = lb + 1; tmp.capacity = cells;
+  tmp.match_scores = malloc(cells * sizeof(score_t));
+  tmp.gap_a_scores = malloc(cells * sizeof(score_t));
+  tmp.gap_b_scores = malloc(cells * sizeof(score_t));
+  if(!tmp.match_scores || !tmp.gap_a_scores || !tmp.gap_b_scores ||
+     seqalign_batch_matrices(mats_eng, i, tmp.match_scores, tmp.gap_a_scores, tmp.gap_b_scores) != SEQALIGN_OK) {
+    fprintf(stderr, "Error: %s\n", seqalign_batch_error(mats_eng));
+    exit(EXIT_FAILURE);
+  }
+  alignment_print_matrices(&tmp);
+  free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores);
+}
+
 static void align_batch(const char *const *a, const size_t *la, const char *const *b, const size_t *lb,
                         char *const *name_a, char *const *name_b, size_t n)
 {
   if(n == 0) return;
   int rc = SEQALIGN_ERR_ARG;
   double t0 = sa_now();
-  if(!opt.print_matrices) rc = seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+  /* matrices that nobody prints (--zam) are not made; several pairs with --printmatrices take the
+   * batch materialise mode on a second engine when the scoring shape allows, else pair by pair */
+  const int want_mats = opt.print_matrices && !opt.zam;
+  int with_mats = 0;
+  if(want_mats && n > 1) {
+    if(!mats_eng) {
+      mats_eng = seqalign_batch_create(0);
+      if(mats_eng) seqalign_batch_set_scoring(mats_eng, &scoring);
+    }
+    with_mats = mats_eng && seqalign_batch_submit(mats_eng, SEQALIGN_NW, SEQALIGN_MODE_MATS, a, la, b, lb, n) == SEQALIGN_OK;
+  }
+  if(!opt.print_matrices || with_mats) rc = seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
   sa_t_align += sa_now() - t0;
   if(rc == SEQALIGN_OK) {
     t0 = sa_now();
     for(size_t i = 0; i < n; i++) {
+      if(with_mats) print_batch_matrices(i, a[i], la[i], b[i], lb[i]);
       alignment_ensure_capacity(result, la[i] + lb[i]);
       rc = seqalign_batch_alignment(eng, i, result);
       if(rc < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
@@ -144,6 +179,7 @@ int main(int argc, char **argv)
   needleman_wunsch_free(nw);
   alignment_free(result);
   seqalign_batch_destroy(eng);
+  if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);
   sa_timing_report();
   return EXIT_SUCCESS;

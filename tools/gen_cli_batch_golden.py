@@ -129,6 +129,12 @@ CASES = [
     ("needleman_wunsch", ["--nogapsin1", "--printscores", "--file", "@fa"], {"@fa": T(fasta([(a, b) for a, b in P7 if len(a) <= len(b)]))}, None, False),
     ("needleman_wunsch", ["--gapopen", "0", "--gapextend", "-3", "--printscores", "--file", "@fa"], {"@fa": T(fasta(P40, 1000))}, None, False),
     ("needleman_wunsch", ["--printmatrices", "--printscores", "--file", "@fa"], {"@fa": T(fasta([(a[:9], b[:7]) for a, b in P5[:2]]))}, None, False),
+    # --printmatrices over several pairs: the batch materialise mode (NW rows) behind alignment_print_matrices;
+    # free start gaps are a shape that mode refuses, so that invocation goes pair by pair
+    ("needleman_wunsch", ["--printmatrices", "--scoring", "BLOSUM62", "--printscores", "--file", "@fa"],
+     {"@fa": T(fasta([(a[:8], b[:11]) for a, b in PROT6[:3]]) + ">e1\n\n>e2\nHEAG\n")}, None, False),
+    ("needleman_wunsch", ["--printmatrices", "--freestartgap", "--printscores", "--file", "@fa"],
+     {"@fa": T(fasta([(a[:6], b[:8]) for a, b in P5[:2]]))}, None, False),
     # a character outside the loaded table: pairs before it are printed, then the reference exits
     ("needleman_wunsch", ["--substitution_matrix", "@m", "--printscores", "--file", "@fa"],
      {"@m": T(DNA_MATRIX), "@fa": T(fasta(P5[:2] + [("ACGTXACGT", "ACGTACGT")] + P5[2:]))}, None, False),
