@@ -39,8 +39,8 @@ typedef struct seqalign_batch seqalign_batch_t;
 #define SEQALIGN_MODE_ALIGN 1 /* + traceback: gapped strings, pos/len fields */
 #define SEQALIGN_MODE_HITS 3  /* SW: every local hit in the reference's order,
                                  up to the limits of seqalign_batch_set_hit_limits */
-#define SEQALIGN_MODE_MATS 4  /* SW: the three DP matrices of every pair, kept on
-                                 the device (seqalign_batch_matrices)            */
+#define SEQALIGN_MODE_MATS 4  /* SW or NW: the three DP matrices of every pair, kept
+                                 on the device (seqalign_batch_matrices)         */
 #define SEQALIGN_MODE_SCORE_ONLY 2 /* scores only (x_end/y_end = 0): lets the
                                       engine use its packed 16-bit SW kernel   */
 
@@ -125,15 +125,18 @@ size_t seqalign_batch_hit_count(const seqalign_batch_t *eng, size_t i);
 /* hit h of pair i into a reference alignment_t (all fields); 1 if written */
 int seqalign_batch_hit(seqalign_batch_t *eng, size_t i, size_t h, alignment_t *out);
 
-/* MODE_MATS (Smith-Waterman): aligner_align() for a whole batch -- the match /
+/* MODE_MATS (Smith-Waterman or Needleman-Wunsch): aligner_align() for a whole batch -- the match /
  * gap_a / gap_b matrices of every pair exactly as alignment_fill_matrices
  * leaves them (reference src/alignment.c:28-168), (len_a+1)*(len_b+1) ints
  * each, index = y*(len_a+1)+x, borders included.  They stay in device memory
  * (12 bytes per cell: SEQALIGN_ERR_NOMEM if the batch does not fit); this
  * copies pair i's three planes into host arrays.  seqalign_batch_scores()
- * gives the best match score per pair.  Available for the scoring shapes of
- * the specialised kernel with len_a <= 511 (SEQALIGN_ERR_ARG otherwise: use
- * seqalign_fill_matrices pair by pair). */
+ * gives the best match score per pair (SW) / the max of the three matrices
+ * at [len_a][len_b] (NW; the border cells carry the reference's INT_MIN-based
+ * sentinel of alignment.c:41 exactly).  Available for the scoring shapes of
+ * the specialised kernel with len_a <= 511: affine gaps with gap_open <= 0, no
+ * gap / mismatch restrictions, and for NW no free start / end gaps
+ * (SEQALIGN_ERR_ARG otherwise: use seqalign_fill_matrices pair by pair). */
 int seqalign_batch_matrices(seqalign_batch_t *eng, size_t i, int32_t *match,
                             int32_t *gap_a, int32_t *gap_b);
 
