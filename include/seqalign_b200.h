@@ -135,7 +135,7 @@ int seqalign_batch_hit(seqalign_batch_t *eng, size_t i, size_t h, alignment_t *o
  * at [len_a][len_b] (NW; the border cells carry the reference's INT_MIN-based
  * sentinel of alignment.c:41 exactly).  Available for the scoring shapes of
  * the specialised kernel with len_a <= 511: affine gaps with gap_open <= 0, no
- * gap / mismatch restrictions, and for NW no free start / end gaps
+ * gap / mismatch restrictions; free start / end gaps for NW only
  * (SEQALIGN_ERR_ARG otherwise: use seqalign_fill_matrices pair by pair). */
 int seqalign_batch_matrices(seqalign_batch_t *eng, size_t i, int32_t *match,
                             int32_t *gap_a, int32_t *gap_b);

@@ -903,13 +903,13 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     if(labs((long)s->gap_open) > pen) pen = labs((long)s->gap_open);
     if(labs((long)eng->ft.min_sub) > pen) pen = labs((long)eng->ft.min_sub);
     if(labs((long)eng->ft.max_sub) > pen) pen = labs((long)eng->ft.max_sub);
-    if(sp.no_start || slack + sp.open < 0 || slack + sp.ext < 0 || slack + eng->ft.min_sub < 0 ||
+    if(slack + sp.open < 0 || slack + sp.ext < 0 || slack + eng->ft.min_sub < 0 ||
        (long)(bm.max_la + bm.max_lb + 2) * pen > (1L << 27))
       return fail(eng, SEQALIGN_ERR_ARG,
-                  "batch materialise (NW) needs affine gaps with gap_open <= 0, no free start / end gaps, no gap/mismatch "
+                  "batch materialise (NW) needs affine gaps with gap_open <= 0, penalties within min_penalty, no gap/mismatch "
                   "restrictions and len_a <= 511; use aligner_align() for this input");
   }
-  if(eng->force_mode == 1 || sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches || s->gap_open > 0 ||
+  if(eng->force_mode == 1 || (sp.no_end && !nw) || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches || s->gap_open > 0 ||
      s->gap_extend > 0 || eng->ft.any_unknown || NB == 0 || eng->ft.min_sub < -32768 || eng->ft.max_sub > 32767 ||
      (long)bm.max_la * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) > (1L << 28) || sp.open < -(1 << 20))
     return fail(eng, SEQALIGN_ERR_ARG,

@@ -38,6 +38,9 @@
  * host admits a batch only if none of the reference's `min + penalty` sums
  * could wrap (run_mats), so leaving the sentinel out of the maxima is exact.
  * gap_b is the same scan, seeded by the border column: T[0] = gap_a[y][0].
+ * Free start gaps only change the border values (0); free end gaps make the
+ * last column's gap_a the plain best of the cell above and the last row's
+ * gap_b the same scan with open = ext = 0 (alignment.c:117-122,136-141).
  *
  * Everything else goes pair by pair through general_kernel<MODE_MATS>.
  */
@@ -92,7 +95,7 @@ struct MatsArgs {
 template <int NB, bool NW>
 __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const int16_t *prow, const int (&hp)[NB],
                                                 const int (&gap)[NB], int &prev_old, int open, int ext,
-                                                int bord, int minv, int &m, int &ga, int &u)
+                                                int bord, int minv, int ext_r, bool free_end, int &m, int &ga, int &u)
 {
   const int x = 32 * j + lane;
   const bool cell = x >= 1 && x <= la;
@@ -103,8 +106,9 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
   if constexpr(NW) {
     /* column 0 is the border: match = min, gap_a = bord (alignment.c:71-79) */
     m = cell ? diag + sub : minv;
-    ga = cell ? fmax2(gap[j] + ext, hp[j] + open) : (x == 0 ? bord : minv);
-    u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext : MATS_NEG);
+    /* free end gaps: in the last column gap_a takes the best of the cell above as it is (alignment.c:117-122) */
+    ga = cell ? ((free_end && x == la) ? hp[j] : fmax2(gap[j] + ext, hp[j] + open)) : (x == 0 ? bord : minv);
+    u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext_r : MATS_NEG);
     return;
   }
   m = cell ? addmax(diag, sub, 0) : 0;
@@ -168,7 +172,7 @@ mats_kernel(const MatsArgs A)
       if constexpr(NW) {
         /* NW row 0: match = gap_a = min, gap_b = gap_open + x*ext (alignment.c:62-69) */
         if(x >= 1 && x <= la) {
-          hp[j] = sp.gap_open + x * ext; gap[j] = MATS_NEG;
+          hp[j] = sp.no_start ? 0 : sp.gap_open + x * ext; gap[j] = MATS_NEG;
           pm[x] = minv; pga[x] = minv; pgb[x] = hp[j];
         } else if(x == 0) { pm[0] = 0; pga[0] = 0; pgb[0] = 0; }
       } else if(x <= la) { pm[x] = 0; pga[x] = 0; pgb[x] = 0; }
@@ -182,7 +186,10 @@ mats_kernel(const MatsArgs A)
       const int c = __shfl_sync(FULL, codes, (y - 1) & 31);
       const int16_t *prow = s_prof + c * PW;
       const int64_t row = (int64_t)y * W;
-      const int bord = NW ? sp.gap_open + y * ext : 0;   /* NW: gap_a[y][0] (alignment.c:77) */
+      const int bord = (NW && !sp.no_start) ? sp.gap_open + y * ext : 0;   /* NW: gap_a[y][0] (alignment.c:76-77) */
+      /* free end gaps: along the last row gap_b costs nothing (alignment.c:136-141), the same scan with 0 / 0 */
+      const bool free_row = NW && sp.no_end && y == lb;
+      const int open_r = free_row ? 0 : open, ext_r = free_row ? 0 : ext;
       int prev_old = 0;            /* this lane's H[y-1] in the block before (lane 31's is the one that travels) */
       int run = MATS_NEG;          /* prefix maximum of u over the blocks before */
 
@@ -193,7 +200,7 @@ mats_kernel(const MatsArgs A)
         const int excl = lane == 0 ? run : fmax2(excl_in_block, run);
         run = fmax2(run, total);
         int gb;
-        if constexpr(NW) gb = cell ? excl + open + (x - 1) * ext : minv;
+        if constexpr(NW) gb = cell ? excl + open_r + (x - 1) * ext_r : minv;
         else gb = cell ? fmax2(excl + open + (x - 1) * ext, 0) : 0;
         const int h = max3(m, ga, gb);
         if(x <= la) {
@@ -210,8 +217,8 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j += 2) {
           int m0, ga0, u0, m1 = 0, ga1 = 0, u1 = 0;
-          mats_block_head<NB, false>(j, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, m0, ga0, u0);
-          if(j + 1 < NB) mats_block_head<NB, false>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, m1, ga1, u1);
+          mats_block_head<NB, false>(j, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, ext, false, m0, ga0, u0);
+          if(j + 1 < NB) mats_block_head<NB, false>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, ext, false, m1, ga1, u1);
           unsigned w = ((unsigned)u0 & 0xffffu) | ((unsigned)u1 << 16);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
@@ -226,7 +233,7 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j++) {
           int m, ga, incl;
-          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, m, ga, incl);
+          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m, ga, incl);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(FULL, incl, o);

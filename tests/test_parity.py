@@ -365,12 +365,13 @@ def test_matrices(engine, big, name):
             assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (a, b, is_sw)
 
 
-@pytest.mark.parametrize("name", ["sw_cli", "nw_default", "linear_gap", "wild_n", "mutations", "blosum62", "pam30"])
+@pytest.mark.parametrize("name", ["sw_cli", "nw_default", "linear_gap", "wild_n", "mutations", "blosum62", "pam30",
+                                  "free_ends", "free_start", "free_end"])
 def test_batch_matrices(engine, big, name, monkeypatch):
     """MODE_MATS: aligner_align() for a whole batch (row-per-step kernel with the gap_b prefix scan):
     all three matrices of every pair, element for element, against the oracle's fill; widths
     around the 32-column blocks, empty sequences.  SW (packed and plain scans) and NW (borders
-    carrying the reference's INT_MIN-based sentinel, alignment.c:41,62-80)"""
+    carrying the reference's INT_MIN-based sentinel, alignment.c:41,62-80; free start / end gaps)"""
     n, maxlen = (60, 200) if big else (10, 45)
     sa, sb = ragged_batch(5200 + _h(name) % 100, n, maxlen, maxlen, alphabet=_alphabet(name))
     widths = [31, 32, 33, 63, 64, 65] + ([127, 160, 300, 511] if big else [])
@@ -382,7 +383,8 @@ def test_batch_matrices(engine, big, name, monkeypatch):
     o = orc_from_scoring(sc)
     engine.set_scoring(sc)
     engine.force_general(0)
-    for nopack in ("", "1"):     # packed 16-bit prefix scans / plain int32 scans
+    # free end gaps: NW only (for SW the flag also changes the fill and stays with the general kernel)
+    for nopack in () if SPECS[name].get("init", [0] * 6)[5] else ("", "1"):     # packed 16-bit prefix scans / plain int32 scans
         if nopack:
             monkeypatch.setenv("SEQALIGN_MATS_NOPACK", "1")
         engine.submit(SW, MODE_MATS, sa, sb)
@@ -414,7 +416,7 @@ def test_batch_matrices_rejects_other_shapes(engine):
     assert e.value.code == seqalign.ERR_ARG
     with pytest.raises(seqalign.SeqAlignError):
         engine.submit(NW, MODE_MATS, [b"ACGT"], [b"ACGT"])
-    for name in ("free_ends", "free_start", "free_end", "no_mismatch"):   # NW shapes the row kernel does not cover
+    for name in ("no_gaps_a", "no_gaps_b", "no_mismatch"):   # NW shapes the row kernel does not cover
         engine.set_scoring(scoring_from_spec(SPECS[name]))
         with pytest.raises(seqalign.SeqAlignError) as e:
             engine.submit(NW, MODE_MATS, [b"ACGT"], [b"ACGT"])

@@ -130,7 +130,7 @@ CASES = [
     ("needleman_wunsch", ["--gapopen", "0", "--gapextend", "-3", "--printscores", "--file", "@fa"], {"@fa": T(fasta(P40, 1000))}, None, False),
     ("needleman_wunsch", ["--printmatrices", "--printscores", "--file", "@fa"], {"@fa": T(fasta([(a[:9], b[:7]) for a, b in P5[:2]]))}, None, False),
     # --printmatrices over several pairs: the batch materialise mode (NW rows) behind alignment_print_matrices;
-    # free start gaps are a shape that mode refuses, so that invocation goes pair by pair
+    # free start gaps: borders of 0, same mode
     ("needleman_wunsch", ["--printmatrices", "--scoring", "BLOSUM62", "--printscores", "--file", "@fa"],
      {"@fa": T(fasta([(a[:8], b[:11]) for a, b in PROT6[:3]]) + ">e1\n\n>e2\nHEAG\n")}, None, False),
     ("needleman_wunsch", ["--printmatrices", "--freestartgap", "--printscores", "--file", "@fa"],
