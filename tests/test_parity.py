@@ -460,6 +460,37 @@ def test_reference_golden_vectors(engine, chunk):
                     assert gb.ravel().tolist() == c[key][2]
 
 
+def test_reference_golden_matrices_batch_mode(engine):
+    """the matrices recorded from the unmodified reference (tests/golden/reference_vectors.json) against
+    MODE_MATS for whole batches, NW and SW; scoring shapes the row kernel refuses (SEQALIGN_ERR_ARG) are
+    counted, the rest must match element for element"""
+    by_spec = {}
+    for c in GOLD["cases"]:
+        if "nw_mats" in c or "sw_mats" in c:
+            by_spec.setdefault(c["spec"], []).append(c)
+    checked = {NW: 0, SW: 0}
+    for spec, cs in by_spec.items():
+        engine.set_scoring(scoring_from_spec(GOLD["specs"][spec]))
+        engine.force_general(False)
+        for algo, key in ((NW, "nw_mats"), (SW, "sw_mats")):
+            sub = [c for c in cs if key in c]
+            if not sub:
+                continue
+            try:
+                engine.submit(algo, MODE_MATS, [c["a"].encode() for c in sub], [c["b"].encode() for c in sub])
+            except seqalign.SeqAlignError as e:
+                assert e.code in (seqalign.ERR_ARG, seqalign.ERR_UNKNOWN_PAIR), (spec, e)
+                continue
+            for i, c in enumerate(sub):
+                m, ga, gb = engine.matrices(i, len(c["a"]), len(c["b"]))
+                assert m.ravel().tolist() == c[key][0], (spec, key, c["a"], c["b"])
+                assert ga.ravel().tolist() == c[key][1], (spec, key, c["a"], c["b"])
+                assert gb.ravel().tolist() == c[key][2], (spec, key, c["a"], c["b"])
+                checked[algo] += 1
+    print("pairs checked against the reference\x27s matrices:", checked)
+    assert checked[NW] >= 70 and checked[SW] >= 60, checked
+
+
 def test_classic_api_single_pair(engine):
     """needleman_wunsch_align / smith_waterman_align + fetch (all hits) via the
     reference's own function names; hit order and visited-mask semantics"""
