@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Differential fuzzing of every mode of the engine against the oracle: random scoring models
 (init values, built-in systems with poked gap penalties, flags), random ragged batches up to the
-kernels' shape limits, all modes.  python tools/gpu_fuzz.py [seconds] [seed]"""
+kernels' shape limits, all modes.  python tools/gpu_fuzz.py [seconds] [seed]
+FUZZ_MODES=4 (comma list of mode numbers), FUZZ_NW=1 (NW only) and FUZZ_SMALL=1 (short batches) narrow a run, e.g.
+for a dry run in the lane emulator (SEQALIGN_LIB=tests/emu/libseqalign_emu.so)."""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -14,6 +16,9 @@ eng = seqalign.BatchAligner(0)
 t_end = time.time() + budget
 stats = dict(rounds=0, pairs=0, kernels={}, failures=[])
 PROT = b"ARNDCQEGHILKMFPSTWYV"
+MODES = [int(x) for x in os.environ.get("FUZZ_MODES", "0,1,3,4,2").split(",")]
+ONLY_NW = bool(os.environ.get("FUZZ_NW"))
+SMALL = bool(os.environ.get("FUZZ_SMALL"))
 
 def model():
     r = rng.random()
@@ -49,8 +54,8 @@ def unsafe(sc, algo):
 
 while time.time() < t_end:
     sc, desc, alpha = model()
-    maxlen = int([20, 60, 150, 300, 512, 700][int(rng.integers(0, 6))])
-    n = int(rng.integers(3, 400 if maxlen <= 150 else 60))
+    maxlen = int(([10, 20, 40, 70, 100, 140] if SMALL else [20, 60, 150, 300, 512, 700])[int(rng.integers(0, 6))])
+    n = int(rng.integers(3, 12)) if SMALL else int(rng.integers(3, 400 if maxlen <= 150 else 60))
     uniform = rng.random() < 0.15 and maxlen <= 512     # one shape for the whole batch: the packed 16-bit kernel's case
     if uniform:
         la_u, lb_u = int(rng.integers(1, maxlen + 1)), int(rng.integers(1, maxlen + 1))
@@ -61,11 +66,12 @@ while time.time() < t_end:
     a, oa = seqalign.pack(sa); b, ob = seqalign.pack(sb)
     o = orc_from_scoring(sc)
     eng.set_scoring(sc)
-    algo = SW if rng.random() < 0.6 else NW
-    if unsafe(sc, algo): algo = SW
-    mode = [MODE_SCORE, MODE_ALIGN, MODE_HITS, MODE_MATS, MODE_SCORE_ONLY][int(rng.integers(0, 5))]
-    if uniform and rng.random() < 0.9: algo, mode = SW, (MODE_SCORE_ONLY if rng.random() < 0.5 else MODE_SCORE)
-    if algo == NW and mode in (MODE_HITS, MODE_MATS): mode = MODE_ALIGN
+    algo = NW if ONLY_NW or rng.random() >= 0.6 else SW
+    mode = MODES[int(rng.integers(0, len(MODES)))]
+    # NW batch matrices: the engine itself has to refuse what it cannot reproduce (stale min_penalty, restriction flags)
+    if unsafe(sc, algo) and not (algo == NW and mode == MODE_MATS): algo = SW
+    if uniform and rng.random() < 0.9 and not os.environ.get("FUZZ_MODES"): algo, mode = SW, (MODE_SCORE_ONLY if rng.random() < 0.5 else MODE_SCORE)
+    if algo == NW and mode == MODE_HITS: mode = MODE_ALIGN
     eng.force_general(1 if rng.random() < 0.1 and mode in (MODE_SCORE, MODE_ALIGN) else 0)
     eng.set_hit_limits(8, 1)
     case = dict(model=desc, algo="SW" if algo == SW else "NW", mode=mode, n=n, maxlen=maxlen)
@@ -105,7 +111,7 @@ while time.time() < t_end:
                 assert [(h.score, h.result_a, h.result_b, h.pos_a, h.pos_b) for h in got] == [(h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"]) for h in hits], "hits %d" % i
             elif mode == MODE_MATS:
                 m, ga, gb = eng.matrices(i, len(sa[i]), len(sb[i]))
-                rc, em, ega, egb = orc_fill(o, sa[i], sb[i], True)
+                rc, em, ega, egb = orc_fill(o, sa[i], sb[i], algo == SW)
                 assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), "matrices %d" % i
         stats["rounds"] += 1; stats["pairs"] += n
     except AssertionError as e:
