@@ -894,6 +894,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   const bool nw = eng->algo == SEQALIGN_NW;
   const ScoreParams sp = make_params(s, !nw, eng->ft.ncodes);
   const int NB = mats_blocks(bm.max_la);
+  long nw_pen = 0;               /* NW: largest |score| one step can add */
   if(nw) {
     /* the NW rows leave the sentinel of alignment.c:41 out of their maxima: exact only while none of
      * the reference's own `min + penalty` sums wraps and every real score stays far above MATS_NEG */
@@ -903,6 +904,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     if(labs((long)s->gap_open) > pen) pen = labs((long)s->gap_open);
     if(labs((long)eng->ft.min_sub) > pen) pen = labs((long)eng->ft.min_sub);
     if(labs((long)eng->ft.max_sub) > pen) pen = labs((long)eng->ft.max_sub);
+    nw_pen = pen;
     if(slack + sp.open < 0 || slack + sp.ext < 0 || slack + eng->ft.min_sub < 0 ||
        (long)(bm.max_la + bm.max_lb + 2) * pen > (1L << 27))
       return fail(eng, SEQALIGN_ERR_ARG,
@@ -940,7 +942,9 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   CU_TRY(cudaEventRecord(eng->ev0, st));
   /* packed 16-bit prefix scans when every scan value (score + x*|ext|) fits */
   const long shortest = (long)(bm.max_la < bm.max_lb ? bm.max_la : bm.max_lb);
-  const bool pack = !nw && shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
+  bool pack = !nw && shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
+  /* NW with packed scans: opt-in until it has been timed; every score and scan value must fit int16 */
+  if(nw && getenv("SEQALIGN_MATS_NW_PACK") && (long)(bm.max_la + bm.max_lb + 2) * nw_pen - 512L * sp.ext < 32000) pack = true;
   if(mats_launch(NB, pack, nw, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
     return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
   CU_TRY(cudaGetLastError());
@@ -953,7 +957,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   eng->last_ms = ms;
   memcpy(eng->score.data(), eng->h_res.p, n * 4);
-  eng->last_kernel = nw ? "mats_nw" : pack ? "mats_sw_packed" : "mats_sw";
+  eng->last_kernel = nw ? (pack ? "mats_nw_packed" : "mats_nw") : pack ? "mats_sw_packed" : "mats_sw";
   return 0;
 }
 

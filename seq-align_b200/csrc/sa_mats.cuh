@@ -119,12 +119,13 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
 /* NB blocks of 32 columns cover x = 0 .. len_a.
  * CS: streaming stores (st.global.cs) -- an experiment, no measurable difference.
  * PACK: the prefix scans of two neighbouring blocks share their shuffles, the two
- * values packed in the halves of a register (needs every scan value in int16). */
+ * values packed in the halves of a register (needs every scan value in int16).
+ * NW + PACK exists but is opt-in (SEQALIGN_MATS_NW_PACK=1): checked in the lane
+ * emulator only, not yet timed on the GPU. */
 template <int NB, bool CS, bool PACK, bool NW = false>
 __global__ void __launch_bounds__(MATS_WARPS * 32)
 mats_kernel(const MatsArgs A)
 {
-  static_assert(!(NW && PACK), "NW scores go negative: int32 scans only");
   constexpr int PW = NB * 32;                         /* profile row width (columns) */
   unsigned char *dsm = SA_DYN_SMEM();
   const ScoreParams &sp = A.sp;
@@ -217,8 +218,9 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j += 2) {
           int m0, ga0, u0, m1 = 0, ga1 = 0, u1 = 0;
-          mats_block_head<NB, false>(j, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, ext, false, m0, ga0, u0);
-          if(j + 1 < NB) mats_block_head<NB, false>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, 0, 0, ext, false, m1, ga1, u1);
+          /* NW: columns past len_a carry MATS_NEG, whose low half is 0 -- like SW's 0 there it only reaches columns that are not cells */
+          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m0, ga0, u0);
+          if(j + 1 < NB) mats_block_head<NB, NW>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m1, ga1, u1);
           unsigned w = ((unsigned)u0 & 0xffffu) | ((unsigned)u1 << 16);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
@@ -278,7 +280,7 @@ int mats_launch_nb(const MatsArgs &M, bool pack, bool nw, size_t smem, int num_s
   const bool cs = cs_env && cs_env[0] == 's';
   void (*kfn)(const MatsArgs) = pack ? (cs ? mats_kernel<NB, true, true> : mats_kernel<NB, false, true>)
                                      : (cs ? mats_kernel<NB, true, false> : mats_kernel<NB, false, false>);
-  if(nw) kfn = mats_kernel<NB, false, false, true>;
+  if(nw) kfn = pack ? mats_kernel<NB, false, true, true> : mats_kernel<NB, false, false, true>;
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;

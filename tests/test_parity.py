@@ -396,15 +396,18 @@ def test_batch_matrices(engine, big, name, monkeypatch):
             assert rc == 0
             assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, nopack, i, a, b)
             assert scores[i] == em.max()
-    engine.submit(NW, MODE_MATS, sa, sb)
-    assert engine.last_kernel == "mats_nw"
-    scores = engine.scores()
-    for i, (a, b) in enumerate(zip(sa, sb)):
-        m, ga, gb = engine.matrices(i, len(a), len(b))
-        rc, em, ega, egb = orc_fill(o, a, b, False)
-        assert rc == 0
-        assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, "nw", i, a, b)
-        assert scores[i] == max(em[-1, -1], ega[-1, -1], egb[-1, -1])
+    for nw_pack in ("", "1"):    # int32 scans (the default) / the opt-in packed 16-bit scans
+        if nw_pack:
+            monkeypatch.setenv("SEQALIGN_MATS_NW_PACK", "1")
+        engine.submit(NW, MODE_MATS, sa, sb)
+        assert engine.last_kernel == ("mats_nw_packed" if nw_pack else "mats_nw")
+        scores = engine.scores()
+        for i, (a, b) in enumerate(zip(sa, sb)):
+            m, ga, gb = engine.matrices(i, len(a), len(b))
+            rc, em, ega, egb = orc_fill(o, a, b, False)
+            assert rc == 0
+            assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, "nw", nw_pack, i, a, b)
+            assert scores[i] == max(em[-1, -1], ega[-1, -1], egb[-1, -1])
 
 
 def test_batch_matrices_rejects_other_shapes(engine):
