@@ -38,9 +38,10 @@
  * host admits a batch only if none of the reference's `min + penalty` sums
  * could wrap (run_mats), so leaving the sentinel out of the maxima is exact.
  * gap_b is the same scan, seeded by the border column: T[0] = gap_a[y][0].
- * Free start gaps only change the border values (0); free end gaps make the
- * last column's gap_a the plain best of the cell above and the last row's
- * gap_b the same scan with open = ext = 0 (alignment.c:117-122,136-141).
+ * Free start gaps only change the border values (0); free end gaps (template
+ * flag FREE) make the last column's gap_a the plain best of the cell above and
+ * the last row's gap_b the same scan with open = ext = 0
+ * (alignment.c:117-122,136-141).
  *
  * Everything else goes pair by pair through general_kernel<MODE_MATS>.
  */
@@ -92,10 +93,10 @@ struct MatsArgs {
  * the scan input u = max(M, GA) - x*ext.  diag: H[y-1][x-1] comes from the
  * lane before; lane 0 takes it from lane 31 of the block before, which that
  * lane sends instead of its own value (one rotating shuffle, no second one) */
-template <int NB, bool NW>
+template <int NB, bool NW, bool FREE = false>
 __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const int16_t *prow, const int (&hp)[NB],
                                                 const int (&gap)[NB], int &prev_old, int open, int ext,
-                                                int bord, int minv, int ext_r, bool free_end, int &m, int &ga, int &u)
+                                                int bord, int minv, int ext_r, int &m, int &ga, int &u)
 {
   const int x = 32 * j + lane;
   const bool cell = x >= 1 && x <= la;
@@ -107,8 +108,13 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
     /* column 0 is the border: match = min, gap_a = bord (alignment.c:71-79) */
     m = cell ? diag + sub : minv;
     /* free end gaps: in the last column gap_a takes the best of the cell above as it is (alignment.c:117-122) */
-    ga = cell ? ((free_end && x == la) ? hp[j] : fmax2(gap[j] + ext, hp[j] + open)) : (x == 0 ? bord : minv);
-    u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext_r : MATS_NEG);
+    if constexpr(FREE) {
+      ga = cell ? (x == la ? hp[j] : fmax2(gap[j] + ext, hp[j] + open)) : (x == 0 ? bord : minv);
+      u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext_r : MATS_NEG);
+    } else {
+      ga = cell ? fmax2(gap[j] + ext, hp[j] + open) : (x == 0 ? bord : minv);
+      u = x == 0 ? bord : (cell ? fmax2(m, ga) - x * ext : MATS_NEG);
+    }
     return;
   }
   m = cell ? addmax(diag, sub, 0) : 0;
@@ -122,7 +128,7 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
  * values packed in the halves of a register (needs every scan value in int16).
  * NW + PACK exists but is opt-in (SEQALIGN_MATS_NW_PACK=1): checked in the lane
  * emulator only, not yet timed on the GPU. */
-template <int NB, bool CS, bool PACK, bool NW = false>
+template <int NB, bool CS, bool PACK, bool NW = false, bool FREE = false>
 __global__ void __launch_bounds__(MATS_WARPS * 32)
 mats_kernel(const MatsArgs A)
 {
@@ -189,7 +195,7 @@ mats_kernel(const MatsArgs A)
       const int64_t row = (int64_t)y * W;
       const int bord = (NW && !sp.no_start) ? sp.gap_open + y * ext : 0;   /* NW: gap_a[y][0] (alignment.c:76-77) */
       /* free end gaps: along the last row gap_b costs nothing (alignment.c:136-141), the same scan with 0 / 0 */
-      const bool free_row = NW && sp.no_end && y == lb;
+      const bool free_row = FREE && y == lb;
       const int open_r = free_row ? 0 : open, ext_r = free_row ? 0 : ext;
       int prev_old = 0;            /* this lane's H[y-1] in the block before (lane 31's is the one that travels) */
       int run = MATS_NEG;          /* prefix maximum of u over the blocks before */
@@ -201,7 +207,8 @@ mats_kernel(const MatsArgs A)
         const int excl = lane == 0 ? run : fmax2(excl_in_block, run);
         run = fmax2(run, total);
         int gb;
-        if constexpr(NW) gb = cell ? excl + open_r + (x - 1) * ext_r : minv;
+        if constexpr(NW && FREE) gb = cell ? excl + open_r + (x - 1) * ext_r : minv;
+        else if constexpr(NW) gb = cell ? excl + open + (x - 1) * ext : minv;
         else gb = cell ? fmax2(excl + open + (x - 1) * ext, 0) : 0;
         const int h = max3(m, ga, gb);
         if(x <= la) {
@@ -219,8 +226,8 @@ mats_kernel(const MatsArgs A)
         for(int j = 0; j < NB; j += 2) {
           int m0, ga0, u0, m1 = 0, ga1 = 0, u1 = 0;
           /* NW: columns past len_a carry MATS_NEG, whose low half is 0 -- like SW's 0 there it only reaches columns that are not cells */
-          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m0, ga0, u0);
-          if(j + 1 < NB) mats_block_head<NB, NW>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m1, ga1, u1);
+          mats_block_head<NB, NW, FREE>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, m0, ga0, u0);
+          if(j + 1 < NB) mats_block_head<NB, NW, FREE>(j + 1, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, m1, ga1, u1);
           unsigned w = ((unsigned)u0 & 0xffffu) | ((unsigned)u1 << 16);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
@@ -235,7 +242,7 @@ mats_kernel(const MatsArgs A)
 #pragma unroll
         for(int j = 0; j < NB; j++) {
           int m, ga, incl;
-          mats_block_head<NB, NW>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, NW && sp.no_end, m, ga, incl);
+          mats_block_head<NB, NW, FREE>(j, lane, la, prow, hp, gap, prev_old, open, ext, bord, minv, ext_r, m, ga, incl);
 #pragma unroll
           for(int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(FULL, incl, o);
@@ -280,7 +287,9 @@ int mats_launch_nb(const MatsArgs &M, bool pack, bool nw, size_t smem, int num_s
   const bool cs = cs_env && cs_env[0] == 's';
   void (*kfn)(const MatsArgs) = pack ? (cs ? mats_kernel<NB, true, true> : mats_kernel<NB, false, true>)
                                      : (cs ? mats_kernel<NB, true, false> : mats_kernel<NB, false, false>);
-  if(nw) kfn = pack ? mats_kernel<NB, false, true, true> : mats_kernel<NB, false, false, true>;
+  /* NW: free end gaps (FREE) are their own instantiations, so that the common rows keep open / ext loop-invariant */
+  if(nw) kfn = M.sp.no_end ? (pack ? mats_kernel<NB, false, true, true, true> : mats_kernel<NB, false, false, true, true>)
+                           : (pack ? mats_kernel<NB, false, true, true, false> : mats_kernel<NB, false, false, true, false>);
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
