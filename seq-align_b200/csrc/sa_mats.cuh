@@ -126,8 +126,12 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
  * CS: streaming stores (st.global.cs) -- an experiment, no measurable difference.
  * PACK: the prefix scans of two neighbouring blocks share their shuffles, the two
  * values packed in the halves of a register (needs every scan value in int16).
- * NW + PACK exists but is opt-in (SEQALIGN_MATS_NW_PACK=1): checked in the lane
- * emulator only, not yet timed on the GPU. */
+ * NW + PACK exists but is opt-in (SEQALIGN_MATS_NW_PACK=1): bit-exact in the lane
+ * emulator and on the B200 spot check of tools/gpu_mats_nw.py, timed only in the
+ * FREE code shape.
+ * FREE (NW): free end gaps; a template flag because open / ext as per-row values
+ * cost the common rows their loop-invariant x*ext terms (measured: 60 / 43 % of the
+ * HBM roofline instead of 67 / 60 %). */
 template <int NB, bool CS, bool PACK, bool NW = false, bool FREE = false>
 __global__ void __launch_bounds__(MATS_WARPS * 32)
 mats_kernel(const MatsArgs A)
