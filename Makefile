@@ -16,7 +16,7 @@ CFLAGS = -std=gnu99 -O2 -Wall -Wextra -fPIC -Iinclude -Iseq-align_b200/host
 
 PKG = seq-align_b200
 LIBDIR = $(PKG)/lib
-HOST_SRCS = $(PKG)/host/sa_scoring.c $(PKG)/host/sa_alignment.c $(PKG)/host/sa_nw.c $(PKG)/host/sa_sw.c
+HOST_SRCS = $(PKG)/host/sa_scoring.c $(PKG)/host/sa_alignment.c $(PKG)/host/sa_nw.c $(PKG)/host/sa_sw.c $(PKG)/host/sa_multi.c
 HOST_OBJS = $(HOST_SRCS:.c=.o)
 CU_DEPS = $(wildcard $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h include/*.h)
 
@@ -30,7 +30,7 @@ $(PKG)/csrc/sa_engine.o: $(PKG)/csrc/sa_engine.cu $(CU_DEPS)
 
 $(LIBDIR)/libseqalign_b200.so: $(PKG)/csrc/sa_engine.o $(HOST_OBJS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $^
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread
 
 $(LIBDIR)/libalign.a: $(PKG)/csrc/sa_engine.o $(HOST_OBJS)
 	mkdir -p $(LIBDIR)
@@ -42,7 +42,7 @@ $(EMU)/libseqalign_emu.so: $(PKG)/csrc/sa_engine.cu $(CU_DEPS) $(EMU)/cuda_emu.c
 	$(CXX) -O1 -g -std=c++17 -fPIC -DSA_EMU -Iinclude -I$(PKG)/csrc -I$(EMU) -c -x c++ $(PKG)/csrc/sa_engine.cu -o $(EMU)/sa_engine_emu.o
 	$(CXX) -O1 -g -std=c++17 -fPIC -I$(EMU) -c $(EMU)/cuda_emu.cpp -o $(EMU)/cuda_emu.o
 	for f in $(HOST_SRCS); do $(CC) $(CFLAGS) -c $$f -o $(EMU)/`basename $$f .c`_emu.o || exit 1; done
-	$(CXX) -shared -o $@ $(EMU)/sa_engine_emu.o $(EMU)/cuda_emu.o $(EMU)/sa_scoring_emu.o $(EMU)/sa_alignment_emu.o $(EMU)/sa_nw_emu.o $(EMU)/sa_sw_emu.o
+	$(CXX) -shared -o $@ $(EMU)/sa_engine_emu.o $(EMU)/cuda_emu.o $(EMU)/sa_scoring_emu.o $(EMU)/sa_alignment_emu.o $(EMU)/sa_nw_emu.o $(EMU)/sa_sw_emu.o $(EMU)/sa_multi_emu.o -lpthread
 
 # batching command-line tools (same flags / stdout as the reference's bin/*)
 TOOLS = bin/needleman_wunsch bin/smith_waterman bin/lcs

@@ -90,6 +90,23 @@ int seqalign_batch_submit_packed(seqalign_batch_t *eng, int algo, int mode,
                                  const char *seq_b, const int64_t *off_b,
                                  size_t n);
 
+/* Fixed-length read sets (every BASELINE config): pair i is seq_a[i*len_a ..
+ * (i+1)*len_a) vs seq_b[i*len_b .. (i+1)*len_b).  No offset arrays exist on the
+ * host, none cross PCIe (the device makes its own) and nothing per pair is
+ * touched by the CPU in the score modes.  Same results and accessors as
+ * seqalign_batch_submit_packed. */
+int seqalign_batch_submit_uniform(seqalign_batch_t *eng, int algo, int mode,
+                                  const char *seq_a, size_t len_a,
+                                  const char *seq_b, size_t len_b, size_t n);
+
+/* Where the score modes (SEQALIGN_MODE_SCORE / _SCORE_ONLY) of the following
+ * submits leave their results: host arrays of n int32 each, written by the
+ * device->host copies themselves (pinned memory: no CPU copy at all).  x_end /
+ * y_end may be NULL.  score == NULL switches back to the engine's own arrays
+ * (seqalign_batch_scores / _ends, which fail with SEQALIGN_ERR_ARG after a
+ * submit into a sink).  The arrays must stay valid until the submit returns. */
+int seqalign_batch_set_result_sink(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end);
+
 /* Results of the last submit (host arrays of n entries each).
  * score: NW = max of the three matrices at [len_a,len_b]
  *        (reference needleman_wunsch.c:53-66); SW = best match score, 0 if
@@ -143,9 +160,12 @@ int seqalign_batch_matrices(seqalign_batch_t *eng, size_t i, int32_t *match,
 /* Device-resident variant (score mode): all pointers are device memory on
  * the engine's device, stream is a cudaStream_t (NULL = engine's own).
  * d_x_end/d_y_end may be NULL (score only: lets the engine use its packed
- * 16-bit kernel).  Returns when the results are in d_score.  Sequence
- * buffers must be readable up to the next 16-byte boundary past their end
- * (the kernels stage them with 16-byte bulk copies). */
+ * 16-bit kernel).  Returns when the results are in d_score.  d_seq_a and
+ * d_seq_b must be 16-byte aligned (SEQALIGN_ERR_ARG otherwise) and readable up
+ * to the next 16-byte boundary past their end: the kernels stage sequences
+ * with 16-byte bulk copies aligned on the offset.  A shard of a larger batch
+ * is passed as the batch's base pointers plus a window of its offset arrays
+ * (offsets are absolute), never as a pointer into the middle of the buffer. */
 int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
                               const void *d_seq_a, const void *d_off_a,
                               const void *d_seq_b, const void *d_off_b,
@@ -208,6 +228,61 @@ int seqalign_fill_matrices(seqalign_batch_t *eng,
 /* characters of the first unknown pair after SEQALIGN_ERR_UNKNOWN_PAIR
  * (case-folded, as the reference prints them) */
 void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b);
+
+/* Page-locked host memory for callers without CUDA headers: input buffers and
+ * result sinks allocated here travel over PCIe by DMA without a staging copy
+ * (cudaMallocHost / cudaFreeHost).  NULL on failure. */
+void *seqalign_host_alloc(size_t bytes);
+void seqalign_host_free(void *p);
+
+/* ---- one batch over several GPUs of one node, one process (host/sa_multi.c) ----
+ * The reference's loop over pairs (src/alignment_cmdline.c:611-622) sharded by
+ * pair index: one engine per device, contiguous pair ranges balanced by cell
+ * count, one host thread per device for the duration of a submit, every device
+ * fed over its own PCIe link.  Pairs are independent, so nothing is exchanged
+ * between devices; results are addressed by the pair's index in the submitted
+ * batch, exactly like the single-engine calls.  The offset arrays must stay
+ * valid until the results have been read (seqalign_multi_ends in score-only
+ * mode reads the lengths from them).  devices == NULL: devices 0..n-1;
+ * n_devices <= 0: every usable device.  A device may be listed twice (two
+ * engines on it). */
+typedef struct seqalign_multi seqalign_multi_t;
+seqalign_multi_t *seqalign_multi_create(const int *devices, int n_devices);
+void seqalign_multi_destroy(seqalign_multi_t *m);
+int seqalign_multi_devices(const seqalign_multi_t *m);
+const char *seqalign_multi_error(const seqalign_multi_t *m);
+int seqalign_multi_set_scoring(seqalign_multi_t *m, const scoring_t *scoring);
+int seqalign_multi_set_hit_limits(seqalign_multi_t *m, size_t max_hits, int32_t min_score);
+int seqalign_multi_submit_packed(seqalign_multi_t *m, int algo, int mode,
+                                 const char *seq_a, const int64_t *off_a,
+                                 const char *seq_b, const int64_t *off_b, size_t n);
+int seqalign_multi_submit_uniform(seqalign_multi_t *m, int algo, int mode,
+                                  const char *seq_a, size_t len_a,
+                                  const char *seq_b, size_t len_b, size_t n);
+size_t seqalign_multi_size(const seqalign_multi_t *m);
+int seqalign_multi_scores(seqalign_multi_t *m, int32_t *score);
+int seqalign_multi_ends(seqalign_multi_t *m, int32_t *score, int32_t *x_end, int32_t *y_end);
+int seqalign_multi_alignment(seqalign_multi_t *m, size_t i, alignment_t *out);
+size_t seqalign_multi_hit_count(seqalign_multi_t *m, size_t i);
+int seqalign_multi_hit(seqalign_multi_t *m, size_t i, size_t h, alignment_t *out);
+int seqalign_multi_matrices(seqalign_multi_t *m, size_t i, int32_t *match, int32_t *gap_a, int32_t *gap_b);
+/* which device aligned pair i of the last submit, and its index there */
+int seqalign_multi_where(seqalign_multi_t *m, size_t i, int *device, size_t *local_index);
+void seqalign_multi_unknown_pair(const seqalign_multi_t *m, char *a, char *b);
+double seqalign_multi_last_kernel_ms(const seqalign_multi_t *m);   /* slowest device */
+
+/* Synthetic pairs of SURVEY.md 8d, generated on the device: pairs
+ * [first_pair, first_pair + npairs) of the counter-based stream `seed`,
+ * fixed lengths, kind 0 = DNA (ACGT; seq_b = seq_a with 5 % substitutions, 1 %
+ * insertions, 1 % deletions), kind 1 = protein (20 letters; 15 % / 2 % / 2 %).
+ * A pair depends only on (seed, pair index), so any rank can make any shard
+ * of a job (csrc/sa_synth.cuh; seqalign/synth.py is the same function in
+ * numpy).  d_seq_a / d_seq_b: device buffers of npairs*len_a / npairs*len_b
+ * bytes.  The reference reads its pairs from files
+ * (src/alignment_cmdline.c:578-640) and has no generator.  stream NULL: the
+ * call returns when the buffers are filled. */
+int seqalign_synth_batch(int device, int kind, uint64_t seed, int64_t first_pair, int64_t npairs,
+                         int len_a, int len_b, void *d_seq_a, void *d_seq_b, void *stream);
 
 /* Instrumentation for bench.py: device time (ms, CUDA events on the
  * engine's stream) and launch count of the DP kernels of the last

@@ -23,12 +23,13 @@
 #include "sa_hits.cuh"
 #include "sa_mats.cuh"
 #include "sa_long.cuh"
+#include "sa_synth.cuh"
 
 using namespace sa;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;
 
 struct DevBuf {
   void *p = nullptr;
@@ -51,7 +52,7 @@ struct seqalign_batch {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t scan_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  enum { MAX_CHUNKS = 8 };
+  enum { MAX_CHUNKS = 32 };
   cudaEvent_t ev_copy[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {}, ev_scan[MAX_CHUNKS] = {};
   std::string err;
   char unk_a = 0, unk_b = 0;
@@ -103,6 +104,10 @@ struct seqalign_batch {
   DevBuf d_mats, d_mat_off;
   std::vector<int64_t> mat_off;            /* batch materialise: first int of pair i's match plane, n+1 entries */
   PinBuf h_in_a, h_in_b, h_off_a, h_off_b, h_meta, h_res, h_walk, h_str_a, h_str_b;
+
+  /* optional host destination of score-mode results (seqalign_batch_set_result_sink) */
+  int32_t *sink_score = nullptr, *sink_x = nullptr, *sink_y = nullptr;
+  bool last_to_sink = false;
 
   /* last batch */
   size_t n = 0;
@@ -194,6 +199,8 @@ ScoreParams make_params(const scoring_t *s, int is_sw, int ncodes)
   sp.ncodes = ncodes;
   return sp;
 }
+
+constexpr size_t COUNTER_BYTES = 8 * (seqalign_batch::MAX_CHUNKS + 1);
 
 struct BatchMeta {
   uint64_t pres_a[4], pres_b[4];
@@ -364,7 +371,7 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
     TRY(ensure_dev(eng, eng->d_bnd, slots * (size_t)A.bnd_rows * sizeof(int4)));
     A.bnd = (int4 *)eng->d_bnd.p;
   }
-  TRY(ensure_dev(eng, eng->d_counter, 8));
+  TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
   CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
   A.counter = (unsigned long long *)eng->d_counter.p;
   if(coop) {
@@ -383,12 +390,15 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
 /* launch the specialised score kernel of `plan` (tables must be on the device) */
 int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScoreParams &sp, const DevBatch &db,
                       int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
-                      cudaEvent_t ev0, cudaEvent_t ev1)
+                      cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0)
 {
   const size_t nn = (size_t)sp.ncodes * (sp.ncodes + 1);
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
   int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
-  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+  /* one work-queue counter per slot: launches of different slots may run on different streams */
+  TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
+  unsigned long long *d_cnt = (unsigned long long *)eng->d_counter.p + slot;
+  CU_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
   FastArgs F;
   memset(&F, 0, sizeof(F));
   F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
@@ -396,7 +406,7 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
   F.tab8 = d_t8;
   F.tab32 = d_t32;
   F.lut = (const uint8_t *)eng->d_lut.p;
-  F.counter = (unsigned long long *)eng->d_counter.p;
+  F.counter = d_cnt;
   F.score = d_score; F.xend = d_xend; F.yend = d_yend;
   F.max_lb = (int)max_lb;
   CU_TRY(cudaEventRecord(ev0, st));
@@ -476,7 +486,7 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     if(eng->force_mode == 2 && plan.track == TRACK_TREE) { plan.track = TRACK_COLUMN; plan.name = "fast_sw_score_endcol"; }
     const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
     TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
-    TRY(ensure_dev(eng, eng->d_counter, 8));
+    TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
     int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
     int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
     if(plan.tab32 != eng->dev_tab32 || plan.tab8 != eng->dev_tab8) {
@@ -613,7 +623,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     CU_TRY(cudaStreamSynchronize(st));
 
     if(fast_dir) {
-      TRY(ensure_dev(eng, eng->d_counter, 8));
+      TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
       CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
       FastArgs F;
       memset(&F, 0, sizeof(F));
@@ -755,7 +765,7 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     eng->dev_tab8 = plan.tab8;
   }
   TRY(ensure_dev(eng, eng->d_score, n * 4));
-  TRY(ensure_dev(eng, eng->d_counter, 8));
+  TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
 
   eng->nhits.assign(n, 0);
   eng->hit_rec.assign(n * (size_t)maxh * 8, 0);
@@ -928,7 +938,7 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   TRY(ensure_dev(eng, eng->d_mats, total * 4 + 64));
   TRY(ensure_dev(eng, eng->d_mat_off, n * 8));
   TRY(ensure_dev(eng, eng->d_score, n * 4));
-  TRY(ensure_dev(eng, eng->d_counter, 8));
+  TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
   CU_TRY(cudaMemcpyAsync(eng->d_mat_off.p, eng->mat_off.data(), n * 8, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
   MatsArgs M;
@@ -961,8 +971,9 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   return 0;
 }
 
+/* h_off_a == NULL: every pair is ula x ulb (seqalign_batch_submit_uniform), nothing per pair is read on the host */
 int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
-                  const char *h_b, const int64_t *h_off_b, size_t n)
+                  const char *h_b, const int64_t *h_off_b, size_t n, int64_t ula = -1, int64_t ulb = -1)
 {
   while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));   /* runs launched ahead finish first */
   eng->err.clear();
@@ -974,19 +985,38 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       mode != SEQALIGN_MODE_HITS && mode != SEQALIGN_MODE_MATS) ||
      (mode == SEQALIGN_MODE_HITS && algo != SEQALIGN_SW))
     return fail(eng, SEQALIGN_ERR_ARG, "bad algo/mode");
+  const bool score_mode = mode == SEQALIGN_MODE_SCORE || mode == SEQALIGN_MODE_SCORE_ONLY;
+  std::vector<int64_t> made_a, made_b;
+  const bool given_uniform = h_off_a == nullptr;
+  if(given_uniform && !score_mode) {
+    /* the other modes walk the offsets on the host anyway */
+    made_a.resize(n + 1); made_b.resize(n + 1);
+    for(size_t i = 0; i <= n; i++) { made_a[i] = (int64_t)i * ula; made_b[i] = (int64_t)i * ulb; }
+    h_off_a = made_a.data(); h_off_b = made_b.data();
+  }
   eng->algo = algo; eng->mode = mode;
-  eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0);
+  const bool to_sink = score_mode && eng->sink_score != nullptr;
+  eng->last_to_sink = to_sink;
+  if(!to_sink) { eng->score.assign(n, 0); eng->xend.assign(n, 0); eng->yend.assign(n, 0); }
   if(n == 0) return 0;
   cudaStream_t st = eng->stream;
-  const int64_t total_a = h_off_a[n], total_b = h_off_b[n];
   bool uniform_batch = true;   /* every pair la0 x lb0: the device can make the offsets itself */
-  const int64_t la0 = h_off_a[1] - h_off_a[0], lb0 = h_off_b[1] - h_off_b[0];
-  for(size_t i = 0; i < n; i++) {
-    const int64_t la = h_off_a[i + 1] - h_off_a[i], lb = h_off_b[i + 1] - h_off_b[i];
-    if(la < 0 || lb < 0 || la > (1 << 30) || lb > (1 << 30))
-      return fail(eng, SEQALIGN_ERR_ARG, "bad offsets / sequence too long");
-    uniform_batch = uniform_batch && la == la0 && lb == lb0;
+  int64_t la0 = ula, lb0 = ulb;
+  if(h_off_a) {
+    la0 = h_off_a[1] - h_off_a[0]; lb0 = h_off_b[1] - h_off_b[0];
+    for(size_t i = 0; i < n; i++) {
+      const int64_t la = h_off_a[i + 1] - h_off_a[i], lb = h_off_b[i + 1] - h_off_b[i];
+      if(la < 0 || lb < 0 || la > (1 << 30) || lb > (1 << 30))
+        return fail(eng, SEQALIGN_ERR_ARG, "bad offsets / sequence too long");
+      uniform_batch = uniform_batch && la == la0 && lb == lb0;
+    }
+  } else if(la0 < 0 || lb0 < 0 || la0 > (1 << 30) || lb0 > (1 << 30)) {
+    return fail(eng, SEQALIGN_ERR_ARG, "bad sequence length");
   }
+  /* offset of pair i in the host buffers */
+  auto hoa = [&](size_t i) -> int64_t { return h_off_a ? h_off_a[i] : (int64_t)i * la0; };
+  auto hob = [&](size_t i) -> int64_t { return h_off_b ? h_off_b[i] : (int64_t)i * lb0; };
+  const int64_t total_a = hoa(n), total_b = hob(n);
   TRY(ensure_dev(eng, eng->d_seq_a, (size_t)total_a + 32));
   TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
   TRY(ensure_dev(eng, eng->d_off_a, (n + 1) * 8));
@@ -1003,8 +1033,11 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     TRY(ensure_dev(eng, eng->d_score, n * 4));
     TRY(ensure_dev(eng, eng->d_xend, n * 4));
     TRY(ensure_dev(eng, eng->d_yend, n * 4));
-    TRY(ensure_pin(eng, eng->h_res, n * 12));
-    int32_t *hr = (int32_t *)eng->h_res.p;
+    if(!to_sink) TRY(ensure_pin(eng, eng->h_res, n * 12));
+    /* results land in the pinned staging block, or straight in the caller's sink */
+    int32_t *hr_s = to_sink ? eng->sink_score : (int32_t *)eng->h_res.p;
+    int32_t *hr_x = to_sink ? eng->sink_x : (int32_t *)eng->h_res.p + n;
+    int32_t *hr_y = to_sink ? eng->sink_y : (int32_t *)eng->h_res.p + 2 * n;
     /* ~16 MB per chunk: small chunks leave the persistent DP kernel with a
      * fraction of a wave at its tail (measured: 4 x 25k pairs of 150 bp cost
      * 0.79 ms of kernel time, 2 x 50k 0.56 ms, one launch 0.54 ms) */
@@ -1014,7 +1047,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     const char *env = getenv("SEQALIGN_CHUNKS");
     if(env && atoi(env) >= 1 && atoi(env) <= seqalign_batch::MAX_CHUNKS) nchunks = atoi(env);
     if((size_t)nchunks > n) nchunks = (int)n;
-    if(uniform_batch && n >= 4096) {
+    if(uniform_batch && (n >= 4096 || given_uniform)) {
       int ogrid = (int)((n + 256) / 256);
       if(ogrid > eng->num_sms * 8) ogrid = eng->num_sms * 8;
       SA_LAUNCH(uniform_offsets_kernel, ogrid, 256, 0, cs, (int64_t *)eng->d_off_a.p, (int64_t *)eng->d_off_b.p,
@@ -1028,8 +1061,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     size_t bounds[seqalign_batch::MAX_CHUNKS + 1];
     for(int c = 0; c <= nchunks; c++) bounds[c] = n * (size_t)c / (size_t)nchunks;
     for(int c = 0; c < nchunks; c++) {
-      const int64_t a0 = h_off_a[bounds[c]], a1 = h_off_a[bounds[c + 1]];
-      const int64_t b0 = h_off_b[bounds[c]], b1 = h_off_b[bounds[c + 1]];
+      const int64_t a0 = hoa(bounds[c]), a1 = hoa(bounds[c + 1]);
+      const int64_t b0 = hob(bounds[c]), b1 = hob(bounds[c + 1]);
       if(a1 > a0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_a.p + a0, h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
       if(b1 > b0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_b.p + b0, h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
       CU_TRY(cudaEventRecord(eng->ev_copy[c], cs));
@@ -1039,7 +1072,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       if(m == 0) continue;
       CU_TRY(cudaStreamWaitEvent(eng->scan_stream, eng->ev_copy[c], 0));
       TRY(scan_launch(eng, d_a, d_b, d_oa + c0, d_ob + c0, m,
-                      h_off_a[c0 + m] - h_off_a[c0] + h_off_b[c0 + m] - h_off_b[c0], eng->scan_stream, c));
+                      hoa(c0 + m) - hoa(c0) + hob(c0 + m) - hob(c0), eng->scan_stream, c));
       CU_TRY(cudaEventRecord(eng->ev_scan[c], eng->scan_stream));
     }
     for(int c = 0; c < nchunks; c++) {
@@ -1052,14 +1085,19 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       scan_decode(eng, m, c, &bm);
       CU_TRY(cudaStreamWaitEvent(st, eng->ev_copy[c], 0));
       TRY(upload_tables(eng, bm, st));
-      if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
+      if(eng->ft.any_unknown) {
+        if(h_off_a) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
+        else {
+          std::vector<int64_t> ta(m + 1), tb(m + 1);
+          for(size_t i = 0; i <= m; i++) { ta[i] = (int64_t)(c0 + i) * la0; tb[i] = (int64_t)(c0 + i) * lb0; }
+          TRY(check_unknown_pairs(eng, h_a, ta.data(), h_b, tb.data(), m));
+        }
+      }
       int32_t *ds = (int32_t *)eng->d_score.p + c0, *dx = (int32_t *)eng->d_xend.p + c0, *dy = (int32_t *)eng->d_yend.p + c0;
       TRY(run_score(eng, algo, db, bm, ds, ends ? dx : nullptr, ends ? dy : nullptr, st, eng->ev_k0[c], eng->ev_k1[c]));
-      CU_TRY(cudaMemcpyAsync(hr + c0, ds, m * 4, cudaMemcpyDeviceToHost, st));
-      if(ends) {
-        CU_TRY(cudaMemcpyAsync(hr + n + c0, dx, m * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(hr + 2 * n + c0, dy, m * 4, cudaMemcpyDeviceToHost, st));
-      }
+      CU_TRY(cudaMemcpyAsync(hr_s + c0, ds, m * 4, cudaMemcpyDeviceToHost, st));
+      if(ends && hr_x) CU_TRY(cudaMemcpyAsync(hr_x + c0, dx, m * 4, cudaMemcpyDeviceToHost, st));
+      if(ends && hr_y) CU_TRY(cudaMemcpyAsync(hr_y + c0, dy, m * 4, cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(st));
     eng->last_ms = 0;
@@ -1069,14 +1107,22 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       CU_TRY(cudaEventElapsedTime(&ms, eng->ev_k0[c], eng->ev_k1[c]));
       eng->last_ms += ms;
     }
-    memcpy(eng->score.data(), hr, n * 4);
-    if(ends) {
-      memcpy(eng->xend.data(), hr + n, n * 4);
-      memcpy(eng->yend.data(), hr + 2 * n, n * 4);
-    } else if(algo == SEQALIGN_NW) {
+    if(!to_sink) {
+      memcpy(eng->score.data(), hr_s, n * 4);
+      if(ends) {
+        memcpy(eng->xend.data(), hr_x, n * 4);
+        memcpy(eng->yend.data(), hr_y, n * 4);
+      } else if(algo == SEQALIGN_NW) {
+        for(size_t i = 0; i < n; i++) {
+          eng->xend[i] = (int32_t)(hoa(i + 1) - hoa(i));
+          eng->yend[i] = (int32_t)(hob(i + 1) - hob(i));
+        }
+      }
+    } else if(!ends) {
+      /* score only into a sink: the end-cell arrays, if given, read like the internal ones */
       for(size_t i = 0; i < n; i++) {
-        eng->xend[i] = (int32_t)(h_off_a[i + 1] - h_off_a[i]);
-        eng->yend[i] = (int32_t)(h_off_b[i + 1] - h_off_b[i]);
+        if(eng->sink_x) eng->sink_x[i] = algo == SEQALIGN_NW ? (int32_t)(hoa(i + 1) - hoa(i)) : 0;
+        if(eng->sink_y) eng->sink_y[i] = algo == SEQALIGN_NW ? (int32_t)(hob(i + 1) - hob(i)) : 0;
       }
     }
   } else {
@@ -1169,6 +1215,40 @@ int seqalign_enable_peer_access(int device, int peer)
 }
 
 const char *seqalign_last_create_error(void) { return g_create_error.c_str(); }
+
+void *seqalign_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if(cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void seqalign_host_free(void *p)
+{
+  if(p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+
+int seqalign_synth_batch(int device, int kind, uint64_t seed, int64_t first_pair, int64_t npairs,
+                         int len_a, int len_b, void *d_seq_a, void *d_seq_b, void *stream)
+{
+  if(npairs < 0 || len_a < 0 || len_b < 0 || (kind != 0 && kind != 1) || !d_seq_a || !d_seq_b) return SEQALIGN_ERR_ARG;
+  if(npairs == 0) return SEQALIGN_OK;
+  if(cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  SynthArgs A;
+  A.seed = seed; A.first_pair = first_pair; A.npairs = npairs; A.len_a = len_a; A.len_b = len_b;
+  A.k = kind == 0 ? 4 : 20;
+  /* substitution / indel probabilities as 16-bit thresholds: DNA 0.05 / 0.01, protein 0.15 / 0.02 */
+  A.t_sub = kind == 0 ? 3277u : 9830u;
+  A.t_indel = kind == 0 ? 655u : 1311u;
+  A.seq_a = (uint8_t *)d_seq_a; A.seq_b = (uint8_t *)d_seq_b;
+  int64_t grid = (npairs + 127) / 128;
+  if(grid > 148 * 32) grid = 148 * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  SA_LAUNCH(synth_kernel, (int)grid, 128, 0, st, A);
+  if(cudaGetLastError() != cudaSuccess) return SEQALIGN_ERR_CUDA;
+  if(!stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return SEQALIGN_ERR_CUDA; }
+  return SEQALIGN_OK;
+}
 
 seqalign_batch_t *seqalign_batch_create(int device)
 {
@@ -1293,9 +1373,27 @@ int seqalign_batch_submit(seqalign_batch_t *eng, int algo, int mode,
 
 size_t seqalign_batch_size(const seqalign_batch_t *eng) { return eng ? eng->n : 0; }
 
+int seqalign_batch_set_result_sink(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  eng->sink_score = score;
+  eng->sink_x = score ? x_end : nullptr;
+  eng->sink_y = score ? y_end : nullptr;
+  return 0;
+}
+
+int seqalign_batch_submit_uniform(seqalign_batch_t *eng, int algo, int mode, const char *seq_a, size_t len_a,
+                                  const char *seq_b, size_t len_b, size_t n)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  CU_TRY(cudaSetDevice(eng->device));
+  return submit_common(eng, algo, mode, seq_a, nullptr, seq_b, nullptr, n, (int64_t)len_a, (int64_t)len_b);
+}
+
 int seqalign_batch_scores(seqalign_batch_t *eng, int32_t *score)
 {
   if(!eng || !score) return SEQALIGN_ERR_ARG;
+  if(eng->last_to_sink) return fail(eng, SEQALIGN_ERR_ARG, "the results of the last submit went to the result sink");
   memcpy(score, eng->score.data(), eng->n * 4);
   return 0;
 }
@@ -1303,6 +1401,7 @@ int seqalign_batch_scores(seqalign_batch_t *eng, int32_t *score)
 int seqalign_batch_ends(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end)
 {
   if(!eng) return SEQALIGN_ERR_ARG;
+  if(eng->last_to_sink) return fail(eng, SEQALIGN_ERR_ARG, "the results of the last submit went to the result sink");
   if(score) memcpy(score, eng->score.data(), eng->n * 4);
   if(x_end) memcpy(x_end, eng->xend.data(), eng->n * 4);
   if(y_end) memcpy(y_end, eng->yend.data(), eng->n * 4);
@@ -1416,6 +1515,7 @@ int seqalign_batch_run_device_async(seqalign_batch_t *eng, int algo,
 {
   if(!eng) return SEQALIGN_ERR_ARG;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
+  if((((uintptr_t)d_seq_a) | ((uintptr_t)d_seq_b)) & 15) return fail(eng, SEQALIGN_ERR_ARG, "d_seq_a / d_seq_b must be 16-byte aligned");
   const bool want_ends = (d_x_end != nullptr || d_y_end != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
   if(n == 0 || !can_speculate(eng, algo, want_ends)) {
     /* nothing to guess from yet (first run, new scoring, ...): the blocking call, which also learns the plan */
@@ -1439,7 +1539,7 @@ int seqalign_batch_run_device_async(seqalign_batch_t *eng, int algo,
   cudaStream_t cs = eng->copy_stream;
   CU_TRY(cudaEventRecord(eng->ev_copy[slot], st));
   TRY(launch_fast_score(eng, eng->spec.plan, sp, db, eng->spec.max_lb, (int32_t *)d_score,
-                        (int32_t *)d_x_end, (int32_t *)d_y_end, st, eng->ev_k0[slot], eng->ev_k1[slot]));
+                        (int32_t *)d_x_end, (int32_t *)d_y_end, st, eng->ev_k0[slot], eng->ev_k1[slot], 1 + slot));
   CU_TRY(cudaStreamWaitEvent(cs, eng->ev_copy[slot], 0));
   TRY(scan_launch(eng, db.a, db.b, db.off_a, db.off_b, n, (int64_t)n * 256, cs, slot));
   CU_TRY(cudaEventRecord(eng->ev_scan[slot], cs));
@@ -1461,6 +1561,8 @@ int seqalign_batch_run_device(seqalign_batch_t *eng, int algo,
   eng->last_launches = 0;
   if(!eng->have_scoring) return fail(eng, SEQALIGN_ERR_ARG, "seqalign_batch_set_scoring() has not been called");
   if(n == 0) return 0;
+  /* the kernels align their 16-byte bulk copies on the OFFSET (seq + (off & ~15)) */
+  if((((uintptr_t)d_seq_a) | ((uintptr_t)d_seq_b)) & 15) return fail(eng, SEQALIGN_ERR_ARG, "d_seq_a / d_seq_b must be 16-byte aligned");
   CU_TRY(cudaSetDevice(eng->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : eng->stream;
   DevBatch db;

@@ -9,6 +9,7 @@
  * the reference's error convention (stderr + exit(EXIT_FAILURE)).
  */
 #include <ctype.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,21 +23,32 @@ const char align_col_indel[] = "\033[91m";
 const char align_col_context[] = "\033[95m";
 const char align_col_stop[] = "\033[0m";
 
-static seqalign_batch_t *g_engine = NULL;
+/* The engine of the single-pair API.  The reference's L0-L2 code has no global
+ * state: distinct aligner objects may be used from distinct threads
+ * (SURVEY.md 8b "Threading").  An engine keeps per-submit state (device and
+ * pinned buffers, the last results), so every calling thread gets its own,
+ * created on first use and destroyed when the thread exits.  SEQALIGN_DEVICE
+ * selects the device (the batch API is the multi-GPU path). */
+static pthread_key_t g_engine_key;
+static pthread_once_t g_engine_once = PTHREAD_ONCE_INIT;
 
-/* the process-wide engine of the single-pair API (one device; the batch API
- * is the multi-GPU path).  SEQALIGN_DEVICE selects the device. */
+static void engine_key_destroy(void *p) { seqalign_batch_destroy((seqalign_batch_t *)p); }
+static void engine_key_make(void) { pthread_key_create(&g_engine_key, engine_key_destroy); }
+
 seqalign_batch_t *sa_host_engine(void)
 {
-  if(!g_engine) {
+  pthread_once(&g_engine_once, engine_key_make);
+  seqalign_batch_t *eng = pthread_getspecific(g_engine_key);
+  if(!eng) {
     const char *dev = getenv("SEQALIGN_DEVICE");
-    g_engine = seqalign_batch_create(dev ? atoi(dev) : 0);
-    if(!g_engine) {
+    eng = seqalign_batch_create(dev ? atoi(dev) : 0);
+    if(!eng) {
       fprintf(stderr, "seq-align (B200): %s\n", seqalign_last_create_error());
       exit(EXIT_FAILURE);
     }
+    pthread_setspecific(g_engine_key, eng);
   }
-  return g_engine;
+  return eng;
 }
 
 void sa_host_check(seqalign_batch_t *eng, int rc)

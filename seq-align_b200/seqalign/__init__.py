@@ -132,6 +132,8 @@ def load():
     L.seqalign_batch_set_scoring.argtypes = [vp, vp]
     L.seqalign_batch_submit.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, sz]
     L.seqalign_batch_submit_packed.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, sz]
+    L.seqalign_batch_submit_uniform.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, sz, vp, sz, sz]
+    L.seqalign_batch_set_result_sink.argtypes = [vp, vp, vp, vp]
     L.seqalign_batch_scores.argtypes = [vp, vp]
     L.seqalign_batch_ends.argtypes = [vp, vp, vp, vp]
     L.seqalign_batch_size.restype = sz
@@ -157,6 +159,33 @@ def load():
     L.seqalign_batch_hit_count.argtypes = [vp, sz]
     L.seqalign_batch_hit.argtypes = [vp, sz, sz, vp]
     L.seqalign_batch_matrices.argtypes = [vp, sz, vp, vp, vp]
+    L.seqalign_host_alloc.restype = vp
+    L.seqalign_host_alloc.argtypes = [sz]
+    L.seqalign_host_free.argtypes = [vp]
+    L.seqalign_multi_create.restype = vp
+    L.seqalign_multi_create.argtypes = [vp, ctypes.c_int]
+    L.seqalign_multi_destroy.argtypes = [vp]
+    L.seqalign_multi_devices.argtypes = [vp]
+    L.seqalign_multi_error.restype = ctypes.c_char_p
+    L.seqalign_multi_error.argtypes = [vp]
+    L.seqalign_multi_set_scoring.argtypes = [vp, vp]
+    L.seqalign_multi_set_hit_limits.argtypes = [vp, sz, ctypes.c_int32]
+    L.seqalign_multi_submit_packed.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, sz]
+    L.seqalign_multi_submit_uniform.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, sz, vp, sz, sz]
+    L.seqalign_multi_size.restype = sz
+    L.seqalign_multi_size.argtypes = [vp]
+    L.seqalign_multi_scores.argtypes = [vp, vp]
+    L.seqalign_multi_ends.argtypes = [vp, vp, vp, vp]
+    L.seqalign_multi_alignment.argtypes = [vp, sz, vp]
+    L.seqalign_multi_hit_count.restype = sz
+    L.seqalign_multi_hit_count.argtypes = [vp, sz]
+    L.seqalign_multi_hit.argtypes = [vp, sz, sz, vp]
+    L.seqalign_multi_matrices.argtypes = [vp, sz, vp, vp, vp]
+    L.seqalign_multi_where.argtypes = [vp, sz, vp, vp]
+    L.seqalign_multi_last_kernel_ms.restype = ctypes.c_double
+    L.seqalign_multi_last_kernel_ms.argtypes = [vp]
+    L.seqalign_synth_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int, ctypes.c_int, vp, vp, vp]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -334,6 +363,15 @@ class BatchAligner:
         self._check(self._L.seqalign_batch_submit_packed(self._h, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n))
         return n
 
+    def submit_uniform_ptrs(self, algo, mode, ptr_a, len_a, ptr_b, len_b, n):
+        """fixed-length pairs from raw host pointers: no offset arrays (seqalign_batch_submit_uniform)"""
+        self._check(self._L.seqalign_batch_submit_uniform(self._h, algo, mode, ptr_a, len_a, ptr_b, len_b, n))
+        return n
+
+    def set_result_sink(self, score_ptr=0, x_ptr=0, y_ptr=0):
+        """host pointers (ints) that receive the score-mode results of the following submits; 0 resets"""
+        self._check(self._L.seqalign_batch_set_result_sink(self._h, score_ptr or None, x_ptr or None, y_ptr or None))
+
     def submit(self, algo, mode, seqs_a, seqs_b):
         a, oa = pack(seqs_a)
         b, ob = pack(seqs_b)
@@ -423,6 +461,93 @@ class BatchAligner:
         return self._L.seqalign_batch_last_kernel(self._h).decode()
 
 
+class MultiAligner:
+    """One batch over several devices of this node from one process (seqalign_multi_t): pair ranges
+    balanced by cells, one engine and host thread per device, results by global pair index."""
+
+    def __init__(self, devices=None, scoring=None):
+        L = load()
+        self._L = L
+        if devices is None:
+            self._h = L.seqalign_multi_create(None, 0)
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            self._h = L.seqalign_multi_create(arr, len(devices))
+        if not self._h:
+            raise SeqAlignError(ERR_CUDA, L.seqalign_last_create_error().decode() or "no usable device")
+        self._res = L.alignment_create(256)
+        self._keep = None
+        if scoring is not None:
+            self.set_scoring(scoring)
+
+    def close(self):
+        if self._h:
+            self._L.alignment_free(self._res)
+            self._L.seqalign_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise SeqAlignError(rc, self._L.seqalign_multi_error(self._h).decode())
+        return rc
+
+    @property
+    def devices(self):
+        return self._L.seqalign_multi_devices(self._h)
+
+    def set_scoring(self, scoring):
+        self._check(self._L.seqalign_multi_set_scoring(self._h, scoring.ptr))
+
+    def set_hit_limits(self, max_hits=8, min_score=1):
+        self._check(self._L.seqalign_multi_set_hit_limits(self._h, max_hits, min_score))
+
+    def submit_packed(self, algo, mode, seq_a, off_a, seq_b, off_b):
+        self._keep = (seq_a, off_a, seq_b, off_b)
+        n = len(off_a) - 1
+        self._check(self._L.seqalign_multi_submit_packed(self._h, algo, mode, seq_a.ctypes.data, off_a.ctypes.data,
+                                                         seq_b.ctypes.data, off_b.ctypes.data, n))
+        return n
+
+    def submit_uniform(self, algo, mode, seq_a, len_a, seq_b, len_b, n):
+        self._keep = (seq_a, seq_b)
+        self._check(self._L.seqalign_multi_submit_uniform(self._h, algo, mode, seq_a.ctypes.data, len_a, seq_b.ctypes.data, len_b, n))
+        return n
+
+    def ends(self):
+        n = self._L.seqalign_multi_size(self._h)
+        s, x, y = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        self._check(self._L.seqalign_multi_ends(self._h, s.ctypes.data, x.ctypes.data, y.ctypes.data))
+        return s, x, y
+
+    def scores(self):
+        n = self._L.seqalign_multi_size(self._h)
+        s = np.zeros(n, dtype=np.int32)
+        self._check(self._L.seqalign_multi_scores(self._h, s.ctypes.data))
+        return s
+
+    def alignment(self, i):
+        rc = self._check(self._L.seqalign_multi_alignment(self._h, i, self._res))
+        return Alignment(self._res.contents) if rc == 1 else None
+
+    def hits(self, i):
+        out = []
+        for h in range(self._L.seqalign_multi_hit_count(self._h, i)):
+            self._check(self._L.seqalign_multi_hit(self._h, i, h, self._res))
+            out.append(Alignment(self._res.contents))
+        return out
+
+    def where(self, i):
+        d, l = ctypes.c_int(), ctypes.c_size_t()
+        self._check(self._L.seqalign_multi_where(self._h, i, ctypes.byref(d), ctypes.byref(l)))
+        return d.value, l.value
+
+
 def needleman_wunsch(a, b, scoring):
     """needleman_wunsch_align through the C API (single pair)."""
     L = load()
@@ -485,6 +610,21 @@ class PipelinedAligner:
         or (score, x_end, y_end)"""
         return self._pool.submit(self._run, algo, mode, (ptr_a, off_a_ptr, ptr_b, off_b_ptr), n)
 
+    def _run_uniform(self, algo, mode, ptr_a, len_a, ptr_b, len_b, n, sink):
+        eng = self._engines.get()
+        try:
+            eng.set_result_sink(sink)
+            eng.submit_uniform_ptrs(algo, mode, ptr_a, len_a, ptr_b, len_b, n)
+            return eng.last_kernel_ms
+        finally:
+            eng.set_result_sink(0)
+            self._engines.put(eng)
+
+    def submit_uniform_ptrs(self, algo, mode, ptr_a, len_a, ptr_b, len_b, n, score_sink):
+        """fixed-length pairs from raw (pinned) host pointers, scores written straight to the host
+        array at `score_sink` (n int32) by the device->host copy; the future's result is the kernel time"""
+        return self._pool.submit(self._run_uniform, algo, mode, ptr_a, len_a, ptr_b, len_b, n, score_sink)
+
     def submit_packed(self, algo, mode, seq_a, off_a, seq_b, off_b):
         keep = (seq_a, off_a, seq_b, off_b)
         fut = self.submit_ptrs(algo, mode, seq_a.ctypes.data, off_a.ctypes.data, seq_b.ctypes.data,
@@ -511,6 +651,16 @@ class PipelinedAligner:
         self._pool.shutdown(wait=True)
         for e in self._all:
             e.close()
+
+
+def synth_device(device, kind, seed, first_pair, npairs, len_a, len_b, d_seq_a, d_seq_b, stream=0):
+    """pairs [first_pair, first_pair+npairs) of the synthetic stream `seed` written into device
+    buffers (pointers as ints) by the CUDA generator; same bytes as seqalign.synth.synth_batch"""
+    from .synth import KINDS
+    rc = load().seqalign_synth_batch(int(device), KINDS[kind][0], int(seed), int(first_pair), int(npairs),
+                                     int(len_a), int(len_b), d_seq_a, d_seq_b, stream or None)
+    if rc != 0:
+        raise SeqAlignError(rc, "seqalign_synth_batch failed")
 
 
 def enable_peer_access(device, peer):

@@ -79,3 +79,57 @@ def test_align_sharded_world2(backend, tmp_path):
     b, ob = seqalign.pack(sb)
     es, ex, ey = orc_batch_sw(orc_from_scoring(scoring_from_spec(SPECS["sw_cli"])), a, oa, b, ob)
     assert np.array_equal(got[0], es) and np.array_equal(got[1], ex) and np.array_equal(got[2], ey)
+
+
+def _stream_worker(rank, world, port, lib, seed, uniform, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if lib:
+        os.environ["SEQALIGN_LIB"] = lib
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "seq-align_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import seqalign
+    from seqalign.distributed import align_sharded_stream
+    eng = seqalign.BatchAligner(0, seqalign.Scoring.sw_cli_default())
+    a, oa, b, ob = _stream_job(seed, uniform)
+    src = world - 1          # not rank 0: the source is a parameter, not an assumption
+    if rank == src:
+        res = align_sharded_stream(eng, seqalign.SW, a, oa, b, ob, src=src, chunk_pairs=7,
+                                   uniform=(24, 30) if uniform else None, ring=2)
+        np.save(out_path, res.numpy())
+    else:
+        assert align_sharded_stream(eng, seqalign.SW, src=src, chunk_pairs=7,
+                                    uniform=(24, 30) if uniform else None, ring=2) is None
+    eng.close()
+    dist.destroy_process_group()
+
+
+def _stream_job(seed, uniform):
+    import seqalign
+    if uniform:
+        from seqalign.synth import synth_batch
+        return synth_batch(seed, 1000, 45, 24, 30)
+    sa, sb = ragged_batch(seed, 45, 40, 40)
+    a, oa = seqalign.pack(sa)
+    b, ob = seqalign.pack(sb)
+    return a, oa, b, ob
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+def test_align_sharded_stream_world2(backend, tmp_path, uniform):
+    """chunk-overlapped scatter from host memory (the BASELINE config 5 data plane): chunks travel
+    rank by rank while earlier ones are aligned; scores come back in pair order"""
+    if backend == "gpu":
+        pytest.skip("CPU/gloo logic test; the GPU box runs the NCCL path through bench.py --gpus N")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_stream_worker, args=(2, port, os.environ.get("SEQALIGN_LIB", ""), 99, uniform, out), nprocs=2, join=True)
+    got = np.load(out)
+    a, oa, b, ob = _stream_job(99, uniform)
+    es, _, _ = orc_batch_sw(orc_from_scoring(scoring_from_spec(SPECS["sw_cli"])), a, oa, b, ob)
+    assert np.array_equal(got, es)

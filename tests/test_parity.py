@@ -172,6 +172,39 @@ def test_uniform_batch_offsets_made_on_device(engine, big):
     assert np.array_equal(s2[:-1], es[:-1])
 
 
+def test_uniform_submit_and_result_sink(engine, big):
+    """seqalign_batch_submit_uniform (no offset arrays) + seqalign_batch_set_result_sink (scores written
+    straight into the caller's array): same numbers as the packed submit, for SW and NW, with and without
+    end cells; the engine's own accessors refuse after a submit into a sink"""
+    from seqalign.synth import synth_batch
+    n = 5000 if big else 9
+    a, oa, b, ob = synth_batch(7, 100, n, 150 if big else 40, 140 if big else 33)
+    la, lb = int(oa[1]), int(ob[1])
+    for algo, spec in ((SW, "sw_cli"), (NW, "nw_default")):
+        engine.set_scoring(scoring_from_spec(SPECS[spec]))
+        engine.submit_packed(algo, MODE_SCORE, a, oa, b, ob)
+        es, ex, ey = engine.ends()
+        engine.submit_uniform_ptrs(algo, MODE_SCORE, a.ctypes.data, la, b.ctypes.data, lb, n)
+        s, x, y = engine.ends()
+        assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
+        sink = [np.full(n, -77, dtype=np.int32) for _ in range(3)]
+        engine.set_result_sink(*[v.ctypes.data for v in sink])
+        try:
+            engine.submit_uniform_ptrs(algo, MODE_SCORE, a.ctypes.data, la, b.ctypes.data, lb, n)
+            assert np.array_equal(sink[0], es) and np.array_equal(sink[1], ex) and np.array_equal(sink[2], ey)
+            with pytest.raises(seqalign.SeqAlignError):
+                engine.scores()
+            sink[0][:] = -77
+            engine.set_result_sink(sink[0].ctypes.data)          # scores only
+            engine.submit_packed(algo, seqalign.MODE_SCORE_ONLY, a, oa, b, ob)
+            assert np.array_equal(sink[0], es)
+        finally:
+            engine.set_result_sink(0)
+        engine.submit_uniform_ptrs(algo, MODE_ALIGN, a.ctypes.data, la, b.ctypes.data, lb, min(n, 50))
+        assert engine.alignment(0).score == es[0]
+    assert np.array_equal(engine.scores()[: min(n, 50)], es[: min(n, 50)])
+
+
 def test_protein_config_sample(engine, big):
     """BASELINE config 4 shape: SW, protein 400x400, BLOSUM62"""
     n, L = (400, 400) if big else (2, 70)
@@ -696,6 +729,32 @@ def _device_arrays(big, arrays):
 
 def _device_result(big, t, n):
     return t.cpu().numpy()[:n] if big else t[:n]
+
+
+def test_full_size_long_pairs_oracle(engine, big):
+    """BASELINE config 3 shape against the oracle itself: 16 pairs of 10k x 10k (SURVEY.md 8d asks for
+    a fixed 16-pair sample), NW with free start and end gaps: score AND both gapped strings, i.e. the
+    reference's GA > GB > M tie-breaking along 20,000 traceback steps per pair.  The oracle fills three
+    400 MB matrices per pair (about a second each)."""
+    if not big:
+        pytest.skip("full size runs on the GPU only")
+    import torch
+    n, L = 16, 10000
+    da = torch.empty(n * L, dtype=torch.uint8, device="cuda:0")
+    db = torch.empty(n * L, dtype=torch.uint8, device="cuda:0")
+    seqalign.synth_device(0, "dna", 3, 4000, n, L, L, da.data_ptr(), db.data_ptr())   # pairs 4000.. of the config-3 stream
+    a, b = da.cpu().numpy(), db.cpu().numpy()
+    oa = np.arange(n + 1, dtype=np.int64) * L
+    sc = scoring_from_spec(SPECS["free_ends"])
+    engine.set_scoring(sc)
+    engine.submit_packed(NW, MODE_ALIGN, a, oa, b, oa)
+    assert engine.last_kernel.startswith("long_nw")
+    o = orc_from_scoring(sc)
+    for i in range(n):
+        rc, es, ea, eb = orc_nw(o, a[i * L:(i + 1) * L].tobytes(), b[i * L:(i + 1) * L].tobytes())
+        al = engine.alignment(i)
+        assert rc == 0 and al.score == es, i
+        assert al.result_a == ea and al.result_b == eb, i
 
 
 def test_device_resident_api(big):
