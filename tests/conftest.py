@@ -63,8 +63,9 @@ def backend():
 
 @pytest.fixture(scope="session")
 def big(backend):
-    """True on the GPU: full-size batches; False in the emulator: small ones."""
-    return backend == "gpu"
+    """True on the GPU: full-size batches; False in the emulator: small ones.
+    SEQALIGN_TEST_SMALL=1 keeps the small sizes on the GPU too (runs under compute-sanitizer)."""
+    return backend == "gpu" and os.environ.get("SEQALIGN_TEST_SMALL") != "1"
 
 
 @pytest.fixture(scope="session")

@@ -714,10 +714,16 @@ def test_full_size_long_pairs_rescore(engine, big):
         assert _rescore(al.result_a, al.result_b, look, sc.s.gap_open, sc.s.gap_extend, free_ends=True) == al.score
 
 
+def _on_gpu():
+    import conftest
+    return conftest.BACKEND == "gpu"
+
+
 def _device_arrays(big, arrays):
     """CUDA copies of numpy arrays (GPU) / the arrays themselves (the emulator's
-    device memory is host memory); returns (keepalive, pointers)"""
-    if big:
+    device memory is host memory); returns (keepalive, pointers).  `big` only sizes the
+    callers' batches; what counts here is which backend runs."""
+    if _on_gpu():
         import torch
         ts = [torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0") for a in arrays]
         torch.cuda.synchronize()
@@ -728,7 +734,7 @@ def _device_arrays(big, arrays):
 
 
 def _device_result(big, t, n):
-    return t.cpu().numpy()[:n] if big else t[:n]
+    return t.cpu().numpy()[:n] if _on_gpu() else t[:n]
 
 
 def test_full_size_long_pairs_oracle(engine, big):
