@@ -544,6 +544,11 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   LongPlan lplan;
   const bool long_dir = !fast_dir && eng->force_mode != 1 &&
                         long_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, &lplan);
+  /* wide pairs trace back through checkpoints and recomputed tiles (0.14 B/cell, fill at score speed);
+   * SEQALIGN_LONG_FLAGS=1 keeps the flag bytes (1 B/cell) */
+  const char *lf_env = getenv("SEQALIGN_LONG_FLAGS");
+  const bool long_ckpt = long_dir && !(lf_env && lf_env[0] == '1');
+  if(long_ckpt) { lplan.ckpt = true; lplan.dir = false; lplan.name = "long_nw_ckpt"; }
   if(algo == SEQALIGN_SW && !fast_dir) {
     TRY(run_score(eng, algo, db, bm, d_score, d_xend, d_yend, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -589,7 +594,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     dir_off.clear(); out_off.clear();
     while(c1 < n) {
       const int64_t la = h_off_a[c1 + 1] - h_off_a[c1], lb = h_off_b[c1 + 1] - h_off_b[c1];
-      const int64_t need = dir_bytes(la, lb);
+      const int64_t need = long_ckpt ? long_trace_bytes((int)la, (int)lb) : dir_bytes(la, lb);
       if(c1 > c0 && dbytes + need > budget) break;
       dir_off.push_back(dbytes);
       out_off.push_back(eng->res_off[c1] - eng->res_off[c0]);
@@ -604,7 +609,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
         c1 = c0 + (c1 - c0) / g * g;
         dir_off.resize(c1 - c0); out_off.resize(c1 - c0);
         const int64_t la = h_off_a[c1] - h_off_a[c1 - 1], lb = h_off_b[c1] - h_off_b[c1 - 1];
-        dbytes = dir_off.back() + dir_bytes(la, lb);
+        dbytes = dir_off.back() + (long_ckpt ? long_trace_bytes((int)la, (int)lb) : dir_bytes(la, lb));
       }
     }
     const size_t m = c1 - c0;
@@ -673,7 +678,13 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
      * bytes; many short ones: a thread per pair */
     const char *wenv = getenv("SEQALIGN_WALK");
     const bool tiled = wenv ? strcmp(wenv, "tiled") == 0 : bm.cells / (int64_t)n >= (1 << 20);
-    if(tiled) {
+    if(long_ckpt) {
+      int8_t *w_t8 = nullptr;
+      int32_t *w_t32 = nullptr;
+      TRY(upload_plan_tables(eng, lplan.tab8, lplan.tab32, &w_t8, &w_t32, st));
+      if(walk_ckpt_launch(lplan, W, w_t8, w_t32, walk_ckpt_grid(eng->num_sms, (int64_t)m), st) != 0)
+        return fail(eng, SEQALIGN_ERR_CUDA, "recompute walk launch failed");
+    } else if(tiled) {
       int wgrid = (int)((m + WT_WARPS - 1) / WT_WARPS);
       if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;
       SA_LAUNCH(walk_tiled_kernel, wgrid, WT_WARPS * 32, 0, st, W);
@@ -712,6 +723,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     c0 = c1;
   }
   eng->last_kernel = fast_dir ? (algo == SEQALIGN_SW ? "fast_sw_dir+walk" : "fast_nw_dir+walk")
+                     : long_ckpt ? "long_nw_ckpt+walk_recompute"
                      : long_dir ? "long_nw_dir+walk"
                                 : (algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk");
 

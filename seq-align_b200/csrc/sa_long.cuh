@@ -30,6 +30,17 @@
  * the "generic" row body that selects the penalties per column / per row;
  * everything else runs the lean body.
  *
+ * Traceback comes in two shapes.  DIR writes one flag byte per cell (below).
+ * CKPT writes almost nothing: the right edge of every strip (H', GB per row,
+ * which the next strip needs anyway) is kept per pair instead of in a ring,
+ * and every LONG_CK_ROWS rows each lane parks its row state (H', GA of its K
+ * columns).  That is 8 bytes per 512 cells plus 8 bytes per 64 cells, 0.14
+ * bytes per cell instead of 1, and the fill runs at the speed of the score
+ * kernel.  walk_ckpt_kernel then recomputes, with this very row body, only the
+ * tiles (one strip wide, LONG_CK_ROWS rows high) that the traceback path
+ * crosses -- about 3 % of the cells of a 10k x 10k pair -- and takes the
+ * reference's decisions (alignment.c:311-327) from the recomputed flags.
+ *
  * Traceback flags are the five equality bits of sa_fast.cuh (same byte
  * layout, same walk): they are computed with the penalties that applied to
  * the cell, so alignment_reverse_move's zeroed penalties in the last column /
@@ -48,6 +59,24 @@ namespace sa {
 
 constexpr int LONG_WARPS = 8;
 constexpr int LONG_NEG = -(1 << 29);   /* "minus infinity" of the NW borders: far from INT_MIN, below every real value */
+constexpr int LONG_K = 16;             /* columns per lane */
+constexpr int LONG_STRIP = 32 * LONG_K;
+constexpr int LONG_CK_ROWS = 64;       /* CKPT: a row checkpoint every this many rows */
+
+/* CKPT: bytes of one pair's trace region, [strip edges | row checkpoints]:
+ *   edge[s][y]  int2 (H', GB) of cell (x = (s+1)*STRIP, y), s < nstrips-1, y in [0, lb]
+ *   ck[r][x-1]  int2 (H', GA) of cell (x, y = (r+1)*CK_ROWS), x in [1, roundup16(la)], r < lb/CK_ROWS */
+__host__ __device__ __forceinline__ int64_t long_edge_ints2(int la, int lb)
+{
+  const int64_t nstrips = ((int64_t)la + LONG_STRIP - 1) / LONG_STRIP;
+  return nstrips > 1 ? (nstrips - 1) * ((int64_t)lb + 1) : 0;
+}
+__host__ __device__ __forceinline__ int64_t long_ck_width(int la) { return ((int64_t)la + 15) & ~(int64_t)15; }
+__host__ __device__ __forceinline__ int64_t long_trace_bytes(int la, int lb)
+{
+  const int64_t ints2 = long_edge_ints2(la, lb) + (int64_t)(lb / LONG_CK_ROWS) * long_ck_width(la);
+  return (ints2 * 8 + 15) & ~(int64_t)15;
+}
 
 struct LongArgs {
   const uint8_t *seq_a, *seq_b;
@@ -59,7 +88,7 @@ struct LongArgs {
   const uint8_t *lut;
   int2 *bnd;                      /* [grid][2][LONG_WARPS][bnd_rows] strip edges */
   int64_t bnd_rows;
-  uint8_t *dir;                   /* DIR: traceback flag bytes, row-major per pair */
+  uint8_t *dir;                   /* DIR: traceback flag bytes, row-major per pair; CKPT: the pairs' trace regions */
   const int64_t *dir_off;
   int32_t *score, *xend, *yend;   /* per pair of the launch */
   int mul_one;
@@ -68,6 +97,7 @@ struct LongArgs {
 struct LongPlan {
   int K = 0;
   bool is_sw = false, prof32 = false, dir = false, noend = false;
+  bool ckpt = false;   /* traceback through checkpoints + recomputed tiles instead of flag bytes */
   const char *name = "";
   std::vector<int8_t> tab8;
   std::vector<int32_t> tab32;
@@ -121,10 +151,12 @@ __device__ __forceinline__ void long_row(int (&hp)[K], int (&ga)[K], int &hl, in
   }
 }
 
-template <int K, bool IS_SW, bool PROF32, bool DIR, bool NOEND>
+template <int K, bool IS_SW, bool PROF32, bool DIR, bool NOEND, bool CKPT = false>
 __global__ void __launch_bounds__(LONG_WARPS * 32, 2)
 long_kernel(const LongArgs A)
 {
+  static_assert(!(DIR && CKPT), "flag bytes or checkpoints, not both");
+  static_assert(!CKPT || K == LONG_K, "the walk recomputes tiles with LONG_K columns per lane");
   constexpr int W = LONG_WARPS;
   constexpr int STRIP = 32 * K;
   constexpr int KW = PROF32 ? K : (K + 3) / 4;
@@ -180,6 +212,13 @@ long_kernel(const LongArgs A)
     uint8_t *dirp = nullptr;
     int dstride = 0;
     if(DIR) { dirp = A.dir + A.dir_off[p]; dstride = (int)dir_stride(la); }
+    int2 *pair_edge = nullptr, *pair_ck = nullptr;
+    int ckw = 0;
+    if(CKPT) {
+      pair_edge = (int2 *)(A.dir + A.dir_off[p]);
+      pair_ck = pair_edge + long_edge_ints2(la, lb);
+      ckw = (int)long_ck_width(la);
+    }
 
     for(int s = (int)((wib + W - gs_base % W) % W); s < nstrips; s += W) {
       const unsigned gs = gs_base + (unsigned)s;
@@ -188,9 +227,14 @@ long_kernel(const LongArgs A)
       const bool more = s + 1 < nstrips;
       int2 *out_bnd = cta_bnd + (int64_t)(((gs / W) & 1) * W + wib) * A.bnd_rows;
       const int2 *in_bnd = cta_bnd + (int64_t)((((gs - 1) / W) & 1) * W + (wib + W - 1) % W) * A.bnd_rows;
+      if(CKPT) {
+        /* the edges are kept per pair (the walk reads them later): no ring, no slot to wait for */
+        out_bnd = pair_edge + (int64_t)s * (lb + 1);
+        in_bnd = pair_edge + (int64_t)(s - 1) * (lb + 1);
+      }
       const unsigned long long in_base = (unsigned long long)(gs - 1) << 32;
       /* my edge slot was last used two rounds ago; its reader must be done */
-      if(more && gs >= 2 * W)
+      if(!CKPT && more && gs >= 2 * W)
         while(s_fin[(wib + 1) % W] < gs - 2 * W + 2) SA_SPIN_HINT();
 
       /* query profile of my K columns: row c holds sub'(a[x], c) */
@@ -315,6 +359,13 @@ long_kernel(const LongArgs A)
                 if(xf - 1 + 4 * q < dstride) drow[q] = dw[q];
             }
           }
+          if(CKPT && (y & (LONG_CK_ROWS - 1)) == 0 && xf - 1 < ckw) {
+            /* row checkpoint: this lane's (H', GA) of row y, 128 contiguous bytes */
+            uint4 *ck = (uint4 *)(pair_ck + (int64_t)(y / LONG_CK_ROWS - 1) * ckw + (xf - 1));
+#pragma unroll
+            for(int q = 0; q < K / 2; q++)
+              ck[q] = make_uint4((unsigned)hp[2 * q], (unsigned)ga[2 * q], (unsigned)hp[2 * q + 1], (unsigned)ga[2 * q + 1]);
+          }
           if(more && lane == 31) {
             out_bnd[y] = make_int2(hl, gb);
             if((y & 31) == 0 || y == lb) {
@@ -346,6 +397,218 @@ long_kernel(const LongArgs A)
       if(lane == 0) s_fin[wib] = gs + 1;
     }
     gs_base += (unsigned)nstrips;
+  }
+}
+
+/* ---------------------------------------------------------------------------
+ * walk_ckpt_kernel: traceback over the checkpoints of a CKPT fill.  One warp
+ * per pair.  The walk itself is walk_pair() of sa_kernels.cuh (the loops of
+ * needleman_wunsch.c:79-132 / smith_waterman.c:187-255 over the five equality
+ * flags); what differs is where the flags come from: when the walk asks for a
+ * cell outside the window in shared memory, the warp recomputes the tile that
+ * holds it -- one strip wide, up to LONG_CK_ROWS rows high, cut off at the
+ * asking cell (the walk only moves up and left) -- from the row checkpoint
+ * above it and the strip edge to its left, with the fill's own row body
+ * (long_row<..., DIR>), so the flags are the ones the fill would have written.
+ */
+constexpr int WK_WARPS = 2;
+
+inline size_t walk_ckpt_smem_bytes(int ncodes, bool prof32)
+{
+  const int KS = prof32 ? prof32_stride(LONG_K) : LONG_K / 4;
+  const size_t tab = (((size_t)(prof32 ? 4 : 1) * ncodes * (ncodes + 1)) + 15) & ~(size_t)15;
+  const size_t warp_bytes = (size_t)ncodes * 32 * KS * 4 + 64 + 32 * 8 + (size_t)LONG_CK_ROWS * LONG_STRIP;
+  return 256 + tab + WK_WARPS * warp_bytes;
+}
+
+/* what a tile recompute needs to know about the pair and the warp's shared memory */
+struct WalkCkCtx {
+  const uint8_t *pa, *pb;
+  int la, lb, nstrips, ckw;
+  const int2 *pair_edge, *pair_ck;
+  const uint8_t *s_lut;
+  const void *s_tab;
+  unsigned char *s_prof;
+  uint8_t *s_bring;
+  int2 *s_chunk;
+  uint8_t *s_flags;
+  int n, open, ext, gap_open, no_start, mul_one;
+};
+
+/* recompute the flags of the tile that holds cell (cx, cy) (0-based), cut off at that cell */
+template <bool IS_SW, bool NOEND, bool PROF32>
+__device__ __noinline__ void walk_ckpt_recompute(WalkCkCtx &C, const int cx, const int cy)
+{
+  constexpr int K = LONG_K, STRIP = LONG_STRIP;
+  constexpr int KW = PROF32 ? K : K / 4;
+  constexpr int KS = PROF32 ? prof32_stride(K) : KW;
+  constexpr int PSTRIDE = 32 * KS * 4;
+  const int lane = threadIdx.x & 31;
+  const int n = C.n, tw = n + 1, open = C.open, ext = C.ext, la = C.la, lb = C.lb;
+  const unsigned *prow = (const unsigned *)C.s_prof + lane * KS;
+  /* H' of the border cell (x, 0) / (0, y) (alignment.c:47-81) */
+  auto border_h = [&](int k) -> int { return IS_SW ? open : (C.no_start ? 0 : C.gap_open + k * ext) + open; };
+
+  __syncwarp();
+  const int s = cx / STRIP, x0c = s * STRIP;
+  const int y0c = (cy / LONG_CK_ROWS) * LONG_CK_ROWS;
+  const int nrows = cy - y0c + 1, nl = (cx - x0c) / K + 1;
+  const bool more = s + 1 < C.nstrips;
+  const int xf = x0c + lane * K + 1;
+  const int2 *in_bnd = C.pair_edge + (int64_t)(s - 1) * (lb + 1);
+  const int2 *ck = C.pair_ck + (int64_t)(y0c / LONG_CK_ROWS - 1) * C.ckw;
+
+  unsigned lastmask = 0;
+  {
+    int acode[K];
+#pragma unroll
+    for(int j = 0; j < K; j++) {
+      acode[j] = (xf + j <= la) ? C.s_lut[C.pa[xf + j - 1]] : n;
+      if(NOEND && xf + j == la) lastmask |= 1u << j;
+    }
+    for(int c = 0; c < n; c++) {
+      unsigned *dst = (unsigned *)(C.s_prof + c * PSTRIDE) + lane * KS;
+      if(PROF32) {
+        const int32_t *trow = (const int32_t *)C.s_tab + c * tw;
+#pragma unroll
+        for(int j = 0; j < K; j++) dst[j] = (unsigned)trow[acode[j]];
+      } else {
+        const int8_t *trow = (const int8_t *)C.s_tab + c * tw;
+#pragma unroll
+        for(int q = 0; q < KW; q++) {
+          unsigned word = 0;
+#pragma unroll
+          for(int b4 = 0; b4 < 4; b4++) word |= (unsigned)(uint8_t)trow[acode[4 * q + b4]] << (8 * b4);
+          dst[q] = word;
+        }
+      }
+    }
+  }
+
+  /* the row above the tile: border row 0 or the checkpoint of row y0c */
+  int hp[K], ga[K];
+  int hd;
+  if(y0c == 0) {
+#pragma unroll
+    for(int j = 0; j < K; j++) { hp[j] = border_h(xf + j); ga[j] = IS_SW ? 0 : LONG_NEG; }
+    hd = (IS_SW || xf == 1) ? open : border_h(xf - 1);
+  } else {
+    const bool in_ck = xf - 1 < C.ckw && lane < nl;
+#pragma unroll
+    for(int q = 0; q < K / 2; q++) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if(in_ck) v = ((const uint4 *)(ck + (xf - 1)))[q];
+      hp[2 * q] = (int)v.x; ga[2 * q] = (int)v.y; hp[2 * q + 1] = (int)v.z; ga[2 * q + 1] = (int)v.w;
+    }
+    if(lane > 0) hd = in_ck ? ck[xf - 2].x : 0;
+    else if(x0c == 0) hd = border_h(y0c);
+    else hd = in_bnd[y0c].x;
+  }
+
+  int out_h = 0, out_gb = 0;
+  const int nsteps = nrows + nl - 1;
+  for(int st = 0; st < nsteps; st++) {
+    const int yl = st - lane + 1, y = y0c + yl;
+    const bool active = yl >= 1 && yl <= nrows && lane < nl;
+    if((st & 31) == 0) {
+      __syncwarp();
+      const int row = y0c + st + 1 + lane;
+      if(row <= y0c + nrows) {
+        C.s_bring[(row - 1) & 63] = C.s_lut[C.pb[row - 1]];
+        if(x0c > 0) C.s_chunk[lane] = in_bnd[row];
+      }
+      __syncwarp();
+    }
+    int hl = __shfl_up_sync(FULL, out_h, 1);
+    int gb = __shfl_up_sync(FULL, out_gb, 1);
+    if(lane == 0) {
+      if(x0c == 0) {
+        if(IS_SW) { hl = open; gb = 0; }
+        else { hl = border_h(y); gb = LONG_NEG; }
+      } else {
+        const int2 v = C.s_chunk[st & 31];
+        hl = v.x; gb = v.y;
+      }
+    }
+    const int hl_in = hl;
+    if(active) {
+      const int c = C.s_bring[(y - 1) & 63];
+      const unsigned *pw = prow + c * (PSTRIDE / 4);
+      unsigned w[KW];
+#pragma unroll
+      for(int q = 0; q < KW / 4; q++) {
+        const uint4 v = ((const uint4 *)pw)[q];
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+      unsigned dw[K / 4];
+#pragma unroll
+      for(int q = 0; q < K / 4; q++) dw[q] = 0;
+      if(NOEND && (!more || y == lb))
+        long_row<K, IS_SW, PROF32, true, true>(hp, ga, hl, gb, hd, w, dw, open, ext, C.mul_one, lastmask, y == lb);
+      else
+        long_row<K, IS_SW, PROF32, true, false>(hp, ga, hl, gb, hd, w, dw, open, ext, C.mul_one, 0u, false);
+      *(uint4 *)(C.s_flags + (yl - 1) * STRIP + lane * K) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+      out_h = hl;
+      out_gb = gb;
+      hd = hl_in;
+    }
+  }
+  __syncwarp();
+}
+
+template <bool IS_SW, bool NOEND, bool PROF32>
+__global__ void __launch_bounds__(WK_WARPS * 32)
+walk_ckpt_kernel(const WalkArgs A, const int8_t *__restrict__ tab8, const int32_t *__restrict__ tab32, const int mul_one)
+{
+  constexpr int K = LONG_K, STRIP = LONG_STRIP;
+  constexpr int KS = PROF32 ? prof32_stride(K) : K / 4;
+  constexpr int PSTRIDE = 32 * KS * 4;
+  unsigned char *dsm = SA_DYN_SMEM();
+  const ScoreParams &sp = A.sp;
+  const int n = sp.ncodes, tw = n + 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+
+  uint8_t *s_lut = dsm;
+  int8_t *s_tab8 = (int8_t *)(dsm + 256);
+  int32_t *s_tab32 = (int32_t *)(dsm + 256);
+  const int tab_bytes = ((PROF32 ? 4 : 1) * n * tw + 15) & ~15;
+  const int warp_bytes = n * PSTRIDE + 64 + 32 * 8 + LONG_CK_ROWS * STRIP;
+  unsigned char *wbase = dsm + 256 + tab_bytes + wib * warp_bytes;
+
+  for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+  if(PROF32) { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab32[i] = tab32[i]; }
+  else       { for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab8[i] = tab8[i]; }
+  __syncthreads();
+
+  WalkCkCtx C;
+  C.s_lut = s_lut; C.s_tab = dsm + 256;
+  C.s_prof = wbase;
+  C.s_bring = wbase + n * PSTRIDE;
+  C.s_chunk = (int2 *)(C.s_bring + 64);
+  C.s_flags = (uint8_t *)(C.s_chunk + 32);
+  C.n = n; C.open = sp.open; C.ext = sp.ext; C.gap_open = sp.gap_open; C.no_start = sp.no_start; C.mul_one = mul_one;
+
+  for(int64_t r = (int64_t)blockIdx.x * WK_WARPS + wib; r < A.npairs; r += (int64_t)gridDim.x * WK_WARPS) {
+    const int64_t p = A.pair0 + r;
+    const int64_t oa = A.off_a[p], ob = A.off_b[p];
+    C.la = (int)(A.off_a[p + 1] - oa); C.lb = (int)(A.off_b[p + 1] - ob);
+    C.pa = A.seq_a + oa; C.pb = A.seq_b + ob;
+    C.nstrips = (C.la + STRIP - 1) / STRIP;
+    C.pair_edge = (const int2 *)(A.dir + A.dir_off[r]);
+    C.pair_ck = C.pair_edge + long_edge_ints2(C.la, C.lb);
+    C.ckw = (int)long_ck_width(C.la);
+    int wx0 = 0, wy0 = 0, wx1 = -1, wy1 = -1;   /* window: cells (0-based) [wx0, wx1] x [wy0, wy1], kept in registers */
+    const uint8_t *flags = C.s_flags;
+    auto get = [&](int cx, int cy) -> unsigned {
+      if(cx < wx0 || cx > wx1 || cy < wy0 || cy > wy1) {
+        walk_ckpt_recompute<IS_SW, NOEND, PROF32>(C, cx, cy);
+        wx0 = (cx / STRIP) * STRIP; wx1 = wx0 + ((cx - wx0) / K + 1) * K - 1;
+        wy0 = (cy / LONG_CK_ROWS) * LONG_CK_ROWS; wy1 = cy;
+      }
+      return flags[(cy - wy0) * STRIP + (cx - wx0)];
+    };
+    walk_pair(A, r, get, lane == 0);
+    __syncwarp();
   }
 }
 
@@ -399,13 +662,14 @@ inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
       if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
     }
   plan->name = want_dir ? "long_nw_dir" : "long_nw_score";
+  plan->ckpt = false;
   return true;
 }
 
-template <int K, bool P32, bool DIR, bool NOEND>
+template <int K, bool P32, bool DIR, bool NOEND, bool CKPT = false>
 int long_launch_one(const LongPlan &plan, const LongArgs &L, int grid, cudaStream_t st)
 {
-  void (*kfn)(const LongArgs) = long_kernel<K, false, P32, DIR, NOEND>;
+  void (*kfn)(const LongArgs) = long_kernel<K, false, P32, DIR, NOEND, CKPT>;
   if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
   SA_LAUNCH(kfn, grid, LONG_WARPS * 32, plan.smem, st, L);
   return 0;
@@ -424,6 +688,12 @@ inline int long_grid(const LongPlan &plan, int num_sms, int64_t npairs)
 inline int long_launch(const LongPlan &plan, LongArgs L, int grid, cudaStream_t st)
 {
   L.mul_one = 1;
+  if(plan.ckpt) {
+    if(plan.prof32) return plan.noend ? long_launch_one<16, true, false, true, true>(plan, L, grid, st)
+                                      : long_launch_one<16, true, false, false, true>(plan, L, grid, st);
+    return plan.noend ? long_launch_one<16, false, false, true, true>(plan, L, grid, st)
+                      : long_launch_one<16, false, false, false, true>(plan, L, grid, st);
+  }
 #define SA_LONG_CASE(P32_, DIR_, NOEND_)                                          \
   if(plan.prof32 == P32_ && plan.dir == DIR_ && plan.noend == NOEND_)             \
     return long_launch_one<16, P32_, DIR_, NOEND_>(plan, L, grid, st)
@@ -433,6 +703,27 @@ inline int long_launch(const LongPlan &plan, LongArgs L, int grid, cudaStream_t 
   SA_LONG_CASE(false, false, true); SA_LONG_CASE(false, false, false);
 #undef SA_LONG_CASE
   return -1;
+}
+
+/* the recompute walk of a CKPT fill; tab8 = the plan's int8 table on the device */
+inline int walk_ckpt_launch(const LongPlan &plan, const WalkArgs &W, const int8_t *d_tab8, const int32_t *d_tab32,
+                            int grid, cudaStream_t st)
+{
+  const size_t smem = walk_ckpt_smem_bytes(W.sp.ncodes, plan.prof32);
+  void (*kfn)(const WalkArgs, const int8_t *, const int32_t *, const int);
+  if(plan.prof32) kfn = plan.noend ? walk_ckpt_kernel<false, true, true> : walk_ckpt_kernel<false, false, true>;
+  else kfn = plan.noend ? walk_ckpt_kernel<false, true, false> : walk_ckpt_kernel<false, false, false>;
+  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  SA_LAUNCH(kfn, grid, WK_WARPS * 32, smem, st, W, d_tab8, d_tab32, 1);
+  return 0;
+}
+
+/* CTAs of the recompute walk: 2 warps and ~70 KB of shared memory each, three per SM */
+inline int walk_ckpt_grid(int num_sms, int64_t npairs)
+{
+  int64_t g = (npairs + WK_WARPS - 1) / WK_WARPS;
+  if(g > (int64_t)num_sms * 3) g = (int64_t)num_sms * 3;
+  return g < 1 ? 1 : (int)g;
 }
 
 } // namespace sa

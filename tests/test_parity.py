@@ -252,12 +252,14 @@ def test_wide_pairs_cooperative(engine, big, shape):
         assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb)
 
 
-@pytest.mark.parametrize("case", ["ragged_wide", "many_strips", "short_free_ends", "protein_wide"])
-def test_wide_pairs_strip_pipeline(engine, big, case):
+@pytest.mark.parametrize("case", ["ragged_wide", "many_strips", "short_free_ends", "protein_wide", "tall_checkpoints"])
+def test_wide_pairs_strip_pipeline(engine, big, case, monkeypatch):
     """NW beyond one strip / with free end gaps: the strip-pipelined kernel
     (sa_long.cuh).  Ragged widths (strips of several pairs interleave in a
     CTA), more than 2 x LONG_WARPS strips (edge slots are reused), the
-    last-column / last-row rules of free end gaps; scores and strings."""
+    last-column / last-row rules of free end gaps; scores and strings.  The traceback runs both
+    ways: through checkpoints + recomputed tiles (default; tall pairs cross several row
+    checkpoints) and through flag bytes (SEQALIGN_LONG_FLAGS=1)."""
     alphabet = b"ACGT"
     names = ("free_ends", "nw_default", "free_end", "free_start", "linear_gap")
     if case == "ragged_wide":
@@ -268,6 +270,10 @@ def test_wide_pairs_strip_pipeline(engine, big, case):
     elif case == "short_free_ends":
         sa, sb = ragged_batch(7, 300 if big else 24, 200 if big else 60, 200 if big else 60)
         names = ("free_ends", "free_end")
+    elif case == "tall_checkpoints":
+        sa, sb = ragged_batch(11, 24 if big else 3, 2100 if big else 1100, 1500 if big else 200, min_len=70)
+        sa[1], sb[1] = sa[1][:64 * 3], sb[1][:64 * 2]          # one strip, last row ON a checkpoint row
+        names = ("free_ends", "nw_default", "linear_gap")
     else:
         alphabet = b"ARNDCQEGHILKMFPSTWYVBZX"
         sa, sb = ragged_batch(10, 20 if big else 5, 2000 if big else 700, 500 if big else 30, alphabet=alphabet, min_len=1)
@@ -284,11 +290,13 @@ def test_wide_pairs_strip_pipeline(engine, big, case):
         es = orc_batch_nw(o, a, oa, b, ob)
         s = engine.scores()
         assert np.array_equal(s, es), (name, np.nonzero(s != es)[0][:8])
-        engine.submit_packed(NW, MODE_ALIGN, a, oa, b, ob)
-        assert engine.last_kernel == "long_nw_dir+walk", engine.last_kernel
-        assert np.array_equal(engine.scores(), es)
-        for i in range(len(sa)):
-            _check_alignment(engine.alignment(i), NW, o, sa[i], sb[i])
+        for flags, kernel in (("0", "long_nw_ckpt+walk_recompute"), ("1", "long_nw_dir+walk")):
+            monkeypatch.setenv("SEQALIGN_LONG_FLAGS", flags)
+            engine.submit_packed(NW, MODE_ALIGN, a, oa, b, ob)
+            assert engine.last_kernel == kernel, engine.last_kernel
+            assert np.array_equal(engine.scores(), es)
+            for i in range(len(sa)):
+                _check_alignment(engine.alignment(i), NW, o, sa[i], sb[i])
 
 
 def test_empty_inputs(engine):
