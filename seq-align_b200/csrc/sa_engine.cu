@@ -200,6 +200,9 @@ ScoreParams make_params(const scoring_t *s, int is_sw, int ncodes)
   return sp;
 }
 
+/* entries of a plan's profile table: rows = codes of seq_b + the padding row, columns = codes of seq_a + the padding code */
+inline size_t plan_elems(int ncodes) { return (size_t)(ncodes + 1) * (ncodes + 1); }
+
 constexpr size_t COUNTER_BYTES = 8 * (seqalign_batch::MAX_CHUNKS + 1);
 
 struct BatchMeta {
@@ -392,7 +395,7 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
                       int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
                       cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0)
 {
-  const size_t nn = (size_t)sp.ncodes * (sp.ncodes + 1);
+  const size_t nn = plan_elems(sp.ncodes);
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
   int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
   /* one work-queue counter per slot: launches of different slots may run on different streams */
@@ -423,7 +426,7 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
 int upload_plan_tables(seqalign_batch *eng, const std::vector<int8_t> &tab8, const std::vector<int32_t> &tab32,
                        int8_t **d_t8_out, int32_t **d_t32_out, cudaStream_t st)
 {
-  const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+  const size_t nn = plan_elems(eng->ft.ncodes);
   TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
   int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
@@ -480,11 +483,10 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   FastPlan plan;
   const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
   /* force modes 2, 4 and 5 keep to the int32 kernels */
-  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb && eng->force_mode != 4 &&
-                       eng->force_mode != 2 && eng->force_mode != 5;
-  if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &plan)) {
+  const bool allow16 = eng->force_mode != 4 && eng->force_mode != 2 && eng->force_mode != 5;
+  if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, allow16, &plan)) {
     if(eng->force_mode == 2 && plan.track == TRACK_TREE) { plan.track = TRACK_COLUMN; plan.name = "fast_sw_score_endcol"; }
-    const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+    const size_t nn = plan_elems(eng->ft.ncodes);
     TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
     TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
     int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
@@ -558,7 +560,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   int8_t *d_t8 = nullptr;
   int32_t *d_t32 = nullptr;
   if(fast_dir) {
-    const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+    const size_t nn = plan_elems(eng->ft.ncodes);
     TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
     d_t8 = (int8_t *)eng->d_tab8.p;
     d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
@@ -766,7 +768,7 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   plan.track = TRACK_NONE;
   const int maxh = eng->hit_max;
   eng->hit_max_used = maxh;
-  const size_t nn = (size_t)eng->ft.ncodes * (eng->ft.ncodes + 1);
+  const size_t nn = plan_elems(eng->ft.ncodes);
   TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
   int32_t *d_t32 = (int32_t *)(d_t8 + ((nn + 15) & ~(size_t)15));
@@ -1465,11 +1467,10 @@ static bool speculation_held(seqalign_batch *eng, int algo, bool want_ends, cons
   for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
   for(int i = 0; i < 8; i++) subset = subset && (pres[i] & ~eng->tables_pres[i]) == 0;
   FastPlan now;
-  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
   const FastPlan &old = eng->spec.plan;
   /* (a larger shape than needed, or int32 where 16 bits would do, is still exact) */
   return subset && bm.max_lb <= eng->spec.max_lb &&
-         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, uniform, &now) &&
+         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, true, &now) &&
          now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) &&
          (old.track != TRACK_TREE || bm.max_lb <= 2047);
 }

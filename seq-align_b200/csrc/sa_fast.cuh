@@ -601,16 +601,16 @@ fast16_kernel(const FastArgs A)
   uint64_t *s_bar = (uint64_t *)dsm;
   uint8_t *s_lut = dsm + 64;
   int8_t *s_tab8 = (int8_t *)(dsm + 64 + 256);
-  const int tab_bytes = (n * tw + 15) & ~15;
-  const int warp_bytes = 2 * n * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
+  const int tab_bytes = (tw * tw + 15) & ~15;              /* n+1 rows: the last one is the padding row */
+  const int warp_bytes = 2 * tw * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
   unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
-  unsigned char *s_prof = wbase;                           /* [half][code][PSTRIDE] */
-  unsigned char *s_a = wbase + 2 * n * PSTRIDE;            /* [stage][pair][a_stage] */
+  unsigned char *s_prof = wbase;                           /* [half][code 0..n][PSTRIDE] */
+  unsigned char *s_a = wbase + 2 * tw * PSTRIDE;           /* [stage][pair][a_stage] */
   unsigned char *s_b = s_a + 2 * NP * A.a_stage;
   uint64_t *bar = s_bar + wib * 2;
 
   for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
-  for(int i = threadIdx.x; i < n * tw; i += blockDim.x) s_tab8[i] = A.tab8[i];
+  for(int i = threadIdx.x; i < tw * tw; i += blockDim.x) s_tab8[i] = A.tab8[i];
   if(lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   mbar_fence_init();
   __syncthreads();
@@ -667,52 +667,57 @@ fast16_kernel(const FastArgs A)
     const int64_t tn = next_set();
     if(tn < nsets) issue(tn, stage ^ 1);
 
-    /* this group's couple: pair plo in the low halves, phi in the high halves */
+    /* this group's couple: pair plo in the low halves, phi in the high halves.  The two pairs
+     * may differ in shape: columns past a pair's len_a and rows past its len_b see the padding
+     * code n, which scores strictly negative against everything -- with open, ext <= 0 no such
+     * cell can reach the pair's best real score (M there is below some earlier H), so neither
+     * the running maximum nor the end-cell key needs a mask. */
     const int64_t plo = t * NP + 2 * grp, phi = plo + 1;
     const bool have_lo = plo < A.npairs, have_hi = phi < A.npairs;
-    int la = 0, lb = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
+    int la_lo = 0, lb_lo = 0, la_hi = 0, lb_hi = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
     if(have_lo) {
       const int64_t oa = A.off_a[plo], ob = A.off_b[plo];
-      la = (int)(A.off_a[plo + 1] - oa); lb = (int)(A.off_b[plo + 1] - ob);   /* uniform batch: same for phi */
+      la_lo = (int)(A.off_a[plo + 1] - oa); lb_lo = (int)(A.off_b[plo + 1] - ob);
       sha_lo = (int)(oa & 15); shb_lo = (int)(ob & 15);
+      /* speculative launches only: a pair the plan did not foresee becomes an empty one (as in issue()) */
+      if(la_lo > G * K || lb_lo > A.max_lb) { la_lo = 0; lb_lo = 0; }
     }
     if(have_hi) {
-      /* speculative launches only: shapes the plan did not foresee become empty pairs */
-      const int la_hi = (int)(A.off_a[phi + 1] - A.off_a[phi]), lb_hi = (int)(A.off_b[phi + 1] - A.off_b[phi]);
-      if(la_hi != la || lb_hi != lb) { la = 0; lb = 0; }
+      const int64_t oa = A.off_a[phi], ob = A.off_b[phi];
+      la_hi = (int)(A.off_a[phi + 1] - oa); lb_hi = (int)(A.off_b[phi + 1] - ob);
+      sha_hi = (int)(oa & 15); shb_hi = (int)(ob & 15);
+      if(la_hi > G * K || lb_hi > A.max_lb) { la_hi = 0; lb_hi = 0; }
     }
-    if(la > G * K || lb > A.max_lb) { la = 0; lb = 0; }
-    if(have_hi) { sha_hi = (int)(A.off_a[phi] & 15); shb_hi = (int)(A.off_b[phi] & 15); }
+    const int lb = imax(lb_lo, lb_hi);
     mbar_wait(&bar[stage], stage ? phase1 : phase0);
     if(stage) phase1 ^= 1; else phase0 ^= 1;
 
-    const int slot_lo = stage * NP + 2 * grp, slot_hi = have_hi ? slot_lo + 1 : slot_lo;
+    const int slot_lo = stage * NP + 2 * grp, slot_hi = slot_lo + 1;
     unsigned char *ra_lo = s_a + slot_lo * A.a_stage + sha_lo;
     unsigned char *rb_lo = s_b + slot_lo * A.b_stage + shb_lo;
-    unsigned char *ra_hi = s_a + slot_hi * A.a_stage + (have_hi ? sha_hi : sha_lo);
-    unsigned char *rb_hi = s_b + slot_hi * A.b_stage + (have_hi ? shb_hi : shb_lo);
+    unsigned char *ra_hi = s_a + slot_hi * A.a_stage + sha_hi;
+    unsigned char *rb_hi = s_b + slot_hi * A.b_stage + shb_hi;
 
-    /* seq_b of both pairs: raw bytes -> codes, in place (a missing high pair aliases the low one) */
+    /* seq_b of both pairs: raw bytes -> codes, in place; rows past the end of a pair get the padding code */
     for(int i = lig; i < lb; i += G) {
-      const unsigned char c = s_lut[rb_lo[i]];
-      const unsigned char d = have_hi ? s_lut[rb_hi[i]] : c;
-      rb_lo[i] = c;
-      if(have_hi) rb_hi[i] = d;
+      rb_lo[i] = i < lb_lo ? s_lut[rb_lo[i]] : (unsigned char)n;
+      rb_hi[i] = i < lb_hi ? s_lut[rb_hi[i]] : (unsigned char)n;
     }
     __syncwarp();
-    const unsigned char *cb_hi = have_hi ? rb_hi : rb_lo;
+    const unsigned char *cb_hi = rb_hi;
 
-    /* query profiles of my K columns, one per half */
+    /* query profiles of my K columns, one per half; row n is the padding row */
     const int xf = lig * K + 1;
 #pragma unroll
     for(int half = 0; half < 2; half++) {
       const unsigned char *ra = half ? ra_hi : ra_lo;   /* seq_a stays raw in shared memory */
+      const int la = half ? la_hi : la_lo;
       int acode[K];
 #pragma unroll
       for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : n;
-      for(int c = 0; c < n; c++) {
+      for(int c = 0; c <= n; c++) {
         const int8_t *trow = s_tab8 + c * tw;
-        unsigned *dst = (unsigned *)(s_prof + (half * n + c) * PSTRIDE) + lane * KW;
+        unsigned *dst = (unsigned *)(s_prof + (half * (n + 1) + c) * PSTRIDE) + lane * KW;
 #pragma unroll
         for(int w = 0; w < KW; w++) {
           unsigned word = 0;
@@ -740,7 +745,7 @@ fast16_kernel(const FastArgs A)
     for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
     const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
     const unsigned prow_lo = smem_addr(s_prof, dsm) + (unsigned)lane * (KW * 4);
-    const unsigned prow_hi = prow_lo + (unsigned)n * PSTRIDE;
+    const unsigned prow_hi = prow_lo + (unsigned)(n + 1) * PSTRIDE;
     /* Everything of the row step that is not the recurrence stays off the ALU
      * pipe (it is the saturated one): the column-0 constants of a pair's first
      * lane come from multiply-adds with per-lane constants instead of selects,
@@ -876,9 +881,9 @@ inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage
 }
 
 /* can the fast kernel take this batch?  fills the plan if so.
- * want_ends: the caller needs the SW end cell (x_end, y_end) */
+ * want_ends: the caller needs the SW end cell (x_end, y_end); allow_s16: the packed 16-bit kernel may be chosen */
 inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
-                      int64_t max_la, int64_t max_lb, bool want_ends, bool uniform, FastPlan *plan,
+                      int64_t max_la, int64_t max_lb, bool want_ends, bool allow_s16, FastPlan *plan,
                       bool want_dir = false)
 {
   if(sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
@@ -912,7 +917,8 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   const long best_biased = shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open;   /* largest M + B */
   /* ... with the end cell: the 16-bit key is (M + B) x 32 + column, so M + B must stay below 1024 */
   const bool s16_ends = want_ends && best_biased < 1024 && max_lb <= 32767;
-  const bool s16 = sp.is_sw && (!want_ends || s16_ends) && !want_dir && uniform && fits8 &&
+  /* (the packed kernel takes couples of different shapes: padding code for the shorter one) */
+  const bool s16 = sp.is_sw && (!want_ends || s16_ends) && !want_dir && allow_s16 && fits8 &&
                    best_biased < 32000 && sp.open > -16000 && ft.min_sub > -16000;
   int G = 0, K = 0;
   if(s16) {
@@ -945,20 +951,21 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   }
   plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
   if(s16) {
-    const size_t warp_bytes = 2 * (size_t)n * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
-    plan->smem = 64 + 256 + (((size_t)n * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
+    const size_t warp_bytes = 2 * (size_t)(n + 1) * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
+    plan->smem = 64 + 256 + (((size_t)(n + 1) * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
   }
   if(plan->smem > 200 * 1024) return false;
-  /* tables are n rows (code of seq_b) x n+1 columns (code of seq_a, last =
-   * padding).  A padding column scores strictly negative against everything,
-   * so (with open, ext <= 0) no cell in it can reach the best real score and
-   * the kernels need not mask it out of the running maximum. */
+  /* tables are n+1 rows (code of seq_b, last = padding row) x n+1 columns
+   * (code of seq_a, last = padding).  A padding cell scores strictly negative
+   * against everything, so (with open, ext <= 0) no cell in a padding column
+   * or row can reach the best real score and the kernels need not mask it out
+   * of the running maximum. */
   const int tw = n + 1;
-  plan->tab8.assign(((size_t)n * tw + 15) & ~(size_t)15, 0);
-  plan->tab32.assign((size_t)n * tw + 4, 0);
-  for(int cb = 0; cb < n; cb++)
+  plan->tab8.assign(((size_t)tw * tw + 15) & ~(size_t)15, 0);
+  plan->tab32.assign((size_t)tw * tw + 4, 0);
+  for(int cb = 0; cb < tw; cb++)
     for(int ca = 0; ca < tw; ca++) {
-      const int v = (ca < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
+      const int v = (ca < n && cb < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
       plan->tab32[(size_t)cb * tw + ca] = v;
       if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
     }

@@ -653,11 +653,11 @@ inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   plan->smem = long_smem_bytes(K, n, prof32);
   if(plan->smem > 100 * 1024) return false;
   const int tw = n + 1;
-  plan->tab8.assign(((size_t)n * tw + 15) & ~(size_t)15, 0);
-  plan->tab32.assign((size_t)n * tw + 4, 0);
-  for(int cb = 0; cb < n; cb++)
+  plan->tab8.assign(((size_t)tw * tw + 15) & ~(size_t)15, 0);   /* same geometry as the fast plans (padding row unused here) */
+  plan->tab32.assign((size_t)tw * tw + 4, 0);
+  for(int cb = 0; cb < tw; cb++)
     for(int ca = 0; ca < tw; ca++) {
-      const int v = (ca < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
+      const int v = (ca < n && cb < n ? ft.sub[(size_t)cb * n + ca] : padsub) - sp.open;
       plan->tab32[(size_t)cb * tw + ca] = v;
       if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
     }

@@ -172,6 +172,26 @@ def test_uniform_batch_offsets_made_on_device(engine, big):
     assert np.array_equal(s2[:-1], es[:-1])
 
 
+def test_fast16_ragged_batches(engine, big):
+    """the packed 16-bit kernel on NON-uniform batches: couples of pairs of different shapes (the
+    shorter one sees padding columns / rows), empty sequences, odd pair counts; scores and end cells"""
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    for seed, n, lo, hi in ((1, 2001 if big else 9, 100, 150), (2, 777 if big else 7, 0, 60), (3, 301 if big else 5, 140, 300)):
+        sa, sb = ragged_batch(seed, n, hi, hi, min_len=lo)
+        a, oa = seqalign.pack(sa)
+        b, ob = seqalign.pack(sb)
+        es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+        engine.submit_packed(SW, seqalign.MODE_SCORE_ONLY, a, oa, b, ob)
+        assert engine.last_kernel == "fast16_sw_score", engine.last_kernel
+        assert np.array_equal(engine.scores(), es)
+        engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+        assert engine.last_kernel == "fast16_sw_score_end", engine.last_kernel
+        s, x, y = engine.ends()
+        assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
+
+
 def test_uniform_submit_and_result_sink(engine, big):
     """seqalign_batch_submit_uniform (no offset arrays) + seqalign_batch_set_result_sink (scores written
     straight into the caller's array): same numbers as the packed submit, for SW and NW, with and without
