@@ -69,7 +69,8 @@ constexpr int LONG_CK_ROWS = 64;       /* CKPT: a row checkpoint every this many
 __host__ __device__ __forceinline__ int64_t long_edge_ints2(int la, int lb)
 {
   const int64_t nstrips = ((int64_t)la + LONG_STRIP - 1) / LONG_STRIP;
-  return nstrips > 1 ? (nstrips - 1) * ((int64_t)lb + 1) : 0;
+  /* even count: the checkpoints behind the edges are read and written 16 bytes at a time */
+  return nstrips > 1 ? ((nstrips - 1) * ((int64_t)lb + 1) + 1) & ~(int64_t)1 : 0;
 }
 __host__ __device__ __forceinline__ int64_t long_ck_width(int la) { return ((int64_t)la + 15) & ~(int64_t)15; }
 __host__ __device__ __forceinline__ int64_t long_trace_bytes(int la, int lb)

@@ -1,6 +1,8 @@
 /*
- * sa_cli.c -- option parsing, sequence reading and scoring-file loading for
- * the batching command-line tools.  See sa_cli.h for the reference code each
+ * sa_cli.c -- option parsing, sequence reading and scoring-file loading: the
+ * host front-end of the library, used by the batching command-line tools and,
+ * through sa_cmdline.c, by callers of the reference's cmdline_* / align_from_file
+ * / align_scoring_load_* functions.  See sa_cli.h for the reference code each
  * part stands in for; the flag set, defaults and error conditions follow
  * reference src/alignment_cmdline.c:179-485.
  */
@@ -569,6 +571,20 @@ static gzFile open_scoring_file(const char *path)
 void sa_load_matrix(const char *path, scoring_t *sc, int case_sensitive)
 {
   gzFile f = open_scoring_file(path);
+  sa_load_matrix_gz(f, path, sc, case_sensitive);
+  gzclose(f);
+}
+
+void sa_load_pairs(const char *path, scoring_t *sc, int case_sensitive)
+{
+  gzFile f = open_scoring_file(path);
+  sa_load_pairs_gz(f, path, sc, case_sensitive);
+  gzclose(f);
+}
+
+void sa_load_matrix_gz(void *gz, const char *path, scoring_t *sc, int case_sensitive)
+{
+  gzFile f = (gzFile)gz;
   sa_str ln = {0, 0, 0};
   int lines = 0, have_header = 0;
   /* heading row: first line that is not blank and not a comment */
@@ -582,7 +598,7 @@ void sa_load_matrix(const char *path, scoring_t *sc, int case_sensitive)
     lines++;
   }
   if(!have_header && lines == 0) load_error(1, "Empty file", path, 0);
-  if(!have_header) { gzclose(f); sa_str_free(&ln); return; }
+  if(!have_header) { sa_str_free(&ln); return; }
   const char sep = ln.b[0];
   if((sep >= '0' && sep <= '9') || sep == '-')
     load_error(1, "Numbers (0-9) and dashes (-) do not make good separators", path, 0);
@@ -636,12 +652,11 @@ void sa_load_matrix(const char *path, scoring_t *sc, int case_sensitive)
   }
   free(cols);
   sa_str_free(&ln);
-  gzclose(f);
 }
 
-void sa_load_pairs(const char *path, scoring_t *sc, int case_sensitive)
+void sa_load_pairs_gz(void *gz, const char *path, scoring_t *sc, int case_sensitive)
 {
-  gzFile f = open_scoring_file(path);
+  gzFile f = (gzFile)gz;
   sa_str ln = {0, 0, 0};
   int added = 0;
   while(gz_line(f, &ln)) {
@@ -668,6 +683,5 @@ void sa_load_pairs(const char *path, scoring_t *sc, int case_sensitive)
     added++;
   }
   sa_str_free(&ln);
-  gzclose(f);
   if(!added) load_error(0, "No pairs added from file (file empty?)", path, 0);
 }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-enum { SA_TOOL_NW = 0, SA_TOOL_SW = 1 };
+enum { SA_TOOL_NW = 0, SA_TOOL_SW = 1, SA_TOOL_LCS = 2 }; /* LCS: neither the NW-only nor the SW-only flags */
 
 typedef struct {
   const char *path1, *path2; /* path2 == NULL: pairs come from consecutive records of path1 */
@@ -65,6 +65,9 @@ int sa_reader_getc(sa_reader *r);
 /* --substitution_matrix / --substitution_pairs files (gzip ok) */
 void sa_load_matrix(const char *path, scoring_t *scoring, int case_sensitive);
 void sa_load_pairs(const char *path, scoring_t *scoring, int case_sensitive);
+/* the same on a gzFile the caller opened and will close (path: for messages) */
+void sa_load_matrix_gz(void *gz, const char *path, scoring_t *scoring, int case_sensitive);
+void sa_load_pairs_gz(void *gz, const char *path, scoring_t *scoring, int case_sensitive);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,24 @@ def test_c_sizeof_matches(tmp_path):
     assert [int(v) for v in out] == [271428, 9276, 271420, 72, 72, 64]
 
 
+def test_cmdline_struct_layout(tmp_path):
+    """cmdline_t / read_t are read field by field by the reference's tool mains (src/tools/nw_cmdline.c:81-143,
+    sw_cmdline.c:192-217, 316-322).  The numbers are those of the reference's own headers
+    (src/alignment_cmdline.h:24-56, libs/seq_file/seq_file.h:61-73), probed with the same program."""
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "alignment_cmdline.h"\n#include "alignment_scoring_load.h"\n'
+        '#include "alignment_macros.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(cmdline_t), offsetof(cmdline_t, file_paths2),'
+        'offsetof(cmdline_t, min_score), offsetof(cmdline_t, print_seq), offsetof(cmdline_t, zam_stle_output),'
+        'offsetof(cmdline_t, interactive), offsetof(cmdline_t, no_mismatches), offsetof(cmdline_t, seq1), sizeof(read_t),'
+        '(int)ARR_2D_INDEX(7, 3, 2) + MAX4(1, 9, 3, 2) + MIN3(4, 2, 8) + ABSDIFF(3, 10));return 0;}\n')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=gnu99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).split()
+    assert [int(v) for v in out] == [96, 24, 52, 66, 71, 72, 78, 80, 96, 17 + 9 + 2 + 7]
+
+
 def _declared_symbols():
     names = set()
     inc = os.path.join(ROOT, "include")
@@ -65,7 +83,8 @@ def _declared_symbols():
         text = re.sub(r"#[^\n]*(\\\n[^\n]*)*", "", text)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text):
             name = m.group(1)
-            if name.startswith(("seqalign_", "scoring_", "aligner_", "alignment_", "needleman_", "smith_")):
+            if name.startswith(("seqalign_", "scoring_", "aligner_", "alignment_", "needleman_", "smith_", "cmdline_",
+                                "parse_entire_", "align_from_", "align_scoring_")):
                 names.add(name)
         for m in re.finditer(r"\b(align_col_[a-z]+)\b", text):
             names.add(m.group(1))
@@ -75,7 +94,12 @@ def _declared_symbols():
 
 def test_library_exports_every_declared_symbol(real_lib):
     syms = _declared_symbols()
-    assert len(syms) > 40
+    assert len(syms) > 50
+    # the command-line layer of the reference's libalign.a (src/alignment_cmdline.h:58-72, alignment_scoring_load.h:14-18)
+    for name in ("cmdline_new", "cmdline_free", "cmdline_add_files", "cmdline_get_num_of_file_pairs", "cmdline_get_file1",
+                 "cmdline_get_file2", "align_from_file", "parse_entire_int", "parse_entire_uint",
+                 "align_scoring_load_matrix", "align_scoring_load_pairwise"):
+        assert name in syms, name
     missing = [s for s in syms if not hasattr(real_lib, s)]
     assert not missing, missing
 

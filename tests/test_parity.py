@@ -293,6 +293,10 @@ def test_wide_pairs_strip_pipeline(engine, big, case, monkeypatch):
     elif case == "tall_checkpoints":
         sa, sb = ragged_batch(11, 24 if big else 3, 2100 if big else 1100, 1500 if big else 200, min_len=70)
         sa[1], sb[1] = sa[1][:64 * 3], sb[1][:64 * 2]          # one strip, last row ON a checkpoint row
+        # two strips and an even number of rows: an odd count of 8-byte strip-edge records sits in front of
+        # the 16-byte checkpoint records (their base was once misaligned: CUDA error 716 on the device)
+        xa, xb = ragged_batch(12, 1, 600, 128, min_len=128)
+        sa.append((xa[0] * 8)[:600]); sb.append((xb[0] * 2)[:128])
         names = ("free_ends", "nw_default", "linear_gap")
     else:
         alphabet = b"ARNDCQEGHILKMFPSTWYVBZX"
