@@ -484,7 +484,8 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   const bool want_ends = (d_xend != nullptr || d_yend != nullptr) && eng->force_mode != 3 && eng->force_mode != 4;
   /* force modes 2, 4 and 5 keep to the int32 kernels */
   const bool allow16 = eng->force_mode != 4 && eng->force_mode != 2 && eng->force_mode != 5;
-  if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, allow16, &plan)) {
+  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
+  if(eng->force_mode != 1 && fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, allow16, &plan, false, uniform)) {
     if(eng->force_mode == 2 && plan.track == TRACK_TREE) { plan.track = TRACK_COLUMN; plan.name = "fast_sw_score_endcol"; }
     const size_t nn = plan_elems(eng->ft.ncodes);
     TRY(ensure_dev(eng, eng->d_tab8, nn * 5 + 64));
@@ -1467,11 +1468,12 @@ static bool speculation_held(seqalign_batch *eng, int algo, bool want_ends, cons
   for(int i = 0; i < 4; i++) { pres[i] = bm.pres_a[i]; pres[4 + i] = bm.pres_b[i]; }
   for(int i = 0; i < 8; i++) subset = subset && (pres[i] & ~eng->tables_pres[i]) == 0;
   FastPlan now;
+  const bool uniform = bm.min_la == bm.max_la && bm.min_lb == bm.max_lb;
   const FastPlan &old = eng->spec.plan;
   /* (a larger shape than needed, or int32 where 16 bits would do, is still exact) */
   return subset && bm.max_lb <= eng->spec.max_lb &&
-         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, true, &now) &&
-         now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) &&
+         fast_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, want_ends, true, &now, false, uniform) &&
+         now.G * now.K <= old.G * old.K && (now.s16 || !old.s16) && (old.pad_row || !now.pad_row) &&
          (old.track != TRACK_TREE || bm.max_lb <= 2047);
 }
 

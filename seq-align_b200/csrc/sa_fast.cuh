@@ -60,6 +60,7 @@ struct FastArgs {
   int32_t *score, *xend, *yend;
   int max_lb;
   int a_stage, b_stage; /* bytes per pair per stage (multiples of 16) */
+  int pad_row;          /* fast16: 1 = the profile has a padding row (couples of different shapes), 0 = uniform batch */
 };
 
 struct FastPlan {
@@ -76,6 +77,7 @@ struct FastPlan {
   bool hits = false;  /* ... and int16 match scores (multi-hit stage) */
   size_t smem = 0;
   int a_stage = 0, b_stage = 0;
+  bool pad_row = false; /* fast16: profile with a padding row, for batches whose pairs differ in shape */
 };
 
 template <int BYTE>
@@ -601,16 +603,20 @@ fast16_kernel(const FastArgs A)
   uint64_t *s_bar = (uint64_t *)dsm;
   uint8_t *s_lut = dsm + 64;
   int8_t *s_tab8 = (int8_t *)(dsm + 64 + 256);
-  const int tab_bytes = (tw * tw + 15) & ~15;              /* n+1 rows: the last one is the padding row */
-  const int warp_bytes = 2 * tw * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
+  /* profile rows: the n codes of seq_b and, when the batch is not uniform, the padding row (a fifth row
+   * for DNA costs the uniform 150 x 150 batch one resident CTA per SM, 8 % of its speed: measured) */
+  const int nr = n + A.pad_row;
+  const int padc = A.pad_row ? n : 0;                     /* code of the rows past a pair's end */
+  const int tab_bytes = (tw * tw + 15) & ~15;
+  const int warp_bytes = 2 * nr * PSTRIDE + 2 * NP * (A.a_stage + A.b_stage);
   unsigned char *wbase = dsm + 64 + 256 + tab_bytes + wib * warp_bytes;
-  unsigned char *s_prof = wbase;                           /* [half][code 0..n][PSTRIDE] */
-  unsigned char *s_a = wbase + 2 * tw * PSTRIDE;           /* [stage][pair][a_stage] */
+  unsigned char *s_prof = wbase;                           /* [half][code 0..nr-1][PSTRIDE] */
+  unsigned char *s_a = wbase + 2 * nr * PSTRIDE;           /* [stage][pair][a_stage] */
   unsigned char *s_b = s_a + 2 * NP * A.a_stage;
   uint64_t *bar = s_bar + wib * 2;
 
   for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
-  for(int i = threadIdx.x; i < tw * tw; i += blockDim.x) s_tab8[i] = A.tab8[i];
+  for(int i = threadIdx.x; i < nr * tw; i += blockDim.x) s_tab8[i] = A.tab8[i];
   if(lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
   mbar_fence_init();
   __syncthreads();
@@ -671,7 +677,8 @@ fast16_kernel(const FastArgs A)
      * may differ in shape: columns past a pair's len_a and rows past its len_b see the padding
      * code n, which scores strictly negative against everything -- with open, ext <= 0 no such
      * cell can reach the pair's best real score (M there is below some earlier H), so neither
-     * the running maximum nor the end-cell key needs a mask. */
+     * the running maximum nor the end-cell key needs a mask.  (Uniform batches carry no padding
+     * row: only a missing or refused pair has rows past its end there, and its result is not kept.) */
     const int64_t plo = t * NP + 2 * grp, phi = plo + 1;
     const bool have_lo = plo < A.npairs, have_hi = phi < A.npairs;
     int la_lo = 0, lb_lo = 0, la_hi = 0, lb_hi = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
@@ -700,8 +707,8 @@ fast16_kernel(const FastArgs A)
 
     /* seq_b of both pairs: raw bytes -> codes, in place; rows past the end of a pair get the padding code */
     for(int i = lig; i < lb; i += G) {
-      rb_lo[i] = i < lb_lo ? s_lut[rb_lo[i]] : (unsigned char)n;
-      rb_hi[i] = i < lb_hi ? s_lut[rb_hi[i]] : (unsigned char)n;
+      rb_lo[i] = i < lb_lo ? s_lut[rb_lo[i]] : (unsigned char)padc;
+      rb_hi[i] = i < lb_hi ? s_lut[rb_hi[i]] : (unsigned char)padc;
     }
     __syncwarp();
     const unsigned char *cb_hi = rb_hi;
@@ -715,9 +722,9 @@ fast16_kernel(const FastArgs A)
       int acode[K];
 #pragma unroll
       for(int j = 0; j < K; j++) acode[j] = (xf + j <= la) ? s_lut[ra[xf + j - 1]] : n;
-      for(int c = 0; c <= n; c++) {
+      for(int c = 0; c < nr; c++) {
         const int8_t *trow = s_tab8 + c * tw;
-        unsigned *dst = (unsigned *)(s_prof + (half * (n + 1) + c) * PSTRIDE) + lane * KW;
+        unsigned *dst = (unsigned *)(s_prof + (half * nr + c) * PSTRIDE) + lane * KW;
 #pragma unroll
         for(int w = 0; w < KW; w++) {
           unsigned word = 0;
@@ -745,7 +752,7 @@ fast16_kernel(const FastArgs A)
     for(int o = 16; o >= G; o >>= 1) maxlb = imax(maxlb, __shfl_xor_sync(FULL, maxlb, o));
     const int nsteps = maxlb > 0 ? maxlb + G - 1 : 0;
     const unsigned prow_lo = smem_addr(s_prof, dsm) + (unsigned)lane * (KW * 4);
-    const unsigned prow_hi = prow_lo + (unsigned)(n + 1) * PSTRIDE;
+    const unsigned prow_hi = prow_lo + (unsigned)nr * PSTRIDE;
     /* Everything of the row step that is not the recurrence stays off the ALU
      * pipe (it is the saturated one): the column-0 constants of a pair's first
      * lane come from multiply-adds with per-lane constants instead of selects,
@@ -884,7 +891,7 @@ inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage
  * want_ends: the caller needs the SW end cell (x_end, y_end); allow_s16: the packed 16-bit kernel may be chosen */
 inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
                       int64_t max_la, int64_t max_lb, bool want_ends, bool allow_s16, FastPlan *plan,
-                      bool want_dir = false)
+                      bool want_dir = false, bool uniform = false)
 {
   if(sp.no_end || sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
   if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
@@ -951,7 +958,8 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   }
   plan->smem = fast_smem_bytes(G, K, n, prof32, plan->a_stage, plan->b_stage, want_dir);
   if(s16) {
-    const size_t warp_bytes = 2 * (size_t)(n + 1) * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
+    plan->pad_row = !uniform;
+    const size_t warp_bytes = 2 * (size_t)(n + (uniform ? 0 : 1)) * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
     plan->smem = 64 + 256 + (((size_t)(n + 1) * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
   }
   if(plan->smem > 200 * 1024) return false;
@@ -1041,6 +1049,7 @@ int fast_launch_gkp(const FastPlan &plan, const FastArgs &F, int num_sms, int64_
 inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t smem_optin, cudaStream_t st)
 {
   F.a_stage = plan.a_stage; F.b_stage = plan.b_stage;
+  F.pad_row = plan.pad_row ? 1 : 0;
   F.mul_one = 1; F.mul_key = 32;
   if(plan.smem > smem_optin) return -1;
   const int NG = (plan.s16 ? 2 : 1) * (32 / plan.G);

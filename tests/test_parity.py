@@ -735,7 +735,7 @@ def test_full_size_long_pairs_rescore(engine, big):
     engine.submit_packed(NW, MODE_SCORE, a, oa, b, ob)
     s_score = engine.scores().copy()
     engine.submit_packed(NW, MODE_ALIGN, a, oa, b, ob)
-    assert engine.last_kernel.startswith("long_nw_dir")
+    assert engine.last_kernel.startswith("long_nw_ckpt")   # wide pairs trace back through checkpoints
     look = _cached_lookup(sc)
     A, B = a.reshape(n, L), b.reshape(n, L)
     for i in range(n):
