@@ -450,3 +450,124 @@ int orc_batch_nw_score(const orc_scoring_t *s, size_t n,
   }
   return 0;
 }
+
+/* =========================================================================
+ * Sequence-file reader (see sa_oracle.h).  A memory buffer stands in for the
+ * reference's gzFile + StreamBuffer pair (libs/seq_file/stream_buffer.h:221-315):
+ * getc / ungetc / readline / chomp below are those of the buffered variants.
+ */
+typedef struct { const char *t; size_t n, pos; } orc_text;
+typedef struct { char *b; size_t len; } orc_buf;   /* caller-sized: never longer than the text */
+
+/* ref: stream_buffer.h:230-238 (getc_buf): the byte as a (signed) char, -1 at the end */
+static int rd_getc(orc_text *s) { return s->pos < s->n ? (int)(signed char)s->t[s->pos++] : -1; }
+/* ref: stream_buffer.h:245-258: the byte goes back in front of the buffer; pushing back the -1 of
+ * the end of input leaves a byte that reads as -1 again, i.e. nothing changes */
+static void rd_ungetc(orc_text *s, int c) { if(c != -1 && s->pos > 0) s->pos--; }
+/* ref: stream_buffer.h:295-315: append up to and including the next '\n'; bytes read */
+static size_t rd_readline(orc_text *s, orc_buf *b)
+{
+  size_t got = 0;
+  while(s->pos < s->n) {
+    const char c = s->t[s->pos++];
+    b->b[b->len++] = c; got++;
+    if(c == '\n') break;
+  }
+  return got;
+}
+/* ref: stream_buffer.h:56-61 */
+static void rd_chomp(orc_buf *b) { while(b->len && (b->b[b->len - 1] == '\n' || b->b[b->len - 1] == '\r')) b->len--; }
+
+/* ref: seq_file.h:245-272 */
+static int rd_fastq(orc_text *s, orc_buf *name, orc_buf *seq, orc_buf *qual, size_t *name_pos)
+{
+  int c = rd_getc(s);
+  if(c == -1) return 0;
+  *name_pos = s->pos;
+  if(c != '@' || rd_readline(s, name) == 0) return -1;
+  rd_chomp(name);
+  while((c = rd_getc(s)) != '+') {
+    if(c == -1) return -1;
+    if(c != '\r' && c != '\n') {
+      seq->b[seq->len++] = (char)c;
+      if(rd_readline(s, seq) == 0) return -1;
+      rd_chomp(seq);
+    }
+  }
+  while((c = rd_getc(s)) != -1 && c != '\n') {}
+  if(c == -1) return -1;
+  do {
+    if(rd_readline(s, qual) > 0) rd_chomp(qual);
+    else return 1;
+  } while(qual->len < seq->len);
+  while((c = rd_getc(s)) != -1 && c != '@') {}
+  rd_ungetc(s, c);
+  return 1;
+}
+
+/* ref: seq_file.h:274-295 */
+static int rd_fasta(orc_text *s, orc_buf *name, orc_buf *seq, size_t *name_pos)
+{
+  int c = rd_getc(s);
+  if(c == -1) return 0;
+  *name_pos = s->pos;
+  if(c != '>' || rd_readline(s, name) == 0) return -1;
+  rd_chomp(name);
+  while((c = rd_getc(s)) != '>') {
+    if(c == -1) return 1;
+    if(c != '\r' && c != '\n') {
+      seq->b[seq->len++] = (char)c;
+      const long nread = (long)rd_readline(s, seq);
+      rd_chomp(seq);
+      if(nread <= 0) return 1;
+    }
+  }
+  rd_ungetc(s, c);
+  return 1;
+}
+
+/* ref: seq_file.h:298-309; the skipline of :303 is the H6 no-op */
+static int rd_plain(orc_text *s, orc_buf *seq)
+{
+  int c;
+  while((c = rd_getc(s)) != -1 && isspace(c)) {}
+  if(c == -1) return 0;
+  seq->b[seq->len++] = (char)c;
+  rd_readline(s, seq);
+  rd_chomp(seq);
+  return 1;
+}
+
+long orc_read_records(const char *text, size_t n, size_t max_rec, char *seq_out, long long *seq_off,
+                      long long *name_pos, long long *name_len, long long *rec_pos, int *fmt, int *last)
+{
+  orc_text s = {text, n, 0};
+  char *nb = (char *)malloc(n + 2), *qb = (char *)malloc(n + 2);
+  long count = 0;
+  size_t used = 0;
+  int st = 0;
+  seq_off[0] = 0;
+  for(;;) {
+    /* ref: seq_file.h:311-323, run for every record */
+    int c;
+    while((c = rd_getc(&s)) != -1 && isspace(c)) {}
+    if(c == -1) { st = 0; break; }
+    const int f = c == '@' ? 4 : c == '>' ? 2 : 1;
+    rd_ungetc(&s, c);
+    const size_t start = s.pos;
+    orc_buf name = {nb, 0}, qual = {qb, 0}, seq = {seq_out + used, 0};
+    size_t npos = start;
+    st = f == 4 ? rd_fastq(&s, &name, &seq, &qual, &npos) : f == 2 ? rd_fasta(&s, &name, &seq, &npos) : rd_plain(&s, &seq);
+    if(st <= 0) break;
+    if((size_t)count == max_rec) { st = -2; break; }
+    fmt[count] = f;
+    rec_pos[count] = (long long)start;
+    name_pos[count] = (long long)npos;
+    name_len[count] = (long long)name.len;
+    used += seq.len;
+    seq_off[++count] = (long long)used;
+  }
+  free(nb); free(qb);
+  if(last) *last = st;
+  return count;
+}

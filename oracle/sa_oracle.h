@@ -117,6 +117,38 @@ int orc_batch_nw_score(const orc_scoring_t *s, size_t n,
                        const char *seq_b, const long long *off_b,
                        int *score);
 
+/* ---- sequence-file reader ------------------------------
+ * Restates the record grammar of the reference's reader as align_from_file()
+ * drives it (src/alignment_cmdline.c:570-622: seq_open(path) = zlib + 1 MiB
+ * stream buffer, seq_read() per record): libs/seq_file/seq_file.h:311-323
+ * (_read_unknown), :245-272 (FASTQ), :274-295 (FASTA), :298-309 (plain).
+ * NB seq_read() calls sf->readfunc, which is only ever set to the "unknown
+ * format" reader (:97, :434-437; :318-320 re-point origreadfunc, not readfunc),
+ * so EVERY record starts with the white-space skip and the format choice of
+ * :315-320; the format is per record, not per file.
+ *
+ * Parity PINNED against the reference's reader itself: oracle/ref_reader.c
+ * includes the unmodified seq_file.h and dumps its records
+ * (tests/test_reader.py, tests/golden/reader_vectors.json).
+ *
+ * Known hazard, excluded from parity (H6): for a non-newline white-space
+ * character in front of a record the buffered reader calls the UNbuffered
+ * skipline on the file behind its buffer (:426-427 pass _sf_gzskipline to the
+ * buffered _read_unknown) -- a no-op once the whole file is in the buffer
+ * (files <= 1 MiB), a loss of not-yet-buffered bytes otherwise.  Restated here as
+ * the no-op.  Bytes >= 0x80 are outside the contract (0xFF reads as EOF, H4).
+ *
+ * text[0..n) -> records.  Sequence bytes of record i: seq[seq_off[i]..seq_off[i+1]);
+ * its name (header line without '>' / '@', chomped): text[name_pos[i] ..+name_len[i]);
+ * rec_pos[i] = text offset of the record's first character; fmt[i] = 1 plain, 2 FASTA,
+ * 4 FASTQ (seq_format values, seq_file.h:34-39).  Arrays hold max_rec (+1 for seq_off)
+ * entries, seq holds n bytes.  Returns the number of records; *last = what the
+ * final seq_read() returned (0 end of input, -1 syntax error / truncated record). */
+long orc_read_records(const char *text, size_t n, size_t max_rec,
+                      char *seq, long long *seq_off,
+                      long long *name_pos, long long *name_len,
+                      long long *rec_pos, int *fmt, int *last);
+
 #ifdef __cplusplus
 }
 #endif
