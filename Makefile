@@ -28,21 +28,25 @@ $(PKG)/host/%.o: $(PKG)/host/%.c $(wildcard include/*.h $(PKG)/host/*.h)
 $(PKG)/csrc/sa_engine.o: $(PKG)/csrc/sa_engine.cu $(CU_DEPS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIBDIR)/libseqalign_b200.so: $(PKG)/csrc/sa_engine.o $(HOST_OBJS)
+$(PKG)/csrc/sa_decode.o: $(PKG)/csrc/sa_decode.cu $(PKG)/csrc/sa_platform.h include/seqalign_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIBDIR)/libseqalign_b200.so: $(PKG)/csrc/sa_engine.o $(PKG)/csrc/sa_decode.o $(HOST_OBJS)
 	mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lpthread -lz
 
-$(LIBDIR)/libalign.a: $(PKG)/csrc/sa_engine.o $(HOST_OBJS)
+$(LIBDIR)/libalign.a: $(PKG)/csrc/sa_engine.o $(PKG)/csrc/sa_decode.o $(HOST_OBJS)
 	mkdir -p $(LIBDIR)
 	ar rcs $@ $^
 
 EMU = tests/emu
 emu: $(EMU)/libseqalign_emu.so
-$(EMU)/libseqalign_emu.so: $(PKG)/csrc/sa_engine.cu $(CU_DEPS) $(EMU)/cuda_emu.cpp $(EMU)/cuda_emu.h $(HOST_SRCS)
+$(EMU)/libseqalign_emu.so: $(PKG)/csrc/sa_engine.cu $(PKG)/csrc/sa_decode.cu $(CU_DEPS) $(EMU)/cuda_emu.cpp $(EMU)/cuda_emu.h $(HOST_SRCS)
 	$(CXX) -O1 -g -std=c++17 -fPIC -fsanitize=alignment -fsanitize-undefined-trap-on-error -DSA_EMU -Iinclude -I$(PKG)/csrc -I$(EMU) -c -x c++ $(PKG)/csrc/sa_engine.cu -o $(EMU)/sa_engine_emu.o
+	$(CXX) -O1 -g -std=c++17 -fPIC -fsanitize=alignment -fsanitize-undefined-trap-on-error -DSA_EMU -Iinclude -I$(PKG)/csrc -I$(EMU) -c -x c++ $(PKG)/csrc/sa_decode.cu -o $(EMU)/sa_decode_emu.o
 	$(CXX) -O1 -g -std=c++17 -fPIC -I$(EMU) -c $(EMU)/cuda_emu.cpp -o $(EMU)/cuda_emu.o
 	for f in $(HOST_SRCS); do $(CC) $(CFLAGS) -c $$f -o $(EMU)/`basename $$f .c`_emu.o || exit 1; done
-	$(CXX) -shared -o $@ $(EMU)/sa_engine_emu.o $(EMU)/cuda_emu.o $(EMU)/sa_scoring_emu.o $(EMU)/sa_alignment_emu.o $(EMU)/sa_nw_emu.o $(EMU)/sa_sw_emu.o $(EMU)/sa_multi_emu.o $(EMU)/sa_cli_emu.o $(EMU)/sa_cmdline_emu.o -lpthread -lz
+	$(CXX) -shared -o $@ $(EMU)/sa_engine_emu.o $(EMU)/sa_decode_emu.o $(EMU)/cuda_emu.o $(EMU)/sa_scoring_emu.o $(EMU)/sa_alignment_emu.o $(EMU)/sa_nw_emu.o $(EMU)/sa_sw_emu.o $(EMU)/sa_multi_emu.o $(EMU)/sa_cli_emu.o $(EMU)/sa_cmdline_emu.o -lpthread -lz
 
 # batching command-line tools (same flags / stdout as the reference's bin/*)
 TOOLS = bin/needleman_wunsch bin/smith_waterman bin/lcs

@@ -51,6 +51,7 @@ typedef struct seqalign_batch seqalign_batch_t;
 #define SEQALIGN_ERR_TRACEBACK (-3) /* reference alignment.c:328-349           */
 #define SEQALIGN_ERR_ARG (-4)
 #define SEQALIGN_ERR_NOMEM (-5)
+#define SEQALIGN_ERR_IRREGULAR (-6) /* seqalign_reads_decode: text outside the device grammar */
 
 /* number of usable sm_100 devices (0 if none / no driver) */
 int seqalign_device_count(void);
@@ -234,6 +235,69 @@ void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b);
  * (cudaMallocHost / cudaFreeHost).  NULL on failure. */
 void *seqalign_host_alloc(size_t bytes);
 void seqalign_host_free(void *p);
+
+/* ---- sequence-file text -> packed records on the device (csrc/sa_decode.cu) ----
+ * Takes over the reference's record reader for whole chunks of file text:
+ * libs/seq_file/seq_file.h:245-325 (FASTA / FASTQ / one sequence per line,
+ * format chosen from the first non-blank character) as driven by
+ * align_from_file (src/alignment_cmdline.c:578-640).  The text crosses PCIe
+ * once; the decoded sequences stay in HBM in the engine's own batch layout
+ * and seqalign_batch_submit_reads() aligns them in place.  Inflating gzip
+ * stays with the caller (zlib on the host, as in the reference).
+ *
+ * seqalign_reads_decode(r, text, bytes, final, split)
+ *   text   bytes of the file, starting at a record boundary (the start of the
+ *          file, or what seqalign_reads_record_start() said to carry over)
+ *   final  1 = the text ends the input; 0 = more follows, the trailing record
+ *          is held back (it may be incomplete)
+ *   split  0 = every record goes to side 0; 1 = records alternate side 0,
+ *          side 1 (pairs from consecutive records of one file)
+ *   returns SEQALIGN_OK, or SEQALIGN_ERR_IRREGULAR when the text leaves the
+ *   grammar the device takes (wrapped FASTQ, '>' / '@' records inside a
+ *   one-per-line file ...: sa_decode.cu lists it) -- nothing was decoded and
+ *   the input has to be read by the host reader (align_from_file), which
+ *   implements the reference's full grammar.
+ * Accessors after a successful decode:
+ *   _format          SEQALIGN_FMT_* of the chunk (values of seq_format, seq_file.h:34-39)
+ *   _records         complete records
+ *   _count(side)     complete records on a side
+ *   _offsets(side)   host array, offsets of every record of the side in its packed
+ *                    buffer, one closing entry behind the last record
+ *   _record_start(i) offset in `text` where record i starts; i == _records: where the
+ *                    held-back tail starts (carry text[that..] to the next call)
+ *   _name(i)         span of record i's name inside `text` (header line without its
+ *                    '>' / '@', line end dropped)
+ *   _fetch(side,out) packed sequence bytes of a side to host memory
+ *   _device_seq / _device_offsets   the same buffers in HBM (const void *)
+ */
+typedef struct seqalign_reads seqalign_reads_t;
+#define SEQALIGN_FMT_PLAIN 1
+#define SEQALIGN_FMT_FASTA 2
+#define SEQALIGN_FMT_FASTQ 4
+seqalign_reads_t *seqalign_reads_create(int device);
+void seqalign_reads_destroy(seqalign_reads_t *r);
+const char *seqalign_reads_error(const seqalign_reads_t *r);
+int seqalign_reads_decode(seqalign_reads_t *r, const char *text, size_t bytes, int final, int split);
+int seqalign_reads_format(const seqalign_reads_t *r);
+size_t seqalign_reads_records(const seqalign_reads_t *r);
+size_t seqalign_reads_count(const seqalign_reads_t *r, int side);
+const int64_t *seqalign_reads_offsets(const seqalign_reads_t *r, int side);
+size_t seqalign_reads_record_start(const seqalign_reads_t *r, size_t i);
+int seqalign_reads_name(const seqalign_reads_t *r, size_t i, size_t *pos, size_t *len);
+int seqalign_reads_fetch(seqalign_reads_t *r, int side, char *out);
+const void *seqalign_reads_device_seq(const seqalign_reads_t *r, int side);
+const void *seqalign_reads_device_offsets(const seqalign_reads_t *r, int side);
+int seqalign_reads_device(const seqalign_reads_t *r);
+double seqalign_reads_last_ms(const seqalign_reads_t *r);   /* H2D of the text + all decode kernels, CUDA events */
+
+/* Align the first n records of side_a of `ra` against the first n records of
+ * side_b of `rb` (the same object for pairs from one file), reading the
+ * sequences where the decoder left them in HBM.  Same modes, same result
+ * calls as seqalign_batch_submit_packed().  Engine and reads objects must be
+ * on the same device. */
+int seqalign_batch_submit_reads(seqalign_batch_t *eng, int algo, int mode,
+                                const seqalign_reads_t *ra, int side_a,
+                                const seqalign_reads_t *rb, int side_b, size_t n);
 
 /* ---- one batch over several GPUs of one node, one process (host/sa_multi.c) ----
  * The reference's loop over pairs (src/alignment_cmdline.c:611-622) sharded by

@@ -988,8 +988,20 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
 
 /* h_off_a == NULL: every pair is ula x ulb (seqalign_batch_submit_uniform), nothing per pair is read on the host */
 int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, const int64_t *h_off_a,
-                  const char *h_b, const int64_t *h_off_b, size_t n, int64_t ula = -1, int64_t ulb = -1)
+                  const char *h_b, const int64_t *h_off_b, size_t n, int64_t ula = -1, int64_t ulb = -1,
+                  const uint8_t *dev_a = nullptr, const uint8_t *dev_b = nullptr)
 {
+  /* dev_a / dev_b: the sequences already lie in HBM (seqalign_batch_submit_reads); h_a / h_b are null then */
+  const bool resident = dev_a != nullptr;
+  std::vector<char> back_a, back_b;   /* host copies, only made when an unknown character pair must be located */
+  auto host_copy = [&](int64_t total_a, int64_t total_b) -> int {
+    if(!resident || h_a) return 0;
+    back_a.resize((size_t)total_a + 1); back_b.resize((size_t)total_b + 1);
+    if(total_a) CU_TRY(cudaMemcpy(back_a.data(), dev_a, (size_t)total_a, cudaMemcpyDeviceToHost));
+    if(total_b) CU_TRY(cudaMemcpy(back_b.data(), dev_b, (size_t)total_b, cudaMemcpyDeviceToHost));
+    h_a = back_a.data(); h_b = back_b.data();
+    return 0;
+  };
   while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));   /* runs launched ahead finish first */
   eng->err.clear();
   eng->n = 0;
@@ -1032,11 +1044,13 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   auto hoa = [&](size_t i) -> int64_t { return h_off_a ? h_off_a[i] : (int64_t)i * la0; };
   auto hob = [&](size_t i) -> int64_t { return h_off_b ? h_off_b[i] : (int64_t)i * lb0; };
   const int64_t total_a = hoa(n), total_b = hob(n);
-  TRY(ensure_dev(eng, eng->d_seq_a, (size_t)total_a + 32));
-  TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
+  if(!resident) {
+    TRY(ensure_dev(eng, eng->d_seq_a, (size_t)total_a + 32));
+    TRY(ensure_dev(eng, eng->d_seq_b, (size_t)total_b + 32));
+  }
   TRY(ensure_dev(eng, eng->d_off_a, (n + 1) * 8));
   TRY(ensure_dev(eng, eng->d_off_b, (n + 1) * 8));
-  const uint8_t *d_a = (const uint8_t *)eng->d_seq_a.p, *d_b = (const uint8_t *)eng->d_seq_b.p;
+  const uint8_t *d_a = resident ? dev_a : (const uint8_t *)eng->d_seq_a.p, *d_b = resident ? dev_b : (const uint8_t *)eng->d_seq_b.p;
   const int64_t *d_oa = (const int64_t *)eng->d_off_a.p, *d_ob = (const int64_t *)eng->d_off_b.p;
 
   if(mode == SEQALIGN_MODE_SCORE || mode == SEQALIGN_MODE_SCORE_ONLY) {
@@ -1078,8 +1092,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     for(int c = 0; c < nchunks; c++) {
       const int64_t a0 = hoa(bounds[c]), a1 = hoa(bounds[c + 1]);
       const int64_t b0 = hob(bounds[c]), b1 = hob(bounds[c + 1]);
-      if(a1 > a0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_a.p + a0, h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
-      if(b1 > b0) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_b.p + b0, h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+      if(a1 > a0 && !resident) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_a.p + a0, h_a + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, cs));
+      if(b1 > b0 && !resident) CU_TRY(cudaMemcpyAsync((uint8_t *)eng->d_seq_b.p + b0, h_b + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
       CU_TRY(cudaEventRecord(eng->ev_copy[c], cs));
       /* the alphabet/shape scan of a chunk runs on its own stream as soon as
        * the chunk has landed, next to the DP kernel of the chunk before it */
@@ -1101,6 +1115,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       CU_TRY(cudaStreamWaitEvent(st, eng->ev_copy[c], 0));
       TRY(upload_tables(eng, bm, st));
       if(eng->ft.any_unknown) {
+        TRY(host_copy(total_a, total_b));
         if(h_off_a) TRY(check_unknown_pairs(eng, h_a, h_off_a + c0, h_b, h_off_b + c0, m));
         else {
           std::vector<int64_t> ta(m + 1), tb(m + 1);
@@ -1141,8 +1156,8 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
       }
     }
   } else {
-    if(total_a) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, h_a, (size_t)total_a, cudaMemcpyHostToDevice, st));
-    if(total_b) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, h_b, (size_t)total_b, cudaMemcpyHostToDevice, st));
+    if(total_a && !resident) CU_TRY(cudaMemcpyAsync(eng->d_seq_a.p, h_a, (size_t)total_a, cudaMemcpyHostToDevice, st));
+    if(total_b && !resident) CU_TRY(cudaMemcpyAsync(eng->d_seq_b.p, h_b, (size_t)total_b, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(eng->d_off_a.p, h_off_a, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(eng->d_off_b.p, h_off_b, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     DevBatch db;
@@ -1150,7 +1165,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     BatchMeta bm;
     TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a + total_b, st, &bm));
     TRY(upload_tables(eng, bm, st));
-    if(eng->ft.any_unknown) TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n));
+    if(eng->ft.any_unknown) { TRY(host_copy(total_a, total_b)); TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n)); }
     if(mode == SEQALIGN_MODE_MATS) TRY(run_mats(eng, db, bm, h_off_a, h_off_b, st));
     else if(mode == SEQALIGN_MODE_HITS) TRY(run_hits(eng, db, bm, h_off_a, h_off_b, st));
     else TRY(run_align(eng, algo, db, bm, h_off_a, h_off_b, st));
@@ -1387,6 +1402,21 @@ int seqalign_batch_submit(seqalign_batch_t *eng, int algo, int mode,
 }
 
 size_t seqalign_batch_size(const seqalign_batch_t *eng) { return eng ? eng->n : 0; }
+
+int seqalign_batch_submit_reads(seqalign_batch_t *eng, int algo, int mode, const seqalign_reads_t *ra, int side_a,
+                                const seqalign_reads_t *rb, int side_b, size_t n)
+{
+  if(!eng) return SEQALIGN_ERR_ARG;
+  if(!ra || !rb || side_a < 0 || side_a > 1 || side_b < 0 || side_b > 1) return fail(eng, SEQALIGN_ERR_ARG, "bad reads / side");
+  if(seqalign_reads_device(ra) != eng->device || seqalign_reads_device(rb) != eng->device)
+    return fail(eng, SEQALIGN_ERR_ARG, "reads and engine live on different devices");
+  if(n > seqalign_reads_count(ra, side_a) || n > seqalign_reads_count(rb, side_b))
+    return fail(eng, SEQALIGN_ERR_ARG, "more pairs asked for than records decoded");
+  CU_TRY(cudaSetDevice(eng->device));
+  if(n == 0) return submit_common(eng, algo, mode, "", nullptr, "", nullptr, 0, 0, 0);
+  return submit_common(eng, algo, mode, nullptr, seqalign_reads_offsets(ra, side_a), nullptr, seqalign_reads_offsets(rb, side_b), n,
+                       -1, -1, (const uint8_t *)seqalign_reads_device_seq(ra, side_a), (const uint8_t *)seqalign_reads_device_seq(rb, side_b));
+}
 
 int seqalign_batch_set_result_sink(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end)
 {

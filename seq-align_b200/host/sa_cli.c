@@ -338,7 +338,7 @@ void sa_str_free(sa_str *s) { free(s->b); s->b = NULL; s->len = s->cap = 0; }
  *   FASTQ  '@'name  sequence lines up to a line starting with '+', then
  *          quality lines until at least as many characters as bases
  *   plain  one sequence per line; lines starting with white space are skipped
- * The format is decided by the first non-blank character of the input. */
+ * The format is decided by the first non-blank character of each record. */
 
 enum { FMT_UNKNOWN = 0, FMT_FASTA, FMT_FASTQ, FMT_PLAIN };
 
@@ -509,7 +509,11 @@ int sa_reader_next(sa_reader *r, sa_record *rec)
 {
   str_clear(&rec->name);
   str_clear(&rec->seq);
-  if(r->fmt == FMT_UNKNOWN) {
+  /* The format is chosen per RECORD, from its first non-blank character: the reference's seq_read()
+   * goes through the "unknown format" reader every time (seq_file.h:97 calls readfunc, which
+   * :318-320 never re-point), so a line starting with '>' or '@' inside a one-per-line file opens
+   * a FASTA / FASTQ record there. */
+  {
     int c;
     while((c = rd_getc(r)) != -1 && isspace(c)) if(c != '\n') rd_skipline(r);
     if(c == -1) return 0;

@@ -186,6 +186,31 @@ def load():
     L.seqalign_multi_last_kernel_ms.argtypes = [vp]
     L.seqalign_synth_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
                                        ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    # sequence-file text -> records on the device (csrc/sa_decode.cu)
+    L.seqalign_reads_create.restype = vp
+    L.seqalign_reads_create.argtypes = [ctypes.c_int]
+    L.seqalign_reads_destroy.argtypes = [vp]
+    L.seqalign_reads_error.restype = ctypes.c_char_p
+    L.seqalign_reads_error.argtypes = [vp]
+    L.seqalign_reads_decode.argtypes = [vp, vp, sz, ctypes.c_int, ctypes.c_int]
+    L.seqalign_reads_format.argtypes = [vp]
+    L.seqalign_reads_records.restype = sz
+    L.seqalign_reads_records.argtypes = [vp]
+    L.seqalign_reads_count.restype = sz
+    L.seqalign_reads_count.argtypes = [vp, ctypes.c_int]
+    L.seqalign_reads_offsets.restype = ctypes.POINTER(ctypes.c_int64)
+    L.seqalign_reads_offsets.argtypes = [vp, ctypes.c_int]
+    L.seqalign_reads_record_start.restype = sz
+    L.seqalign_reads_record_start.argtypes = [vp, sz]
+    L.seqalign_reads_name.argtypes = [vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+    L.seqalign_reads_fetch.argtypes = [vp, ctypes.c_int, vp]
+    L.seqalign_reads_device_seq.restype = vp
+    L.seqalign_reads_device_seq.argtypes = [vp, ctypes.c_int]
+    L.seqalign_reads_device_offsets.restype = vp
+    L.seqalign_reads_device_offsets.argtypes = [vp, ctypes.c_int]
+    L.seqalign_reads_last_ms.restype = ctypes.c_double
+    L.seqalign_reads_last_ms.argtypes = [vp]
+    L.seqalign_batch_submit_reads.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, sz]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -361,6 +386,11 @@ class BatchAligner:
     def submit_ptrs(self, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n):
         """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         self._check(self._L.seqalign_batch_submit_packed(self._h, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n))
+        return n
+
+    def submit_reads(self, algo, mode, reads_a, side_a, reads_b, side_b, n):
+        """align the first n records of two decoded sides where they lie in HBM (seqalign_batch_submit_reads)"""
+        self._check(self._L.seqalign_batch_submit_reads(self._h, algo, mode, reads_a._h, side_a, reads_b._h, side_b, n))
         return n
 
     def submit_uniform_ptrs(self, algo, mode, ptr_a, len_a, ptr_b, len_b, n):
@@ -651,6 +681,86 @@ class PipelinedAligner:
         self._pool.shutdown(wait=True)
         for e in self._all:
             e.close()
+
+
+ERR_IRREGULAR = -6
+FMT_PLAIN, FMT_FASTA, FMT_FASTQ = 1, 2, 4
+
+
+class Reads:
+    """Records of a chunk of sequence-file text, decoded on the device (seqalign_reads_*, csrc/sa_decode.cu):
+    FASTA / FASTQ / one sequence per line as the reference's reader takes them (libs/seq_file/seq_file.h:245-325).
+    decode() returns False when the text leaves the grammar the device takes (the host reader handles those)."""
+
+    def __init__(self, device=0):
+        self._L = load()
+        self._h = self._L.seqalign_reads_create(device)
+        if not self._h:
+            raise SeqAlignError(-1, "cannot create a reads object on device %d (sm_100 only, no CPU path)" % device)
+        self._text = b""
+
+    def close(self):
+        if self._h:
+            self._L.seqalign_reads_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode(self, text, final=True, split=False):
+        self._text = bytes(text)
+        buf = ctypes.create_string_buffer(self._text, len(self._text) + 1)
+        rc = self._L.seqalign_reads_decode(self._h, buf, len(self._text), int(bool(final)), int(bool(split)))
+        if rc == ERR_IRREGULAR:
+            return False
+        if rc < 0:
+            raise SeqAlignError(rc, self._L.seqalign_reads_error(self._h).decode())
+        return True
+
+    @property
+    def format(self):
+        return self._L.seqalign_reads_format(self._h)
+
+    @property
+    def records(self):
+        return self._L.seqalign_reads_records(self._h)
+
+    @property
+    def last_ms(self):
+        return self._L.seqalign_reads_last_ms(self._h)
+
+    def count(self, side=0):
+        return self._L.seqalign_reads_count(self._h, side)
+
+    def offsets(self, side=0):
+        n = self.count(side)
+        p = self._L.seqalign_reads_offsets(self._h, side)
+        return np.array([p[i] for i in range(n + 1)], dtype=np.int64) if p else np.zeros(1, dtype=np.int64)
+
+    def record_start(self, i):
+        return self._L.seqalign_reads_record_start(self._h, i)
+
+    def name(self, i):
+        pos, ln = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        rc = self._L.seqalign_reads_name(self._h, i, ctypes.byref(pos), ctypes.byref(ln))
+        if rc < 0:
+            raise SeqAlignError(rc, "bad record index")
+        return self._text[pos.value:pos.value + ln.value]
+
+    def sequences(self, side=0):
+        """the side's sequences as a list of bytes (complete records only)"""
+        off = self.offsets(side)
+        total = int(off[-1]) if len(off) else 0
+        # the packed buffer also holds the held-back tail record: fetch copies all of it
+        out = ctypes.create_string_buffer(len(self._text) + 64)
+        rc = self._L.seqalign_reads_fetch(self._h, side, out)
+        if rc < 0:
+            raise SeqAlignError(rc, self._L.seqalign_reads_error(self._h).decode())
+        raw = out.raw[:total]
+        return [raw[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
 def synth_device(device, kind, seed, first_pair, npairs, len_a, len_b, d_seq_a, d_seq_b, stream=0):
