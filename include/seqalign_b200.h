@@ -290,14 +290,15 @@ const void *seqalign_reads_device_offsets(const seqalign_reads_t *r, int side);
 int seqalign_reads_device(const seqalign_reads_t *r);
 double seqalign_reads_last_ms(const seqalign_reads_t *r);   /* H2D of the text + all decode kernels, CUDA events */
 
-/* Align the first n records of side_a of `ra` against the first n records of
- * side_b of `rb` (the same object for pairs from one file), reading the
- * sequences where the decoder left them in HBM.  Same modes, same result
- * calls as seqalign_batch_submit_packed().  Engine and reads objects must be
- * on the same device. */
+/* Align records [first, first + n) of side_a of `ra` against records
+ * [first, first + n) of side_b of `rb` (the same object for pairs from one
+ * file), reading the sequences where the decoder left them in HBM.  Same
+ * modes, same result calls as seqalign_batch_submit_packed() (pair i of the
+ * submit is record first + i).  Engine and reads objects must be on the same
+ * device. */
 int seqalign_batch_submit_reads(seqalign_batch_t *eng, int algo, int mode,
                                 const seqalign_reads_t *ra, int side_a,
-                                const seqalign_reads_t *rb, int side_b, size_t n);
+                                const seqalign_reads_t *rb, int side_b, size_t first, size_t n);
 
 /* ---- one batch over several GPUs of one node, one process (host/sa_multi.c) ----
  * The reference's loop over pairs (src/alignment_cmdline.c:611-622) sharded by

@@ -1004,6 +1004,12 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
   };
   while(eng->pend_count > 0) TRY(seqalign_batch_run_device_wait(eng));   /* runs launched ahead finish first */
   eng->err.clear();
+  {
+    /* an error some earlier runtime call of this thread left behind would otherwise be pinned on the first launch below */
+    const cudaError_t stale = cudaGetLastError();
+    if(stale != cudaSuccess)
+      return fail(eng, SEQALIGN_ERR_CUDA, (std::string("CUDA error pending before this submit: ") + cudaGetErrorString(stale)).c_str());
+  }
   eng->n = 0;
   eng->last_launches = 0;
   eng->last_ms = 0;
@@ -1070,7 +1076,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     /* ~16 MB per chunk: small chunks leave the persistent DP kernel with a
      * fraction of a wave at its tail (measured: 4 x 25k pairs of 150 bp cost
      * 0.79 ms of kernel time, 2 x 50k 0.56 ms, one launch 0.54 ms) */
-    int nchunks = (int)((total_a + total_b) / (16 << 20)) + 1;
+    int nchunks = (int)((total_a - hoa(0) + total_b - hob(0)) / (16 << 20)) + 1;
     if(nchunks > seqalign_batch::MAX_CHUNKS) nchunks = seqalign_batch::MAX_CHUNKS;
     if((size_t)nchunks > n / 2048 + 1) nchunks = (int)(n / 2048 + 1);
     const char *env = getenv("SEQALIGN_CHUNKS");
@@ -1163,7 +1169,7 @@ int submit_common(seqalign_batch *eng, int algo, int mode, const char *h_a, cons
     DevBatch db;
     db.a = d_a; db.b = d_b; db.off_a = d_oa; db.off_b = d_ob; db.n = n;
     BatchMeta bm;
-    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a + total_b, st, &bm));
+    TRY(scan_batch(eng, db.a, db.b, db.off_a, db.off_b, n, total_a - hoa(0) + total_b - hob(0), st, &bm));
     TRY(upload_tables(eng, bm, st));
     if(eng->ft.any_unknown) { TRY(host_copy(total_a, total_b)); TRY(check_unknown_pairs(eng, h_a, h_off_a, h_b, h_off_b, n)); }
     if(mode == SEQALIGN_MODE_MATS) TRY(run_mats(eng, db, bm, h_off_a, h_off_b, st));
@@ -1404,18 +1410,20 @@ int seqalign_batch_submit(seqalign_batch_t *eng, int algo, int mode,
 size_t seqalign_batch_size(const seqalign_batch_t *eng) { return eng ? eng->n : 0; }
 
 int seqalign_batch_submit_reads(seqalign_batch_t *eng, int algo, int mode, const seqalign_reads_t *ra, int side_a,
-                                const seqalign_reads_t *rb, int side_b, size_t n)
+                                const seqalign_reads_t *rb, int side_b, size_t first, size_t n)
 {
   if(!eng) return SEQALIGN_ERR_ARG;
   if(!ra || !rb || side_a < 0 || side_a > 1 || side_b < 0 || side_b > 1) return fail(eng, SEQALIGN_ERR_ARG, "bad reads / side");
   if(seqalign_reads_device(ra) != eng->device || seqalign_reads_device(rb) != eng->device)
     return fail(eng, SEQALIGN_ERR_ARG, "reads and engine live on different devices");
-  if(n > seqalign_reads_count(ra, side_a) || n > seqalign_reads_count(rb, side_b))
+  if(first + n > seqalign_reads_count(ra, side_a) || first + n > seqalign_reads_count(rb, side_b))
     return fail(eng, SEQALIGN_ERR_ARG, "more pairs asked for than records decoded");
   CU_TRY(cudaSetDevice(eng->device));
   if(n == 0) return submit_common(eng, algo, mode, "", nullptr, "", nullptr, 0, 0, 0);
-  return submit_common(eng, algo, mode, nullptr, seqalign_reads_offsets(ra, side_a), nullptr, seqalign_reads_offsets(rb, side_b), n,
-                       -1, -1, (const uint8_t *)seqalign_reads_device_seq(ra, side_a), (const uint8_t *)seqalign_reads_device_seq(rb, side_b));
+  /* offsets stay absolute (relative to the start of the side's buffer): the kernels add them to the base pointer */
+  return submit_common(eng, algo, mode, nullptr, seqalign_reads_offsets(ra, side_a) + first, nullptr,
+                       seqalign_reads_offsets(rb, side_b) + first, n, -1, -1,
+                       (const uint8_t *)seqalign_reads_device_seq(ra, side_a), (const uint8_t *)seqalign_reads_device_seq(rb, side_b));
 }
 
 int seqalign_batch_set_result_sink(seqalign_batch_t *eng, int32_t *score, int32_t *x_end, int32_t *y_end)

@@ -210,7 +210,7 @@ def load():
     L.seqalign_reads_device_offsets.argtypes = [vp, ctypes.c_int]
     L.seqalign_reads_last_ms.restype = ctypes.c_double
     L.seqalign_reads_last_ms.argtypes = [vp]
-    L.seqalign_batch_submit_reads.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, sz]
+    L.seqalign_batch_submit_reads.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, sz, sz]
     # reference C API
     L.scoring_init.argtypes = [vp] + [ctypes.c_int] * 4 + [ctypes.c_bool] * 6
     L.scoring_add_wildcard.argtypes = [vp, ctypes.c_char, ctypes.c_int]
@@ -388,9 +388,9 @@ class BatchAligner:
         self._check(self._L.seqalign_batch_submit_packed(self._h, algo, mode, ptr_a, off_a_ptr, ptr_b, off_b_ptr, n))
         return n
 
-    def submit_reads(self, algo, mode, reads_a, side_a, reads_b, side_b, n):
-        """align the first n records of two decoded sides where they lie in HBM (seqalign_batch_submit_reads)"""
-        self._check(self._L.seqalign_batch_submit_reads(self._h, algo, mode, reads_a._h, side_a, reads_b._h, side_b, n))
+    def submit_reads(self, algo, mode, reads_a, side_a, reads_b, side_b, n, first=0):
+        """align records [first, first + n) of two decoded sides where they lie in HBM (seqalign_batch_submit_reads)"""
+        self._check(self._L.seqalign_batch_submit_reads(self._h, algo, mode, reads_a._h, side_a, reads_b._h, side_b, first, n))
         return n
 
     def submit_uniform_ptrs(self, algo, mode, ptr_a, len_a, ptr_b, len_b, n):

@@ -97,10 +97,13 @@ static void print_batch_matrices(size_t i, const char *a, size_t la, const char 
   free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores);
 }
 
-static void align_batch(const char *const *a, const size_t *la, const char *const *b, const size_t *lb,
-                        char *const *name_a, char *const *name_b, size_t n)
+static void align_batch(sa_pairs *p)
 {
+  const size_t n = p->n;
+  const size_t *la = p->la, *lb = p->lb;
+  char *const *name_a = p->name_a, *const *name_b = p->name_b;
   if(n == 0) return;
+  sa_engine_wait();
   int rc = SEQALIGN_ERR_ARG;
   double t0 = sa_now();
   /* matrices that nobody prints (--zam) are not made; several pairs with --printmatrices take the
@@ -112,14 +115,15 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
       mats_eng = seqalign_batch_create(0);
       if(mats_eng) seqalign_batch_set_scoring(mats_eng, &scoring);
     }
-    with_mats = mats_eng && seqalign_batch_submit(mats_eng, SEQALIGN_NW, SEQALIGN_MODE_MATS, a, la, b, lb, n) == SEQALIGN_OK;
+    with_mats = mats_eng && sa_submit(mats_eng, SEQALIGN_NW, SEQALIGN_MODE_MATS, p) == SEQALIGN_OK;
   }
-  if(!opt.print_matrices || with_mats) rc = seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+  if(!opt.print_matrices || with_mats) rc = sa_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, p);
   sa_t_align += sa_now() - t0;
   if(rc == SEQALIGN_OK) {
     t0 = sa_now();
+    if(with_mats) sa_pairs_host(p);   /* the matrix printer shows the sequences */
     for(size_t i = 0; i < n; i++) {
-      if(with_mats) print_batch_matrices(i, a[i], la[i], b[i], lb[i]);
+      if(with_mats) print_batch_matrices(i, p->a[i], la[i], p->b[i], lb[i]);
       alignment_ensure_capacity(result, la[i] + lb[i]);
       rc = seqalign_batch_alignment(eng, i, result);
       if(rc < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
@@ -134,13 +138,14 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
   }
   /* pair by pair: prints everything up to the offending pair, then the
    * reference's "Unknown character pair" message and exit(EXIT_FAILURE) */
-  for(size_t i = 0; i < n; i++) align_single(a[i], b[i], name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
+  sa_pairs_host(p);
+  for(size_t i = 0; i < n; i++) align_single(p->a[i], p->b[i], name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
 }
 
 static void flush_pairs(sa_pairs *p, sa_reader *r)
 {
   (void)r;
-  align_batch((const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->name_a, p->name_b, p->n);
+  align_batch(p);
   fflush(stdout);
   sa_pairs_clear(p);
 }
@@ -153,31 +158,32 @@ int main(int argc, char **argv)
   if(!opt.print_matrices) setenv("SEQALIGN_SKIP_MATRICES", "1", 1);
 
   sa_t_start = sa_now();
-  eng = seqalign_batch_create(0);
-  sa_t_init = sa_now() - sa_t_start;
-  if(!eng) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); return EXIT_FAILURE; }
-  if(seqalign_batch_set_scoring(eng, &scoring) != SEQALIGN_OK) {
-    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
-    return EXIT_FAILURE;
-  }
+  sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
   nw = needleman_wunsch_new();
   result = alignment_create(256);
 
   if(opt.seq1) {
-    const size_t la = strlen(opt.seq1), lb = strlen(opt.seq2);
-    align_batch(&opt.seq1, &la, &opt.seq2, &lb, NULL, NULL, 1);
+    sa_pairs one;
+    memset(&one, 0, sizeof(one));
+    sa_pairs_reserve(&one, 1);
+    one.a[0] = sa_dup(opt.seq1, strlen(opt.seq1)); one.la[0] = strlen(opt.seq1);
+    one.b[0] = sa_dup(opt.seq2, strlen(opt.seq2)); one.lb[0] = strlen(opt.seq2);
+    one.n = 1;
+    align_batch(&one);
     fflush(stdout);
+    sa_pairs_free(&one);
   }
   sa_pairs pairs;
   memset(&pairs, 0, sizeof(pairs));
   for(size_t i = 0; i < opt.nfiles; i++) {
     const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
     if(f1 && *f1 == '\0' && !f2) f1 = "-";
-    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, SA_BATCH_MAX_PAIRS, &pairs, flush_pairs);
+    sa_read_input(f1, f2, opt.interactive, 0, SA_BATCH_MAX_PAIRS, opt.print_fasta, &pairs, flush_pairs);
   }
   sa_pairs_free(&pairs);
   needleman_wunsch_free(nw);
   alignment_free(result);
+  sa_engine_wait();
   seqalign_batch_destroy(eng);
   if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);

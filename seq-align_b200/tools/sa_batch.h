@@ -11,7 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <pthread.h>
+#include <zlib.h>
 #include "sa_cli.h"
+#include "seqalign_b200.h"
 
 /* SEQALIGN_CLI_TIMING=1: seconds spent reading, aligning and printing, on stderr at exit */
 static double sa_t_read = 0, sa_t_align = 0, sa_t_print = 0, sa_t_init = 0, sa_t_start = 0;
@@ -29,11 +32,58 @@ static inline void sa_timing_report(void)
             sa_t_align, sa_t_print, sa_now() - sa_t_start);
 }
 
+/* The engine (CUDA context, streams) is created on a helper thread while the main thread parses
+ * options, opens the first input and inflates its first chunk: context creation is the largest fixed
+ * cost of a run (0.4 s and more).  sa_engine_wait() joins it before the first use. */
+static pthread_t sa_eng_thread;
+static int sa_eng_pending = 0;
+static seqalign_batch_t **sa_eng_slot = NULL;
+static const scoring_t *sa_eng_scoring = NULL;
+static void *sa_engine_main(void *arg)
+{
+  (void)arg;
+  const double t0 = sa_now();
+  *sa_eng_slot = seqalign_batch_create(0);
+  if(*sa_eng_slot && seqalign_batch_set_scoring(*sa_eng_slot, sa_eng_scoring) != SEQALIGN_OK) {
+    fprintf(stderr, "Error: %s\n", seqalign_batch_error(*sa_eng_slot));
+    exit(EXIT_FAILURE);
+  }
+  sa_t_init = sa_now() - t0;
+  return NULL;
+}
+static inline void sa_engine_start(seqalign_batch_t **slot, const scoring_t *scoring)
+{
+  sa_eng_slot = slot; sa_eng_scoring = scoring;
+  if(pthread_create(&sa_eng_thread, NULL, sa_engine_main, NULL) == 0) sa_eng_pending = 1;
+  else sa_engine_main(NULL);
+}
+static inline void sa_engine_wait(void)
+{
+  if(sa_eng_pending) { pthread_join(sa_eng_thread, NULL); sa_eng_pending = 0; }
+  if(sa_eng_slot && !*sa_eng_slot) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); exit(EXIT_FAILURE); }
+}
+
 typedef struct {
   char **a, **b, **name_a, **name_b; /* owned copies; names NULL when the record had none */
   size_t *la, *lb;
   size_t n, cap, bytes;
+  /* a batch decoded on the device (sa_for_each_batch_dev): the sequences lie in HBM as records
+   * [dev_first, dev_first + n) of two decoded sides; a[] / b[] stay NULL until sa_pairs_host() */
+  const seqalign_reads_t *dev_a, *dev_b;
+  int dev_side_a, dev_side_b;
+  size_t dev_first;
+  struct sa_dev_chunk *chunk;
 } sa_pairs;
+
+/* host copies of a decoded chunk's packed sides, fetched at most once per chunk and only when a
+ * tool has to print or re-align the sequences themselves */
+struct sa_dev_chunk {
+  seqalign_reads_t *ra, *rb;
+  char *host_a, *host_b;
+  size_t cap_a, cap_b;
+  size_t text_a, text_b;   /* bytes of text the sides were decoded from: no side is longer */
+  int have_a, have_b;
+};
 
 static inline char *sa_dup(const char *s, size_t n)
 {
@@ -44,17 +94,11 @@ static inline char *sa_dup(const char *s, size_t n)
   return d;
 }
 
+static inline void sa_pairs_reserve(sa_pairs *p, size_t n);
+
 static inline void sa_pairs_add(sa_pairs *p, const sa_record *r1, const sa_record *r2)
 {
-  if(p->n == p->cap) {
-    p->cap = p->cap ? 2 * p->cap : 1024;
-    p->a = realloc(p->a, p->cap * sizeof(char *)); p->b = realloc(p->b, p->cap * sizeof(char *));
-    p->name_a = realloc(p->name_a, p->cap * sizeof(char *)); p->name_b = realloc(p->name_b, p->cap * sizeof(char *));
-    p->la = realloc(p->la, p->cap * sizeof(size_t)); p->lb = realloc(p->lb, p->cap * sizeof(size_t));
-    if(!p->a || !p->b || !p->name_a || !p->name_b || !p->la || !p->lb) {
-      fprintf(stderr, "%s:%i: Out of memory\n", __FILE__, __LINE__); exit(EXIT_FAILURE);
-    }
-  }
+  sa_pairs_reserve(p, p->n + 1);
   const size_t i = p->n++;
   p->a[i] = sa_dup(r1->seq.b, r1->seq.len); p->la[i] = r1->seq.len;
   p->b[i] = sa_dup(r2->seq.b, r2->seq.len); p->lb[i] = r2->seq.len;
@@ -67,6 +111,58 @@ static inline void sa_pairs_clear(sa_pairs *p)
 {
   for(size_t i = 0; i < p->n; i++) { free(p->a[i]); free(p->b[i]); free(p->name_a[i]); free(p->name_b[i]); }
   p->n = 0; p->bytes = 0;
+  p->dev_a = p->dev_b = NULL; p->chunk = NULL;
+}
+
+static inline void sa_pairs_reserve(sa_pairs *p, size_t n)
+{
+  if(n <= p->cap) return;
+  size_t cap = p->cap ? p->cap : 1024;
+  while(cap < n) cap *= 2;
+  const size_t old = p->cap;
+  p->cap = cap;
+  p->a = realloc(p->a, p->cap * sizeof(char *)); p->b = realloc(p->b, p->cap * sizeof(char *));
+  p->name_a = realloc(p->name_a, p->cap * sizeof(char *)); p->name_b = realloc(p->name_b, p->cap * sizeof(char *));
+  p->la = realloc(p->la, p->cap * sizeof(size_t)); p->lb = realloc(p->lb, p->cap * sizeof(size_t));
+  if(!p->a || !p->b || !p->name_a || !p->name_b || !p->la || !p->lb) {
+    fprintf(stderr, "%s:%i: Out of memory\n", __FILE__, __LINE__); exit(EXIT_FAILURE);
+  }
+  for(size_t i = old; i < cap; i++) p->a[i] = p->b[i] = p->name_a[i] = p->name_b[i] = NULL;
+}
+
+/* one submit for both kinds of batch */
+static inline int sa_submit(seqalign_batch_t *eng, int algo, int mode, const sa_pairs *p)
+{
+  if(p->dev_a)
+    return seqalign_batch_submit_reads(eng, algo, mode, p->dev_a, p->dev_side_a, p->dev_b, p->dev_side_b, p->dev_first, p->n);
+  return seqalign_batch_submit(eng, algo, mode, (const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->n);
+}
+
+/* NUL-terminated host copies of a device-decoded batch's sequences (no-op for host batches) */
+static inline void sa_pairs_host(sa_pairs *p)
+{
+  if(!p->dev_a || p->n == 0 || p->a[0]) return;
+  struct sa_dev_chunk *c = p->chunk;
+  for(int side = 0; side < 2; side++) {
+    int *have = side ? &c->have_b : &c->have_a;
+    char **host = side ? &c->host_b : &c->host_a;
+    size_t *cap = side ? &c->cap_b : &c->cap_a;
+    const seqalign_reads_t *r = side ? p->dev_b : p->dev_a;
+    const int rs = side ? p->dev_side_b : p->dev_side_a;
+    if(!*have) {
+      const size_t need = (side ? c->text_b : c->text_a) + 64;
+      if(*cap < need) { free(*host); *host = malloc(need); *cap = need; }
+      if(!*host || seqalign_reads_fetch((seqalign_reads_t *)r, rs, *host) != SEQALIGN_OK) {
+        fprintf(stderr, "Error: %s\n", seqalign_reads_error(r)); exit(EXIT_FAILURE);
+      }
+      *have = 1;
+    }
+    const int64_t *off = seqalign_reads_offsets(r, rs) + p->dev_first;
+    for(size_t i = 0; i < p->n; i++) {
+      char *d = sa_dup(*host + off[i], (size_t)(off[i + 1] - off[i]));
+      if(side) p->b[i] = d; else p->a[i] = d;
+    }
+  }
 }
 
 static inline void sa_pairs_free(sa_pairs *p)
@@ -85,8 +181,9 @@ static inline void sa_pairs_free(sa_pairs *p)
  * interactive: flush after every pair (request/response protocol of the perl
  * wrappers, reference perl/NeedlemanWunsch.pm:182-210).  Messages as
  * reference src/alignment_cmdline.c:584-632. */
-static inline void sa_for_each_batch(const char *path1, const char *path2, int interactive, int buffered,
-                                     size_t max_pairs, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
+static inline void sa_for_each_batch_from(const char *path1, const char *path2, int interactive, int buffered,
+                                          size_t max_pairs, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *),
+                                          unsigned long skip)
 {
   sa_reader *r1 = sa_reader_open(path1, buffered), *r2 = r1;
   if(!r1) { fprintf(stderr, "Alignment Error: couldn't open file %s\n", path1); fflush(stderr); return; }
@@ -99,6 +196,10 @@ static inline void sa_for_each_batch(const char *path1, const char *path2, int i
   unsigned long count = 0;
   double t0 = sa_now();
   for(; sa_reader_next(r1, &rec1) > 0; count++) {
+    if(count < skip) {   /* pairs the device path has already handled */
+      if(sa_reader_next(r2, &rec2) <= 0) break;
+      continue;
+    }
     if(sa_reader_next(r2, &rec2) <= 0) {
       flush(pairs, r1);
       fprintf(stderr, "Alignment Error: Odd number of sequences - I read in pairs!\n"); fflush(stderr);
@@ -117,6 +218,177 @@ static inline void sa_for_each_batch(const char *path1, const char *path2, int i
   sa_reader_close(r1);
   if(path2) sa_reader_close(r2);
   sa_str_free(&rec1.name); sa_str_free(&rec1.seq); sa_str_free(&rec2.name); sa_str_free(&rec2.seq);
+}
+
+static inline void sa_for_each_batch(const char *path1, const char *path2, int interactive, int buffered,
+                                     size_t max_pairs, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
+{
+  sa_for_each_batch_from(path1, path2, interactive, buffered, max_pairs, pairs, flush, 0);
+}
+
+/* ---- the same loop with the records decoded on the device ---------------------------------
+ * (SURVEY.md 8 f-4).  The file is read (and inflated, zlib) in chunks of text into pinned memory;
+ * each chunk goes to the GPU once, seqalign_reads_decode() turns it into packed sides + offsets in
+ * HBM, and flush() aligns sub-batches of it in place.  The tail the decoder holds back (a record
+ * that may continue in the next chunk) is carried to the front of the buffer.
+ * Returns 0 when the input was handled to its end; 1 when the decoder declined a chunk (text
+ * outside its grammar) after *done pairs had been flushed: the caller goes on with the host reader,
+ * skipping that many pairs; -1 when the path could not be used at all (nothing read, nothing printed). */
+typedef struct { gzFile gz; char *buf; size_t len, cap; int eof; seqalign_reads_t *reads; } sa_dev_file;
+
+static inline void sa_dev_fill(sa_dev_file *f)
+{
+  while(!f->eof && f->len < f->cap) {
+    const size_t room = f->cap - f->len;
+    const int n = gzread(f->gz, f->buf + f->len, room > ((size_t)1 << 30) ? 1u << 30 : (unsigned)room);
+    if(n <= 0) f->eof = 1; else f->len += (size_t)n;
+  }
+  if(!f->eof) {
+    /* is the input exactly at its end?  then this chunk is the last one */
+    const int c = gzgetc(f->gz);
+    if(c == -1) f->eof = 1; else gzungetc(c, f->gz);
+  }
+}
+
+static inline int sa_dev_grow(sa_dev_file *f)
+{
+  const size_t cap = f->cap * 2;
+  if(cap > ((size_t)1 << 30)) return 0;
+  char *nb = seqalign_host_alloc(cap + 64);
+  if(!nb) return 0;
+  memcpy(nb, f->buf, f->len);
+  seqalign_host_free(f->buf);
+  f->buf = nb; f->cap = cap;
+  return 1;
+}
+
+static inline int sa_for_each_batch_dev(const char *path1, const char *path2, int device, size_t max_pairs, int want_names,
+                                        sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *), unsigned long *done)
+{
+  *done = 0;
+  const char *env = getenv("SEQALIGN_CLI_CHUNK_MB");
+  size_t cap = (size_t)(env && atoi(env) > 0 ? atoi(env) : 64) << 20;
+  if(env && atoi(env) < 0) cap = (size_t)(-atoi(env));   /* negative: bytes (tests cut chunks inside records) */
+  sa_dev_file f[2];
+  memset(f, 0, sizeof(f));
+  const int nf = path2 ? 2 : 1;
+  int ok = 1;
+  for(int k = 0; k < nf && ok; k++) {
+    f[k].gz = gzopen(k ? path2 : path1, "r");
+    if(f[k].gz) gzbuffer(f[k].gz, 1 << 20);
+    ok = f[k].gz != NULL;
+  }
+  if(ok) sa_engine_wait();   /* the pinned buffers and the reads objects need the context */
+  for(int k = 0; k < nf && ok; k++) {
+    f[k].cap = cap;
+    f[k].buf = seqalign_host_alloc(cap + 64);
+    f[k].reads = f[k].buf ? seqalign_reads_create(device) : NULL;
+    ok = f[k].buf && f[k].reads;
+  }
+  int rc = ok ? 0 : -1;
+  struct sa_dev_chunk chunk;
+  memset(&chunk, 0, sizeof(chunk));
+  while(ok) {
+    double t0 = sa_now();
+    size_t cnt[2] = {0, 0};
+    int declined = 0;
+    for(int k = 0; k < nf; k++) {
+      sa_dev_fill(&f[k]);
+      const int drc = seqalign_reads_decode(f[k].reads, f[k].buf, f[k].len, f[k].eof, nf == 1);
+      if(drc == SEQALIGN_ERR_IRREGULAR) { declined = 1; break; }
+      if(drc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_reads_error(f[k].reads)); exit(EXIT_FAILURE); }
+      cnt[k] = seqalign_reads_records(f[k].reads);
+    }
+    sa_t_read += sa_now() - t0;
+    if(declined) { rc = 1; break; }
+    const size_t navail = nf == 1 ? cnt[0] / 2 : (cnt[0] < cnt[1] ? cnt[0] : cnt[1]);
+    if(navail == 0) {
+      /* not one whole pair in the buffer: more text needed (a record longer than the chunk), or the end */
+      int grew = 0, stuck = 0;
+      for(int k = 0; k < nf; k++)
+        if(!f[k].eof && cnt[k] < (size_t)(nf == 1 ? 2 : 1)) { if(sa_dev_grow(&f[k])) grew = 1; else stuck = 1; }
+      if(stuck) { rc = *done == 0 ? -1 : 1; break; }
+      if(grew) continue;
+    }
+    chunk.ra = f[0].reads; chunk.rb = f[nf - 1].reads; chunk.have_a = chunk.have_b = 0;
+    chunk.text_a = f[0].len; chunk.text_b = f[nf - 1].len;
+    for(size_t first = 0; first < navail; first += max_pairs) {
+      const size_t n = navail - first < max_pairs ? navail - first : max_pairs;
+      t0 = sa_now();
+      sa_pairs_clear(pairs);
+      sa_pairs_reserve(pairs, n);
+      const int64_t *oa = seqalign_reads_offsets(f[0].reads, 0) + first;
+      const int64_t *ob = seqalign_reads_offsets(f[nf - 1].reads, nf == 1 ? 1 : 0) + first;
+      for(size_t i = 0; i < n; i++) {
+        pairs->la[i] = (size_t)(oa[i + 1] - oa[i]);
+        pairs->lb[i] = (size_t)(ob[i + 1] - ob[i]);
+        pairs->a[i] = pairs->b[i] = pairs->name_a[i] = pairs->name_b[i] = NULL;
+        if(want_names) {
+          size_t pos = 0, len = 0;
+          seqalign_reads_name(f[0].reads, nf == 1 ? 2 * (first + i) : first + i, &pos, &len);
+          if(len) pairs->name_a[i] = sa_dup(f[0].buf + pos, len);
+          seqalign_reads_name(f[nf - 1].reads, nf == 1 ? 2 * (first + i) + 1 : first + i, &pos, &len);
+          if(len) pairs->name_b[i] = sa_dup(f[nf - 1].buf + pos, len);
+        }
+      }
+      pairs->n = n;
+      pairs->dev_a = f[0].reads; pairs->dev_side_a = 0;
+      pairs->dev_b = f[nf - 1].reads; pairs->dev_side_b = nf == 1 ? 1 : 0;
+      pairs->dev_first = first;
+      pairs->chunk = &chunk;
+      sa_t_read += sa_now() - t0;
+      flush(pairs, NULL);
+      sa_pairs_clear(pairs);
+    }
+    *done += navail;
+    /* what is left of each buffer goes to its front */
+    for(int k = 0; k < nf; k++) {
+      /* record_start(i) is where record i starts, or (i = number of complete records) the held-back tail */
+      size_t cut = seqalign_reads_record_start(f[k].reads, nf == 1 ? 2 * navail : navail);
+      if(cut > f[k].len) cut = f[k].len;
+      memmove(f[k].buf, f[k].buf + cut, f[k].len - cut);
+      f[k].len -= cut;
+    }
+    /* end of the input (messages as reference src/alignment_cmdline.c:613-620) */
+    if(nf == 1) {
+      if(f[0].eof) {
+        if(cnt[0] & 1) { fprintf(stderr, "Alignment Error: Odd number of sequences - I read in pairs!\n"); fflush(stderr); }
+        break;
+      }
+    } else {
+      if(f[0].eof && cnt[0] == navail) break;                 /* first file exhausted: done, whatever the second still holds */
+      if(f[1].eof && cnt[1] == navail && cnt[0] > navail) {   /* a record of the first file without a partner */
+        fprintf(stderr, "Alignment Error: Odd number of sequences - I read in pairs!\n"); fflush(stderr);
+        break;
+      }
+    }
+  }
+  if(rc == 0 && *done == 0) { fprintf(stderr, "Alignment Warning: empty input\n"); fflush(stderr); }
+  for(int k = 0; k < nf; k++) {
+    if(f[k].reads) seqalign_reads_destroy(f[k].reads);
+    if(f[k].buf) seqalign_host_free(f[k].buf);
+    if(f[k].gz) gzclose(f[k].gz);
+  }
+  free(chunk.host_a); free(chunk.host_b);
+  return rc;
+}
+
+/* One input of a tool: regular files go through the device decoder (SEQALIGN_CLI_DECODE=host keeps them
+ * on the host reader); stdin and anything the decoder declines go through the host reader. */
+static inline void sa_read_input(const char *path1, const char *path2, int interactive, int device, size_t max_pairs,
+                                 int want_names, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
+{
+  const char *mode = getenv("SEQALIGN_CLI_DECODE");
+  const int dev_ok = !interactive && strcmp(path1, "-") != 0 && (!path2 || strcmp(path2, "-") != 0) &&
+                     !(mode && strcmp(mode, "host") == 0);
+  unsigned long done = 0;
+  if(dev_ok) {
+    const int rc = sa_for_each_batch_dev(path1, path2, device, max_pairs, want_names, pairs, flush, &done);
+    if(rc == 0) return;
+    if(rc < 0) done = 0;
+    if(mode && strcmp(mode, "device") == 0) { fprintf(stderr, "Error: the device decoder declined this input\n"); exit(EXIT_FAILURE); }
+  }
+  sa_for_each_batch_from(path1, path2, interactive, !interactive, max_pairs, pairs, flush, done);
 }
 
 #endif

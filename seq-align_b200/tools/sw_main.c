@@ -135,14 +135,14 @@ static int next_hit_wanted(void)
   return next;
 }
 
-static int rejects_pair(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b)
+static int rejects_pair(size_t len_a, size_t len_b, const char *name_a, const char *name_b)
 {
   if((name_a || name_b) && wait_on_keystroke) {
     fprintf(stderr, "Error: Interactive input takes seq only (no FASTA/FASTQ) '%s:%s'\n", name_a, name_b);
     fflush(stderr);
     exit(EXIT_FAILURE);
   }
-  if(seq_a[0] == '\0' || seq_b[0] == '\0') {
+  if(len_a == 0 || len_b == 0) {
     fprintf(stderr, "Error: Sequences must have length > 0\n");
     fflush(stderr);
     if(opt.print_fasta && name_a && name_b) fprintf(stderr, "%s\n%s\n", name_a, name_b);
@@ -155,7 +155,7 @@ static int rejects_pair(const char *seq_a, const char *seq_b, const char *name_a
 /* single-pair API: smith_waterman_align + fetch loop, hit by hit */
 static void align_single(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b)
 {
-  if(rejects_pair(seq_a, seq_b, name_a, name_b)) return;
+  if(rejects_pair(strlen(seq_a), strlen(seq_b), name_a, name_b)) return;
   smith_waterman_align(seq_a, seq_b, &scoring, sw);
   aligner_t *al = smith_waterman_get_aligner(sw);
   const size_t len_a = al->score_width - 1, len_b = al->score_height - 1;
@@ -171,10 +171,13 @@ static void align_single(const char *seq_a, const char *seq_b, const char *name_
   alignment_index++;
 }
 
-static void align_batch(const char *const *a, const size_t *la, const char *const *b, const size_t *lb,
-                        char *const *name_a, char *const *name_b, size_t n)
+static void align_batch(sa_pairs *p)
 {
+  const size_t n = p->n;
+  const size_t *la = p->la, *lb = p->lb;
+  char *const *name_a = p->name_a, *const *name_b = p->name_b;
   if(n == 0) return;
+  sa_engine_wait();
   int batch_ok = !wait_on_keystroke;
   size_t cap = HIT_CAP;
   /* --printmatrices: all three matrices of every pair from the batch materialise mode
@@ -187,7 +190,7 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
       if(mats_eng) seqalign_batch_set_scoring(mats_eng, &scoring);
     }
     with_mats = mats_eng && n > 1 &&
-                seqalign_batch_submit(mats_eng, SEQALIGN_SW, SEQALIGN_MODE_MATS, a, la, b, lb, n) == SEQALIGN_OK;
+                sa_submit(mats_eng, SEQALIGN_SW, SEQALIGN_MODE_MATS, p) == SEQALIGN_OK;
     if(!with_mats) batch_ok = 0;
   }
   /* --maxhits 1: only the first fetch matters, and that is what align mode delivers (best cell
@@ -195,7 +198,7 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
   const int first_only = batch_ok && opt.max_hits_set && opt.max_hits == 1;
   if(first_only) {
     const double t0 = sa_now();
-    const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN, a, la, b, lb, n);
+    const int rc = sa_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN, p);
     sa_t_align += sa_now() - t0;
     if(rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0;
     else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
@@ -210,16 +213,20 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
     if(opt.max_hits_set && opt.max_hits < HIT_CAP) cap = opt.max_hits ? opt.max_hits : 1;
     seqalign_batch_set_hit_limits(eng, cap, min_all < 1 ? 1 : min_all);
     const double t0 = sa_now();
-    const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, a, la, b, lb, n);
+    const int rc = sa_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, p);
     sa_t_align += sa_now() - t0;
     if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0; /* single-pair API handles both */
     else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
   }
   const double t1 = sa_now();
+  /* the sequences themselves are only needed on the host to print them (--printseq, --context, the matrix
+   * printer) or to go pair by pair; a device-decoded batch fetches them then, and only then */
+  if(!batch_ok || opt.print_seq || opt.context || with_mats) sa_pairs_host(p);
+  char *const *a = p->a, *const *b = p->b;
   for(size_t i = 0; i < n; i++) {
     const char *na = name_a ? name_a[i] : NULL, *nb = name_b ? name_b[i] : NULL;
     if(!batch_ok) { align_single(a[i], b[i], na, nb); continue; }
-    if(rejects_pair(a[i], b[i], na, nb)) continue;
+    if(rejects_pair(la[i], lb[i], na, nb)) continue;
     const int min_score = pair_min_score(la[i], lb[i]);
     aligner_t tmp;
     aligner_t *mats = NULL;
@@ -248,7 +255,8 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
         seqalign_batch_hit(eng, i, nh - 1, result);
         if(result->score >= min_score) {
           if(mats) { free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores); }
-          align_single(a[i], b[i], na, nb);
+          sa_pairs_host(p);
+          align_single(p->a[i], p->b[i], na, nb);
           continue;
         }
       }
@@ -278,7 +286,7 @@ static void align_batch(const char *const *a, const size_t *la, const char *cons
 static void flush_pairs(sa_pairs *p, sa_reader *r)
 {
   prompt_input = r;
-  align_batch((const char *const *)p->a, p->la, (const char *const *)p->b, p->lb, p->name_a, p->name_b, p->n);
+  align_batch(p);
   sa_pairs_clear(p);
 }
 
@@ -293,30 +301,31 @@ int main(int argc, char **argv)
   sa_cli_parse(argc, argv, &scoring, SA_TOOL_SW, &opt);
 
   sa_t_start = sa_now();
-  eng = seqalign_batch_create(0);
-  sa_t_init = sa_now() - sa_t_start;
-  if(!eng) { fprintf(stderr, "Error: %s\n", seqalign_last_create_error()); return EXIT_FAILURE; }
-  if(seqalign_batch_set_scoring(eng, &scoring) != SEQALIGN_OK) {
-    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
-    return EXIT_FAILURE;
-  }
+  sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
   sw = smith_waterman_new();
   result = alignment_create(256);
 
   if(opt.seq1) {
-    const size_t la = strlen(opt.seq1), lb = strlen(opt.seq2);
-    align_batch(&opt.seq1, &la, &opt.seq2, &lb, NULL, NULL, 1);
+    sa_pairs one;
+    memset(&one, 0, sizeof(one));
+    sa_pairs_reserve(&one, 1);
+    one.a[0] = sa_dup(opt.seq1, strlen(opt.seq1)); one.la[0] = strlen(opt.seq1);
+    one.b[0] = sa_dup(opt.seq2, strlen(opt.seq2)); one.lb[0] = strlen(opt.seq2);
+    one.n = 1;
+    align_batch(&one);
+    sa_pairs_free(&one);
   }
   sa_pairs pairs;
   memset(&pairs, 0, sizeof(pairs));
   for(size_t i = 0; i < opt.nfiles; i++) {
     const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
     if(f1 && *f1 == '\0' && !f2) { wait_on_keystroke = 1; f1 = "-"; }
-    sa_for_each_batch(f1, f2, opt.interactive, !opt.interactive, SW_BATCH_PAIRS, &pairs, flush_pairs);
+    sa_read_input(f1, f2, opt.interactive, 0, SW_BATCH_PAIRS, opt.print_fasta, &pairs, flush_pairs);
   }
   sa_pairs_free(&pairs);
   smith_waterman_free(sw);
   alignment_free(result);
+  sa_engine_wait();
   seqalign_batch_destroy(eng);
   if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);

@@ -52,7 +52,7 @@ def tool_dir(request):
     return os.path.join(ROOT, "tests", "emu", "bin")
 
 
-def _run(tool_dir, case):
+def _run(tool_dir, case, env=None):
     with tempfile.TemporaryDirectory() as td:
         args = []
         for x in case["argv"]:
@@ -71,7 +71,7 @@ def _run(tool_dir, case):
             else:
                 args.append(x)
         p = subprocess.run([os.path.join(tool_dir, case["tool"])] + args, input=case["stdin"],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
         return p.returncode, p.stdout, p.stderr.replace(td, "<tmp>")
 
 
@@ -93,6 +93,45 @@ def test_batched_invocations(tool_dir, i):
     if case["stderr_first"] is not None:
         # usage errors print the usage text on stdout/stderr in their own words; the message is the contract
         assert err.split("\n")[0] == case["stderr_first"], (case["argv"], err[:300])
+
+
+# how the tools read files: records decoded on the device from whole chunks of text (default; 64 MB chunks),
+# the same with chunks so small that every record straddles one (carry + buffer growth), the host reader only
+READERS = {"device": {}, "device_tiny_chunks": {"SEQALIGN_CLI_CHUNK_MB": "-48"}, "host": {"SEQALIGN_CLI_DECODE": "host"}}
+
+
+@pytest.mark.parametrize("reader", ["device_tiny_chunks", "host"])
+@pytest.mark.parametrize("i", range(len(GOLD2)))
+def test_batched_invocations_other_readers(tool_dir, i, reader):
+    """the recorded multi-pair invocations again, through the other two ways of reading the input"""
+    if tool_dir == REFMAIN:
+        pytest.skip("the reference's mains read through align_from_file only")
+    case = GOLD2[i]
+    rc, out, err = _run(tool_dir, case, READERS[reader])
+    assert rc == case["rc"], (case["argv"], err)
+    if case["rc"] == 0 or not case["stderr_first"].startswith("Error: "):
+        assert out == case["stdout"], (case["tool"], case["argv"])
+    if case["stderr_first"] is not None:
+        assert err.split("\n")[0] == case["stderr_first"], (case["argv"], err[:300])
+
+
+def test_device_reader_is_the_one_that_runs(tool_dir):
+    """SEQALIGN_CLI_DECODE=device turns a decline into an error: a FASTA file must not need the host reader,
+    a wrapped FASTQ file must"""
+    if tool_dir == REFMAIN:
+        pytest.skip("batching tools only")
+    with tempfile.TemporaryDirectory() as td:
+        fa, fq = os.path.join(td, "x.fa"), os.path.join(td, "x.fq")
+        open(fa, "w").write(">a\nACGTACGT\n>b\nACGAACGT\n>c\nTTTT\n>d\nTTAT\n")
+        open(fq, "w").write("@a\nACGT\nACGT\n+\nIIII\nIIII\n@b\nACGAACGT\n+\nIIIIIIII\n")
+        env = dict(os.environ, SEQALIGN_CLI_DECODE="device")
+        exe = os.path.join(tool_dir, "needleman_wunsch")
+        p = subprocess.run([exe, "--printscores", "--file", fa], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0 and p.stdout.count("score:") == 2, p.stderr
+        q = subprocess.run([exe, "--printscores", "--file", fq], capture_output=True, text=True, env=env, timeout=300)
+        assert q.returncode != 0 and "declined" in q.stderr
+        r = subprocess.run([exe, "--printscores", "--file", fq], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.count("score:") == 1 and "ACGTACGT" in r.stdout
 
 
 def test_interactive_smith_waterman_prompt(tool_dir):

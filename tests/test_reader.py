@@ -219,14 +219,31 @@ def test_decoded_reads_align_in_place(reads, engine):
     n = reads.records // 2
     assert n == len(sa)
     engine.set_scoring(scoring_from_spec(SPECS["sw_cli"]))
-    a, oa = seqalign.pack(sa)
-    b, ob = seqalign.pack(sb)
-    for algo, mode in ((SW, MODE_SCORE), (NW, MODE_SCORE), (SW, MODE_ALIGN), (NW, MODE_ALIGN)):
-        engine.submit_packed(algo, mode, a, oa, b, ob)
-        want_scores = engine.scores().copy()
-        want_al = [engine.alignment(i) for i in (0, 5, n - 1)] if mode == MODE_ALIGN else []
-        engine.submit_reads(algo, mode, reads, 0, reads, 1, n)
-        assert np.array_equal(engine.scores(), want_scores)
-        for i, w in zip((0, 5, n - 1), want_al):
-            g = engine.alignment(i)
-            assert (g.score, g.result_a, g.result_b) == (w.score, w.result_a, w.result_b)
+    from seqalign import MODE_HITS, MODE_MATS, MODE_SCORE_ONLY
+    for first in (0, 7):
+        m = n - first
+        a, oa = seqalign.pack(sa[first:])
+        b, ob = seqalign.pack(sb[first:])
+        probe = (0, 5, m - 1)
+        for algo, mode in ((SW, MODE_SCORE), (SW, MODE_SCORE_ONLY), (NW, MODE_SCORE), (SW, MODE_ALIGN), (NW, MODE_ALIGN),
+                           (SW, MODE_HITS), (NW, MODE_MATS)):
+            if mode == MODE_HITS:
+                engine.set_hit_limits(4, 5)
+            engine.submit_packed(algo, mode, a, oa, b, ob)
+            want_scores = engine.scores().copy() if mode not in (MODE_HITS, MODE_MATS) else None
+            want_al = [engine.alignment(i) for i in probe] if mode == MODE_ALIGN else []
+            want_hits = [engine.hits(i) for i in probe] if mode == MODE_HITS else []
+            want_mats = [engine.matrices(i, len(sa[first + i]), len(sb[first + i])) for i in probe] if mode == MODE_MATS else []
+            engine.submit_reads(algo, mode, reads, 0, reads, 1, m, first=first)
+            if want_scores is not None:
+                assert np.array_equal(engine.scores(), want_scores), (first, algo, mode)
+            for i, w in zip(probe, want_al):
+                g = engine.alignment(i)
+                assert (g.score, g.result_a, g.result_b) == (w.score, w.result_a, w.result_b)
+            for i, w in zip(probe, want_hits):
+                got = engine.hits(i)
+                assert [(x.score, x.result_a, x.result_b, x.pos_a, x.pos_b) for x in got] == \
+                       [(x.score, x.result_a, x.result_b, x.pos_a, x.pos_b) for x in w]
+            for i, w in zip(probe, want_mats):
+                g = engine.matrices(i, len(sa[first + i]), len(sb[first + i]))
+                assert all(np.array_equal(x, y) for x, y in zip(g, w))
