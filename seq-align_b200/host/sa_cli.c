@@ -49,7 +49,8 @@ static void die_usage(const char *fmt, ...)
           "  OPTIONS:\n"
           "    --file <file>        read two sequences at a time from <file> and align them\n"
           "    --files <f1> <f2>    read one sequence from each file at a time\n"
-          "    --stdin              read from STDIN (same as '--file -'), answer pair by pair\n\n"
+          "    --stdin              read from STDIN (same as '--file -'), answer pair by pair\n"
+          "    --gpus <n|all>       cut the batches over <n> GPUs of this machine [default: 1]\n\n"
           "    --case_sensitive     case sensitive character comparison [default: off]\n\n"
           "    --match <score>      [default: %i]\n"
           "    --mismatch <score>   [default: %i]\n"
@@ -134,7 +135,7 @@ enum {
   O_PRINTSCORES, O_PRINTFASTA, O_PRETTY, O_COLOUR, O_ZAM, O_STDIN,
   /* one parameter */
   O_SCORING, O_SUBMATRIX, O_SUBPAIRS, O_MINSCORE, O_MAXHITS, O_CONTEXT, O_MATCH, O_MISMATCH, O_GAPOPEN,
-  O_GAPEXTEND, O_FILE,
+  O_GAPEXTEND, O_FILE, O_GPUS,
   /* two parameters, checked by the option itself */
   O_FILES, O_WILDCARD
 };
@@ -165,6 +166,7 @@ static const struct { const char *name; int id, nparam, who; const char *only_ms
     {"--gapopen", O_GAPOPEN, 1, ANY, NULL},
     {"--gapextend", O_GAPEXTEND, 1, ANY, NULL},
     {"--file", O_FILE, 1, ANY, NULL},
+    {"--gpus", O_GPUS, 1, ANY, NULL},
     {"--files", O_FILES, 2, ANY, NULL},
     {"--wildcard", O_WILDCARD, 2, ANY, NULL},
 };
@@ -274,6 +276,11 @@ void sa_cli_parse(int argc, char **argv, scoring_t *sc, int tool, sa_opts *o)
         if(!whole_int(p, &sc->gap_extend)) die_usage("Invalid --gapextend argument ('%s') must be an int", p);
         break;
       case O_FILE: add_files(o, p, NULL); break;
+      case O_GPUS:
+        if(!strcasecmp(p, "all")) o->gpus = 0;
+        else if(!whole_int(p, &o->gpus) || o->gpus < 1) die_usage("Invalid --gpus <n> argument (a number >= 1, or 'all')");
+        o->gpus_set = 1;
+        break;
       case O_FILES:
         if(i >= argc - 2) die_usage("--files option takes 2 arguments");
         if(!strcmp(p, "-") && !strcmp(argv[i + 2], "-")) add_files(o, p, NULL); /* both from stdin */

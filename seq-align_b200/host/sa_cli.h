@@ -37,6 +37,7 @@ typedef struct {
   int min_score, min_score_set;
   unsigned max_hits; int max_hits_set;
   unsigned context;
+  int gpus, gpus_set;     /* --gpus <n>: devices the batches are cut over (0 = all); not a flag of the reference */
   const char *seq1, *seq2; /* pair given on the command line */
   sa_file_pair *files; size_t nfiles, files_cap;
 } sa_opts;

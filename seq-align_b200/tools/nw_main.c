@@ -117,7 +117,7 @@ static void align_batch(sa_pairs *p)
     }
     with_mats = mats_eng && sa_submit(mats_eng, SEQALIGN_NW, SEQALIGN_MODE_MATS, p) == SEQALIGN_OK;
   }
-  if(!opt.print_matrices || with_mats) rc = sa_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN, p);
+  if(!opt.print_matrices || with_mats) rc = sa_main_submit(SEQALIGN_NW, SEQALIGN_MODE_ALIGN, p);
   sa_t_align += sa_now() - t0;
   if(rc == SEQALIGN_OK) {
     t0 = sa_now();
@@ -125,15 +125,15 @@ static void align_batch(sa_pairs *p)
     for(size_t i = 0; i < n; i++) {
       if(with_mats) print_batch_matrices(i, p->a[i], la[i], p->b[i], lb[i]);
       alignment_ensure_capacity(result, la[i] + lb[i]);
-      rc = seqalign_batch_alignment(eng, i, result);
-      if(rc < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+      rc = sa_main_alignment(i, result);
+      if(rc < 0) { fprintf(stderr, "Error: %s\n", sa_main_error()); exit(EXIT_FAILURE); }
       print_pair(name_a ? name_a[i] : NULL, name_b ? name_b[i] : NULL);
     }
     sa_t_print += sa_now() - t0;
     return;
   }
   if(!opt.print_matrices && rc != SEQALIGN_ERR_UNKNOWN_PAIR) {
-    fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng));
+    fprintf(stderr, "Error: %s\n", sa_main_error());
     exit(EXIT_FAILURE);
   }
   /* pair by pair: prints everything up to the offending pair, then the
@@ -158,6 +158,7 @@ int main(int argc, char **argv)
   if(!opt.print_matrices) setenv("SEQALIGN_SKIP_MATRICES", "1", 1);
 
   sa_t_start = sa_now();
+  sa_gpus = opt.gpus_set ? opt.gpus : 1;
   sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
   nw = needleman_wunsch_new();
   result = alignment_create(256);
@@ -184,7 +185,7 @@ int main(int argc, char **argv)
   needleman_wunsch_free(nw);
   alignment_free(result);
   sa_engine_wait();
-  seqalign_batch_destroy(eng);
+  sa_main_destroy();
   if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);
   sa_timing_report();

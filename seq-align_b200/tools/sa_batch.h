@@ -39,6 +39,11 @@ static pthread_t sa_eng_thread;
 static int sa_eng_pending = 0;
 static seqalign_batch_t **sa_eng_slot = NULL;
 static const scoring_t *sa_eng_scoring = NULL;
+/* --gpus N (N > 1): the batches of the main engine are cut over N devices by seqalign_multi_* (one
+ * engine + one host thread per device, every device fed over its own PCIe link); the engine on device
+ * 0 stays for decoding and for the paths that go pair by pair */
+static int sa_gpus = 1;
+static seqalign_multi_t *sa_multi = NULL;
 static void *sa_engine_main(void *arg)
 {
   (void)arg;
@@ -47,6 +52,21 @@ static void *sa_engine_main(void *arg)
   if(*sa_eng_slot && seqalign_batch_set_scoring(*sa_eng_slot, sa_eng_scoring) != SEQALIGN_OK) {
     fprintf(stderr, "Error: %s\n", seqalign_batch_error(*sa_eng_slot));
     exit(EXIT_FAILURE);
+  }
+  if(*sa_eng_slot && sa_gpus != 1) {
+    /* SEQALIGN_CLI_DEVICES=0,0,1: an explicit device list (a device may appear twice: two engines on it) */
+    int devs[64], nd = 0;
+    const char *list = getenv("SEQALIGN_CLI_DEVICES");
+    for(const char *q = list; q && *q && nd < 64;) {
+      devs[nd++] = atoi(q);
+      q = strchr(q, ',');
+      if(q) q++;
+    }
+    sa_multi = nd ? seqalign_multi_create(devs, nd) : seqalign_multi_create(NULL, sa_gpus);   /* <= 0: every usable device */
+    if(!sa_multi || seqalign_multi_set_scoring(sa_multi, sa_eng_scoring) != SEQALIGN_OK) {
+      fprintf(stderr, "Error: --gpus: %s\n", sa_multi ? seqalign_multi_error(sa_multi) : seqalign_last_create_error());
+      exit(EXIT_FAILURE);
+    }
   }
   sa_t_init = sa_now() - t0;
   return NULL;
@@ -170,6 +190,74 @@ static inline void sa_pairs_free(sa_pairs *p)
   sa_pairs_clear(p);
   free(p->a); free(p->b); free(p->name_a); free(p->name_b); free(p->la); free(p->lb);
   memset(p, 0, sizeof(*p));
+}
+
+/* ---- the tool's main engine: one device, or --gpus N through seqalign_multi_* -------------- */
+static char *sa_pack_a = NULL, *sa_pack_b = NULL;
+static int64_t *sa_pack_oa = NULL, *sa_pack_ob = NULL;
+static size_t sa_pack_cap = 0, sa_pack_ncap = 0;
+
+static inline int sa_main_submit(int algo, int mode, sa_pairs *p)
+{
+  if(!sa_multi) return sa_submit(*sa_eng_slot, algo, mode, p);
+  /* packed host arrays for the multi-device call: a device-decoded chunk comes back to the host once
+   * (every device then pulls its own range of it), host batches are packed here */
+  if(p->dev_a) {
+    struct sa_dev_chunk *c = p->chunk;
+    for(int side = 0; side < 2; side++) {
+      int *have = side ? &c->have_b : &c->have_a;
+      char **host = side ? &c->host_b : &c->host_a;
+      size_t *cap = side ? &c->cap_b : &c->cap_a;
+      const seqalign_reads_t *r = side ? p->dev_b : p->dev_a;
+      if(*have) continue;
+      const size_t need = (side ? c->text_b : c->text_a) + 64;
+      if(*cap < need) { free(*host); *host = malloc(need); *cap = need; }
+      if(!*host || seqalign_reads_fetch((seqalign_reads_t *)r, side ? p->dev_side_b : p->dev_side_a, *host) != SEQALIGN_OK) {
+        fprintf(stderr, "Error: %s\n", seqalign_reads_error(r)); exit(EXIT_FAILURE);
+      }
+      *have = 1;
+    }
+    return seqalign_multi_submit_packed(sa_multi, algo, mode, c->host_a, seqalign_reads_offsets(p->dev_a, p->dev_side_a) + p->dev_first,
+                                        c->host_b, seqalign_reads_offsets(p->dev_b, p->dev_side_b) + p->dev_first, p->n);
+  }
+  size_t ta = 0, tb = 0;
+  for(size_t i = 0; i < p->n; i++) { ta += p->la[i]; tb += p->lb[i]; }
+  if(ta + tb + 64 > sa_pack_cap) {
+    sa_pack_cap = (ta + tb + 64) * 2;
+    free(sa_pack_a); free(sa_pack_b);
+    sa_pack_a = malloc(sa_pack_cap); sa_pack_b = malloc(sa_pack_cap);
+  }
+  if(p->n + 1 > sa_pack_ncap) {
+    sa_pack_ncap = (p->n + 1) * 2;
+    free(sa_pack_oa); free(sa_pack_ob);
+    sa_pack_oa = malloc(sa_pack_ncap * sizeof(int64_t)); sa_pack_ob = malloc(sa_pack_ncap * sizeof(int64_t));
+  }
+  if(!sa_pack_a || !sa_pack_b || !sa_pack_oa || !sa_pack_ob) { fprintf(stderr, "%s:%i: Out of memory\n", __FILE__, __LINE__); exit(EXIT_FAILURE); }
+  ta = tb = 0;
+  for(size_t i = 0; i < p->n; i++) {
+    sa_pack_oa[i] = (int64_t)ta; sa_pack_ob[i] = (int64_t)tb;
+    memcpy(sa_pack_a + ta, p->a[i], p->la[i]); ta += p->la[i];
+    memcpy(sa_pack_b + tb, p->b[i], p->lb[i]); tb += p->lb[i];
+  }
+  sa_pack_oa[p->n] = (int64_t)ta; sa_pack_ob[p->n] = (int64_t)tb;
+  return seqalign_multi_submit_packed(sa_multi, algo, mode, sa_pack_a, sa_pack_oa, sa_pack_b, sa_pack_ob, p->n);
+}
+static inline int sa_main_alignment(size_t i, alignment_t *out)
+{ return sa_multi ? seqalign_multi_alignment(sa_multi, i, out) : seqalign_batch_alignment(*sa_eng_slot, i, out); }
+static inline size_t sa_main_hit_count(size_t i)
+{ return sa_multi ? seqalign_multi_hit_count(sa_multi, i) : seqalign_batch_hit_count(*sa_eng_slot, i); }
+static inline int sa_main_hit(size_t i, size_t h, alignment_t *out)
+{ return sa_multi ? seqalign_multi_hit(sa_multi, i, h, out) : seqalign_batch_hit(*sa_eng_slot, i, h, out); }
+static inline int sa_main_set_hit_limits(size_t max_hits, int32_t min_score)
+{ return sa_multi ? seqalign_multi_set_hit_limits(sa_multi, max_hits, min_score) : seqalign_batch_set_hit_limits(*sa_eng_slot, max_hits, min_score); }
+static inline const char *sa_main_error(void)
+{ return sa_multi ? seqalign_multi_error(sa_multi) : seqalign_batch_error(*sa_eng_slot); }
+static inline void sa_main_destroy(void)
+{
+  if(sa_multi) seqalign_multi_destroy(sa_multi);
+  sa_multi = NULL;
+  if(sa_eng_slot && *sa_eng_slot) seqalign_batch_destroy(*sa_eng_slot);
+  free(sa_pack_a); free(sa_pack_b); free(sa_pack_oa); free(sa_pack_ob);
 }
 
 /* a batch is full at this many pairs or bytes of sequence */

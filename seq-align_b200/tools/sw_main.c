@@ -198,10 +198,10 @@ static void align_batch(sa_pairs *p)
   const int first_only = batch_ok && opt.max_hits_set && opt.max_hits == 1;
   if(first_only) {
     const double t0 = sa_now();
-    const int rc = sa_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN, p);
+    const int rc = sa_main_submit(SEQALIGN_SW, SEQALIGN_MODE_ALIGN, p);
     sa_t_align += sa_now() - t0;
     if(rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0;
-    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", sa_main_error()); exit(EXIT_FAILURE); }
   } else if(batch_ok) {
     /* empty sequences are reported at print time; the engine sees them as pairs without hits */
     int min_all = 0, have = 0;
@@ -211,12 +211,12 @@ static void align_batch(sa_pairs *p)
       if(!have || m < min_all) { min_all = m; have = 1; }
     }
     if(opt.max_hits_set && opt.max_hits < HIT_CAP) cap = opt.max_hits ? opt.max_hits : 1;
-    seqalign_batch_set_hit_limits(eng, cap, min_all < 1 ? 1 : min_all);
+    sa_main_set_hit_limits(cap, min_all < 1 ? 1 : min_all);
     const double t0 = sa_now();
-    const int rc = sa_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, p);
+    const int rc = sa_main_submit(SEQALIGN_SW, SEQALIGN_MODE_HITS, p);
     sa_t_align += sa_now() - t0;
     if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_UNKNOWN_PAIR) batch_ok = 0; /* single-pair API handles both */
-    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+    else if(rc != SEQALIGN_OK) { fprintf(stderr, "Error: %s\n", sa_main_error()); exit(EXIT_FAILURE); }
   }
   const double t1 = sa_now();
   /* the sequences themselves are only needed on the host to print them (--printseq, --context, the matrix
@@ -249,10 +249,10 @@ static void align_batch(sa_pairs *p)
     size_t nh = 0;
     const size_t want = opt.max_hits_set ? opt.max_hits : (size_t)-1;
     if(!first_only) {
-      nh = seqalign_batch_hit_count(eng, i);
+      nh = sa_main_hit_count(i);
       /* the device list is complete unless it is full and the caller wants more */
       if(nh == cap && want > cap) {
-        seqalign_batch_hit(eng, i, nh - 1, result);
+        sa_main_hit(i, nh - 1, result);
         if(result->score >= min_score) {
           if(mats) { free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores); }
           sa_pairs_host(p);
@@ -265,13 +265,13 @@ static void align_batch(sa_pairs *p)
     if(mats) { free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores); }
     if(first_only) {
       alignment_ensure_capacity(result, la[i] + lb[i]);
-      const int got = seqalign_batch_alignment(eng, i, result);
-      if(got < 0) { fprintf(stderr, "Error: %s\n", seqalign_batch_error(eng)); exit(EXIT_FAILURE); }
+      const int got = sa_main_alignment(i, result);
+      if(got < 0) { fprintf(stderr, "Error: %s\n", sa_main_error()); exit(EXIT_FAILURE); }
       if(got == 1 && result->score >= min_score) print_hit(a[i], b[i], la[i], lb[i], 0);
     } else {
       size_t hit_index = 0;
       for(size_t h = 0; h < nh && hit_index < want; h++) {
-        if(seqalign_batch_hit(eng, i, h, result) != 1) break;
+        if(sa_main_hit(i, h, result) != 1) break;
         if(result->score < min_score) break;
         print_hit(a[i], b[i], la[i], lb[i], hit_index++);
       }
@@ -301,6 +301,7 @@ int main(int argc, char **argv)
   sa_cli_parse(argc, argv, &scoring, SA_TOOL_SW, &opt);
 
   sa_t_start = sa_now();
+  sa_gpus = opt.gpus_set ? opt.gpus : 1;
   sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
   sw = smith_waterman_new();
   result = alignment_create(256);
@@ -326,7 +327,7 @@ int main(int argc, char **argv)
   smith_waterman_free(sw);
   alignment_free(result);
   sa_engine_wait();
-  seqalign_batch_destroy(eng);
+  sa_main_destroy();
   if(mats_eng) seqalign_batch_destroy(mats_eng);
   sa_cli_free(&opt);
   sa_timing_report();

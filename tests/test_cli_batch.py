@@ -97,16 +97,23 @@ def test_batched_invocations(tool_dir, i):
 
 # how the tools read files: records decoded on the device from whole chunks of text (default; 64 MB chunks),
 # the same with chunks so small that every record straddles one (carry + buffer growth), the host reader only
-READERS = {"device": {}, "device_tiny_chunks": {"SEQALIGN_CLI_CHUNK_MB": "-48"}, "host": {"SEQALIGN_CLI_DECODE": "host"}}
+READERS = {"device": {}, "device_tiny_chunks": {"SEQALIGN_CLI_CHUNK_MB": "-48"}, "host": {"SEQALIGN_CLI_DECODE": "host"},
+           # --gpus 3 (the flag is added to argv below): batches cut over three engines -- the box's GPUs, or three
+           # engines on the one (emulated) device
+           "three_engines": {"SEQALIGN_CLI_DEVICES": "0,0,0"}, "three_engines_host_reader": {"SEQALIGN_CLI_DEVICES": "0,0,0", "SEQALIGN_CLI_DECODE": "host"}}
 
 
-@pytest.mark.parametrize("reader", ["device_tiny_chunks", "host"])
+@pytest.mark.parametrize("reader", ["device_tiny_chunks", "host", "three_engines", "three_engines_host_reader"])
 @pytest.mark.parametrize("i", range(len(GOLD2)))
 def test_batched_invocations_other_readers(tool_dir, i, reader):
     """the recorded multi-pair invocations again, through the other two ways of reading the input"""
     if tool_dir == REFMAIN:
         pytest.skip("the reference's mains read through align_from_file only")
     case = GOLD2[i]
+    if reader.startswith("three_engines"):
+        if case["tool"] == "lcs":
+            pytest.skip("lcs takes no options")
+        case = dict(case, argv=["--gpus", "3"] + case["argv"])
     rc, out, err = _run(tool_dir, case, READERS[reader])
     assert rc == case["rc"], (case["argv"], err)
     if case["rc"] == 0 or not case["stderr_first"].startswith("Error: "):
