@@ -233,6 +233,13 @@ void seqalign_batch_unknown_pair(const seqalign_batch_t *eng, char *a, char *b);
 /* Page-locked host memory for callers without CUDA headers: input buffers and
  * result sinks allocated here travel over PCIe by DMA without a staging copy
  * (cudaMallocHost / cudaFreeHost).  NULL on failure. */
+/* Classic single-pair API (needleman_wunsch_align*, smith_waterman_align*): the three matrices of
+ * the caller's aligner_t are by default filled only when something in this library reads them
+ * (alignment_print_matrices, alignment_reverse_move, aligner_align itself always fills).  on = 1
+ * restores the reference's behaviour for callers that index aligner->match_scores[] themselves:
+ * filled on every call (12 bytes per cell over PCIe).  Also: environment SEQALIGN_EAGER_MATRICES=1. */
+void seqalign_host_eager_matrices(int on);
+
 void *seqalign_host_alloc(size_t bytes);
 void seqalign_host_free(void *p);
 

@@ -996,14 +996,9 @@ int fast_per_sm(KF kfn, size_t smem)
   thread_local std::vector<FastKernelInfo> cache;
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t opted = 0;   /* largest opt-in made for this kernel so far: the attribute is only ever raised */
-  for(const FastKernelInfo &k : cache) {
-    if(k.fn != (const void *)kfn || k.device != dev) continue;
-    if(k.smem == smem) return k.per_sm;
-    if(k.smem > opted) opted = k.smem;
-  }
-  if(smem > opted &&
-     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  for(const FastKernelInfo &k : cache)
+    if(k.fn == (const void *)kfn && k.device == dev && k.smem == smem) return k.per_sm;
+  if(!smem_opt_in(kfn, smem)) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, FAST_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   cache.push_back({(const void *)kfn, smem, dev, per_sm});

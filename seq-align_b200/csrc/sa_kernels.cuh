@@ -19,8 +19,37 @@
 #define SA_KERNELS_CUH
 
 #include "sa_platform.h"
+#include <mutex>
+#include <vector>
 
 namespace sa {
+
+/* Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the FUNCTION (per
+ * device), not to the calling thread: engines on several host threads launch the same kernels with
+ * different sizes, so the limit is only ever raised, under one process-wide lock.  (A per-thread
+ * record of what had been opted in let one thread lower the limit under another thread's launch:
+ * "invalid argument" on hardware, invisible in the emulator.) */
+template <class KF>
+inline bool smem_opt_in(KF kfn, size_t smem)
+{
+  struct Opted { const void *fn; int device; size_t smem; };
+  static std::mutex mu;
+  static std::vector<Opted> opted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for(Opted &o : opted) {
+    if(o.fn != (const void *)kfn || o.device != dev) continue;
+    if(o.smem >= smem) return true;
+    if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    o.smem = smem;
+    return true;
+  }
+  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+  opted.push_back({(const void *)kfn, dev, smem});
+  return true;
+}
+
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GK = 8;            /* columns per lane, general kernel */

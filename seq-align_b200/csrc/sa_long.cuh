@@ -671,7 +671,7 @@ template <int K, bool P32, bool DIR, bool NOEND, bool CKPT = false>
 int long_launch_one(const LongPlan &plan, const LongArgs &L, int grid, cudaStream_t st)
 {
   void (*kfn)(const LongArgs) = long_kernel<K, false, P32, DIR, NOEND, CKPT>;
-  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess) return -1;
+  if(!smem_opt_in(kfn, plan.smem)) return -1;
   SA_LAUNCH(kfn, grid, LONG_WARPS * 32, plan.smem, st, L);
   return 0;
 }
@@ -714,7 +714,7 @@ inline int walk_ckpt_launch(const LongPlan &plan, const WalkArgs &W, const int8_
   void (*kfn)(const WalkArgs, const int8_t *, const int32_t *, const int);
   if(plan.prof32) kfn = plan.noend ? walk_ckpt_kernel<false, true, true> : walk_ckpt_kernel<false, false, true>;
   else kfn = plan.noend ? walk_ckpt_kernel<false, true, false> : walk_ckpt_kernel<false, false, false>;
-  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if(!smem_opt_in(kfn, smem)) return -1;
   SA_LAUNCH(kfn, grid, WK_WARPS * 32, smem, st, W, d_tab8, d_tab32, 1);
   return 0;
 }

@@ -294,7 +294,7 @@ int mats_launch_nb(const MatsArgs &M, bool pack, bool nw, size_t smem, int num_s
   /* NW: free end gaps (FREE) are their own instantiations, so that the common rows keep open / ext loop-invariant */
   if(nw) kfn = M.sp.no_end ? (pack ? mats_kernel<NB, false, true, true, true> : mats_kernel<NB, false, false, true, true>)
                            : (pack ? mats_kernel<NB, false, true, true, false> : mats_kernel<NB, false, false, true, false>);
-  if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if(!smem_opt_in(kfn, smem)) return -1;
   int per_sm = 1;
   if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, MATS_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)num_sms * per_sm;

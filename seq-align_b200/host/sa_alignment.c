@@ -69,9 +69,74 @@ void sa_host_check(seqalign_batch_t *eng, int rc)
   exit(EXIT_FAILURE);
 }
 
+/* ---- deferred matrices ---------------------------------------------------
+ * needleman_wunsch_align* and smith_waterman_align* get their results (score, gapped strings, hit
+ * lists) straight from the engine's align / multi-hit modes; the three (len_a+1) x (len_b+1) int32
+ * matrices of the reference's aligner_t (12 bytes per cell over PCIe: 1.2 GB for one 10k x 10k pair)
+ * are only needed by callers that LOOK at them.  Everything in this library that does --
+ * alignment_print_matrices, alignment_reverse_move, the host hit iteration -- fills them on demand
+ * (sa_host_materialise).  aligner_align() itself, the reference's seam, always fills at once.
+ * Code that reads aligner->match_scores[] directly after needleman_wunsch_align() asks for the
+ * reference's eager behaviour with seqalign_host_eager_matrices(1) or SEQALIGN_EAGER_MATRICES=1. */
+#define SA_DEFER_SLOTS 64
+static struct { const aligner_t *al; char is_sw; } g_defer[SA_DEFER_SLOTS];
+static volatile int g_deferred = 0;   /* entries in use: lets the hot callers skip the lock */
+static pthread_mutex_t g_defer_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_eager = -1;
+
+void seqalign_host_eager_matrices(int on) { g_eager = on ? 1 : 0; }
+
+static int eager_matrices(void)
+{
+  if(g_eager < 0) {
+    const char *e = getenv("SEQALIGN_EAGER_MATRICES");
+    g_eager = e && e[0] == '1';
+  }
+  return g_eager;
+}
+
+static int defer_forget(const aligner_t *al)
+{
+  int was = -1;
+  if(g_deferred == 0) return was;
+  pthread_mutex_lock(&g_defer_lock);
+  for(int i = 0; i < SA_DEFER_SLOTS; i++)
+    if(g_defer[i].al == al) { was = g_defer[i].is_sw; g_defer[i].al = NULL; g_deferred--; break; }
+  pthread_mutex_unlock(&g_defer_lock);
+  return was;
+}
+
+void sa_host_bind(aligner_t *aligner, const char *seq_a, const char *seq_b, size_t len_a, size_t len_b,
+                  const scoring_t *scoring, char is_sw)
+{
+  if(eager_matrices()) { aligner_align(aligner, seq_a, seq_b, len_a, len_b, scoring, is_sw); return; }
+  defer_forget(aligner);
+  aligner->scoring = scoring;
+  aligner->seq_a = seq_a;
+  aligner->seq_b = seq_b;
+  aligner->score_width = len_a + 1;
+  aligner->score_height = len_b + 1;
+  pthread_mutex_lock(&g_defer_lock);
+  int slot = -1;
+  for(int i = 0; i < SA_DEFER_SLOTS && slot < 0; i++) if(!g_defer[i].al) slot = i;
+  if(slot >= 0) { g_defer[slot].al = aligner; g_defer[slot].is_sw = is_sw; g_deferred++; }
+  pthread_mutex_unlock(&g_defer_lock);
+  /* more aligners with pending matrices than slots: this one is filled now */
+  if(slot < 0) aligner_align(aligner, seq_a, seq_b, len_a, len_b, scoring, is_sw);
+}
+
+void sa_host_materialise(const aligner_t *al)
+{
+  const int is_sw = defer_forget(al);
+  if(is_sw < 0) return;   /* matrices are current */
+  aligner_t *w = (aligner_t *)al;
+  aligner_align(w, w->seq_a, w->seq_b, w->score_width - 1, w->score_height - 1, w->scoring, (char)is_sw);
+}
+
 void aligner_align(aligner_t *aligner, const char *seq_a, const char *seq_b,
                    size_t len_a, size_t len_b, const scoring_t *scoring, char is_sw)
 {
+  defer_forget(aligner);
   aligner->scoring = scoring;
   aligner->seq_a = seq_a;
   aligner->seq_b = seq_b;
@@ -101,6 +166,7 @@ void aligner_align(aligner_t *aligner, const char *seq_a, const char *seq_b,
 
 void aligner_destroy(aligner_t *aligner)
 {
+  defer_forget(aligner);
   if(aligner->capacity > 0) {
     free(aligner->match_scores);
     free(aligner->gap_a_scores);
@@ -155,6 +221,7 @@ void alignment_reverse_move(enum Matrix *curr_matrix, score_t *curr_score,
                             size_t *score_x, size_t *score_y,
                             size_t *arr_index, const aligner_t *al)
 {
+  if(g_deferred) sa_host_materialise(al);
   const scoring_t *sc = al->scoring;
   const size_t la = al->score_width - 1, lb = al->score_height - 1;
   const size_t seq_x = *score_x - 1, seq_y = *score_y - 1;
@@ -231,6 +298,7 @@ static void print_matrix(const char *name, const score_t *m, size_t w, size_t h)
 /* reference alignment.c:353-403 (byte-for-byte the same text) */
 void alignment_print_matrices(const aligner_t *al)
 {
+  if(g_deferred) sa_host_materialise(al);
   printf("seq_a: %.*s\nseq_b: %.*s\n", (int)al->score_width - 1, al->seq_a,
          (int)al->score_height - 1, al->seq_b);
   print_matrix("match_scores", al->match_scores, al->score_width, al->score_height);

@@ -6,8 +6,8 @@
  * alignment_reverse_move (src/needleman_wunsch.c:34-145), this submits a
  * batch of one in align mode: fill + direction bytes + walk all run on the
  * GPU and the gapped strings come back ready.  The aligner_t matrices are
- * materialised as well (callers such as `needleman_wunsch --printmatrices`
- * read them after the call); SEQALIGN_SKIP_MATRICES=1 turns that off.
+ * filled when a caller looks at them (`needleman_wunsch --printmatrices` through
+ * alignment_print_matrices); seqalign_host_eager_matrices(1) fills them at once.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,15 +37,9 @@ void needleman_wunsch_align(const char *a, const char *b, const scoring_t *scori
 void needleman_wunsch_align2(const char *a, const char *b, size_t len_a, size_t len_b,
                              const scoring_t *scoring, nw_aligner_t *nw, alignment_t *result)
 {
-  const char *skip = getenv("SEQALIGN_SKIP_MATRICES");
-  if(skip && skip[0] == '1') {
-    nw->scoring = scoring;
-    nw->seq_a = a; nw->seq_b = b;
-    nw->score_width = len_a + 1; nw->score_height = len_b + 1;
-  } else {
-    aligner_align(nw, a, b, len_a, len_b, scoring, 0);
-  }
-
+  /* one fill: score, traceback bytes (or checkpoints) and walk on the device; the matrices of the
+   * aligner_t follow only if somebody reads them (sa_alignment.c "deferred matrices") */
+  sa_host_bind(nw, a, b, len_a, len_b, scoring, 0);
   seqalign_batch_t *eng = sa_host_engine();
   seqalign_batch_set_scoring(eng, scoring);
   sa_host_check(eng, seqalign_batch_submit(eng, SEQALIGN_NW, SEQALIGN_MODE_ALIGN,

@@ -1,18 +1,23 @@
 /*
  * sa_sw.c -- Smith-Waterman front-end of the seq-align C API.
  *
- * Implements include/smith_waterman.h.  smith_waterman_align2() fills on the
- * GPU (matrices materialised into the embedded aligner_t, which
- * smith_waterman_get_aligner() exposes, reference smith_waterman.c:126-129).
- * The first smith_waterman_fetch() -- the only one `--maxhits 1` and the
- * batch path need -- is served by the GPU: best cell under the reference's
- * hit order + walk kernel.  Further hits are iterated on the host over the
- * materialised match matrix with the reference's semantics
- * (smith_waterman.c:152-161, 165-277): candidates with match>0 in (score
- * desc, x asc, y asc) order, a visited mask, a hit dropped as soon as its
- * walk meets a marked cell.  The mask is cleared completely for every pair
- * (the reference clears a quarter of it, smith_waterman.c:149 -- see
- * DESIGN.md "known upstream defects").
+ * Implements include/smith_waterman.h.  smith_waterman_align2() only binds the
+ * pair (the matrices of the embedded aligner_t, which smith_waterman_get_aligner()
+ * exposes, reference smith_waterman.c:126-129, are filled when somebody reads
+ * them: sa_alignment.c "deferred matrices").  Every smith_waterman_fetch() is
+ * served by the GPU: the first one by the engine's align mode (best cell under
+ * the reference's hit order + walk kernel: all `--maxhits 1` needs), the
+ * following ones by its multi-hit mode (SEQALIGN_MODE_HITS: candidate sort and
+ * masked walks on the device, reference smith_waterman.c:152-161, 165-277), whose
+ * list is copied into the aligner and grown eightfold whenever the caller
+ * fetches past its end.
+ * Only scoring shapes the device multi-hit stage refuses (no_gaps_in_a/b,
+ * no_mismatches, free end gaps: SEQALIGN_ERR_ARG) iterate on the host over the
+ * materialised match matrix, with the reference's semantics: candidates with
+ * match>0 in (score desc, x asc, y asc) order, a visited mask, a hit dropped
+ * as soon as its walk meets a marked cell.  The mask is cleared completely
+ * for every pair (the reference clears a quarter of it, smith_waterman.c:149
+ * -- see DESIGN.md "known upstream defects").
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,6 +39,10 @@ struct sw_aligner_t
   size_t ncands, cand_cap, next_cand;
   int have_cands;
   size_t fetched;            /* hits returned so far for this pair */
+  /* hit list made by the device (copied out of the engine, which other aligners share) */
+  alignment_t **list;
+  size_t list_n, list_cap, list_alloc;
+  int use_host;              /* the device stage refused this scoring shape */
 };
 
 sw_aligner_t *smith_waterman_new()
@@ -46,6 +55,8 @@ sw_aligner_t *smith_waterman_new()
 void smith_waterman_free(sw_aligner_t *sw)
 {
   aligner_destroy(&sw->aligner);
+  for(size_t i = 0; i < sw->list_alloc; i++) alignment_free(sw->list[i]);
+  free(sw->list);
   free(sw->mask);
   free(sw->cands);
   free(sw);
@@ -64,10 +75,12 @@ void smith_waterman_align(const char *a, const char *b, const scoring_t *scoring
 void smith_waterman_align2(const char *a, const char *b, size_t len_a, size_t len_b,
                            const scoring_t *scoring, sw_aligner_t *sw)
 {
-  aligner_align(&sw->aligner, a, b, len_a, len_b, scoring, 1);
+  sa_host_bind(&sw->aligner, a, b, len_a, len_b, scoring, 1);
   sw->have_cands = 0;
   sw->ncands = sw->next_cand = 0;
   sw->fetched = 0;
+  sw->list_n = sw->list_cap = 0;
+  sw->use_host = 0;
 }
 
 /* total order of hits: score desc, x asc, y asc */
@@ -83,6 +96,7 @@ static int cand_cmp(const void *pa, const void *pb)
 static void build_candidates(sw_aligner_t *sw)
 {
   const aligner_t *al = &sw->aligner;
+  sa_host_materialise(al);
   const size_t w = al->score_width, cells = w * al->score_height;
   size_t words = (cells + 31) / 32;
   if(words > sw->mask_words) {
@@ -120,6 +134,7 @@ static void build_candidates(sw_aligner_t *sw)
 static int follow_candidate(sw_aligner_t *sw, const sw_cand_t *c, alignment_t *result)
 {
   const aligner_t *al = &sw->aligner;
+  sa_host_materialise(al);
   size_t x = c->x, y = c->y, k = (size_t)c->y * al->score_width + c->x;
   enum Matrix m = MATCH;
   score_t s = c->score;
@@ -149,27 +164,57 @@ static int follow_candidate(sw_aligner_t *sw, const sw_cand_t *c, alignment_t *r
   return 1;
 }
 
-int smith_waterman_fetch(sw_aligner_t *sw, alignment_t *result)
+static void copy_alignment(alignment_t *dst, const alignment_t *src)
+{
+  alignment_ensure_capacity(dst, src->length);
+  memcpy(dst->result_a, src->result_a, src->length + 1);
+  memcpy(dst->result_b, src->result_b, src->length + 1);
+  dst->length = src->length; dst->score = src->score;
+  dst->pos_a = src->pos_a; dst->pos_b = src->pos_b; dst->len_a = src->len_a; dst->len_b = src->len_b;
+}
+
+/* (re)build the device hit list with room for `cap` hits; 0 if the engine's multi-hit stage
+ * does not take this scoring shape */
+static int build_device_list(sw_aligner_t *sw, size_t cap)
 {
   const aligner_t *al = &sw->aligner;
-  if(sw->fetched == 0) {
-    /* first hit: GPU best cell + GPU walk (batch of one, align mode) */
-    seqalign_batch_t *eng = sa_host_engine();
-    const size_t la = al->score_width - 1, lb = al->score_height - 1;
-    seqalign_batch_set_scoring(eng, al->scoring);
-    sa_host_check(eng, seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN,
-                                             &al->seq_a, &la, &al->seq_b, &lb, 1));
-    const int rc = seqalign_batch_alignment(eng, 0, result);
-    sa_host_check(eng, rc);
-    sw->fetched = 1;
-    return rc;
+  seqalign_batch_t *eng = sa_host_engine();
+  const size_t la = al->score_width - 1, lb = al->score_height - 1;
+  seqalign_batch_set_scoring(eng, al->scoring);
+  seqalign_batch_set_hit_limits(eng, cap, 1);
+  const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, &al->seq_a, &la, &al->seq_b, &lb, 1);
+  if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_NOMEM) return 0;
+  sa_host_check(eng, rc);
+  const size_t n = seqalign_batch_hit_count(eng, 0);
+  if(n > sw->list_alloc) {
+    sw->list = realloc(sw->list, n * sizeof(alignment_t *));
+    if(!sw->list) { fprintf(stderr, "%s:%i: Out of memory\n", __FILE__, __LINE__); exit(EXIT_FAILURE); }
+    for(size_t i = sw->list_alloc; i < n; i++) sw->list[i] = alignment_create(la + lb + 1);
+    sw->list_alloc = n;
   }
+  alignment_t *tmp = alignment_create(la + lb + 1);
+  for(size_t i = 0; i < n; i++) {
+    sa_host_check(eng, seqalign_batch_hit(eng, 0, i, tmp));
+    copy_alignment(sw->list[i], tmp);
+  }
+  alignment_free(tmp);
+  sw->list_n = n;
+  sw->list_cap = cap;
+  return 1;
+}
+
+static int fetch_on_host(sw_aligner_t *sw, alignment_t *result)
+{
+  const aligner_t *al = &sw->aligner;
   if(!sw->have_cands) {
-    /* replay hit 0 on the host to mark its path, then continue from hit 1 */
+    /* replay the hits already handed out (their paths mark cells), then continue */
     build_candidates(sw);
-    if(sw->ncands == 0) return 0;
-    follow_candidate(sw, &sw->cands[0], NULL);
-    sw->next_cand = 1;
+    size_t replay = sw->fetched;
+    while(replay > 0 && sw->next_cand < sw->ncands) {
+      const sw_cand_t *c = &sw->cands[sw->next_cand++];
+      const size_t k = (size_t)c->y * al->score_width + c->x;
+      if(!bitset32_get(sw->mask, k) && follow_candidate(sw, c, NULL)) replay--;
+    }
   }
   while(sw->next_cand < sw->ncands) {
     const sw_cand_t *c = &sw->cands[sw->next_cand++];
@@ -180,4 +225,36 @@ int smith_waterman_fetch(sw_aligner_t *sw, alignment_t *result)
     }
   }
   return 0;
+}
+
+int smith_waterman_fetch(sw_aligner_t *sw, alignment_t *result)
+{
+  const aligner_t *al = &sw->aligner;
+  if(sw->fetched == 0) {
+    /* first hit: best cell + walk (batch of one, align mode; every scoring shape) */
+    seqalign_batch_t *eng = sa_host_engine();
+    const size_t la = al->score_width - 1, lb = al->score_height - 1;
+    seqalign_batch_set_scoring(eng, al->scoring);
+    sa_host_check(eng, seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_ALIGN,
+                                             &al->seq_a, &la, &al->seq_b, &lb, 1));
+    const int rc = seqalign_batch_alignment(eng, 0, result);
+    sa_host_check(eng, rc);
+    sw->fetched = 1;
+    return rc;
+  }
+  if(!sw->use_host) {
+    /* later hits: the device's list, made with room to spare and grown when the caller reads past it */
+    if(sw->list_cap == 0 || (sw->fetched >= sw->list_n && sw->list_n == sw->list_cap)) {
+      size_t cap = sw->list_cap ? sw->list_cap * 8 : 8;
+      while(cap <= sw->fetched) cap *= 8;
+      if(!build_device_list(sw, cap)) sw->use_host = 1;
+    }
+    if(!sw->use_host) {
+      if(sw->fetched >= sw->list_n) return 0;
+      copy_alignment(result, sw->list[sw->fetched]);
+      sw->fetched++;
+      return 1;
+    }
+  }
+  return fetch_on_host(sw, result);
 }

@@ -154,8 +154,6 @@ int main(int argc, char **argv)
 {
   scoring_system_default(&scoring);
   sa_cli_parse(argc, argv, &scoring, SA_TOOL_NW, &opt);
-  /* the matrices only travel to the host when they are going to be printed */
-  if(!opt.print_matrices) setenv("SEQALIGN_SKIP_MATRICES", "1", 1);
 
   sa_t_start = sa_now();
   sa_gpus = opt.gpus_set ? opt.gpus : 1;
