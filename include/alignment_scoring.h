@@ -45,8 +45,8 @@ typedef struct
 
 #ifndef bitset32_get
   #define bitset32_get(arr,idx)   (((arr)[(idx)>>5] >> ((idx)&31)) & 0x1)
-  #define bitset32_set(arr,idx)   ((arr)[(idx)>>5] |=   (1<<((idx)&31)))
-  #define bitset32_clear(arr,idx) ((arr)[(idx)>>5] &=  ~(1<<((idx)&31)))
+  #define bitset32_set(arr,idx)   ((arr)[(idx)>>5] |=   (1u<<((idx)&31)))   /* 1u: bit 31 of a signed 1 is undefined behaviour (UBSan) */
+  #define bitset32_clear(arr,idx) ((arr)[(idx)>>5] &=  ~(1u<<((idx)&31)))
 #endif
 
 #define get_wildcard_bit(scoring,c) bitset32_get((scoring)->wildcards,c)

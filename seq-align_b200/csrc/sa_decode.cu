@@ -266,6 +266,32 @@ __global__ void __launch_bounds__(DEC_TPB) contrib_kernel(const DecArgs A)
 
 constexpr int EMIT_WARPS = DEC_TPB / 32;
 
+/* One line's content, text[cs .. cs+len) -> dst[0 .. len), by a whole warp.  Source and destination
+ * have unrelated byte alignments: the body moves destination-aligned 32-bit words, each assembled from
+ * the two aligned source words it straddles (one load per lane, the neighbour's word by shuffle, a
+ * funnel shift); at most 3 bytes at either end go one by one.  Aligned source words may reach 3 bytes
+ * outside the line: inside the text buffer all the same (its base is 16-byte aligned, its end padded). */
+__device__ __forceinline__ void emit_line(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int len, int lane)
+{
+  const int head = imin((int)((4 - ((uintptr_t)dst & 3)) & 3), len);
+  if(lane < head) dst[lane] = src[lane];
+  const int nwords = (len - head) >> 2;
+  const uint8_t *sb = src + head;
+  unsigned *dw = (unsigned *)(dst + head);
+  const int k8 = 8 * (int)((uintptr_t)sb & 3);
+  const unsigned *sw = (const unsigned *)(sb - ((uintptr_t)sb & 3));
+  for(int w0 = 0; w0 < nwords; w0 += 32) {
+    const int w = w0 + lane;
+    /* the words of this round are sw[w0 .. w0+32]: lane l loads sw[w0+l], lane 31 also the one behind */
+    const unsigned lo = w <= nwords ? sw[w] : 0u;
+    unsigned hi = __shfl_down_sync(0xffffffffu, lo, 1);
+    if(lane == 31 && w < nwords && k8) hi = sw[w + 1];
+    if(w < nwords) dw[w] = k8 ? (unsigned)((((unsigned long long)hi << 32) | lo) >> k8) : lo;
+  }
+  const int done = head + 4 * nwords;
+  if(lane < len - done) dst[done + lane] = src[done + lane];
+}
+
 __global__ void __launch_bounds__(DEC_TPB) emit_kernel(const DecArgs A)
 {
   const int lane = threadIdx.x & 31;
@@ -286,18 +312,7 @@ __global__ void __launch_bounds__(DEC_TPB) emit_kernel(const DecArgs A)
       A.name_len[r] = (kind & LK_DATA) ? 0 : ce - cs;
       (side ? A.off1 : A.off0)[A.split ? (r >> 1) : r] = (int64_t)at;
     }
-    if(kind & LK_DATA) {
-      uint8_t *dst = (side ? A.out1 : A.out0) + at;
-      const uint8_t *src = A.text + cs;
-      const int len = ce - cs;
-      /* four independent 32-byte rows in flight per warp */
-      int i = lane;
-      for(; i + 96 < len; i += 128) {
-        const uint8_t v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
-        dst[i] = v0; dst[i + 32] = v1; dst[i + 64] = v2; dst[i + 96] = v3;
-      }
-      for(; i < len; i += 32) dst[i] = src[i];
-    }
+    if(kind & LK_DATA) emit_line(A.text + cs, (side ? A.out1 : A.out0) + at, ce - cs, lane);
   }
 }
 

@@ -93,7 +93,7 @@ struct seqalign_batch {
   /* inputs on device */
   DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
   /* scratch */
-  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd, d_lbnd;
+  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd, d_lbnd, d_swkey;
   /* score-mode results */
   DevBuf d_score, d_xend, d_yend, d_state;
   /* align-mode wave buffers */
@@ -464,8 +464,18 @@ int launch_long(seqalign_batch *eng, const LongPlan &plan, const ScoreParams &sp
   L.score = d_score + c0;
   L.xend = d_xend ? d_xend + c0 : nullptr;
   L.yend = d_yend ? d_yend + c0 : nullptr;
+  if(plan.is_sw) {
+    TRY(ensure_dev(eng, eng->d_swkey, m * 8));
+    L.swkey = (unsigned long long *)eng->d_swkey.p;
+  }
   CU_TRY(cudaEventRecord(ev0, st));
+  if(plan.is_sw) CU_TRY(cudaMemsetAsync(L.swkey, 0, m * 8, st));
   if(long_launch(plan, L, grid, st) != 0) return fail(eng, SEQALIGN_ERR_CUDA, "wide-pair kernel launch failed");
+  if(plan.is_sw) {
+    SA_LAUNCH(long_sw_finish_kernel, (unsigned)((m + 255) / 256), 256, 0, st, (const unsigned long long *)L.swkey, (int64_t)m,
+              L.score, L.xend, L.yend);
+    eng->last_launches++;
+  }
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaEventRecord(ev1, st));
   eng->last_launches++;
@@ -622,6 +632,10 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     TRY(ensure_dev(eng, eng->d_out_off, m * 8));
     TRY(ensure_dev(eng, eng->d_out_a, (size_t)obytes + 16));
     TRY(ensure_dev(eng, eng->d_out_b, (size_t)obytes + 16));
+    /* the walks write each pair's strings right-aligned: the part in front stays untouched, and the copy
+     * to the host takes the whole block (initcheck: no uninitialised byte may cross PCIe) */
+    CU_TRY(cudaMemsetAsync(eng->d_out_a.p, 0, (size_t)obytes, st));
+    CU_TRY(cudaMemsetAsync(eng->d_out_b.p, 0, (size_t)obytes, st));
     TRY(ensure_dev(eng, eng->d_walk, m * 4 * 7));
     TRY(ensure_pin(eng, eng->h_walk, m * 4 * 7));
     TRY(ensure_pin(eng, eng->h_str_a, (size_t)obytes + 16));
@@ -828,6 +842,10 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     TRY(ensure_dev(eng, eng->d_rec, m * (size_t)maxh * 32));
     TRY(ensure_dev(eng, eng->d_out_a, (size_t)obytes + 16));
     TRY(ensure_dev(eng, eng->d_out_b, (size_t)obytes + 16));
+    /* the walks write each pair's strings right-aligned: the part in front stays untouched, and the copy
+     * to the host takes the whole block (initcheck: no uninitialised byte may cross PCIe) */
+    CU_TRY(cudaMemsetAsync(eng->d_out_a.p, 0, (size_t)obytes, st));
+    CU_TRY(cudaMemsetAsync(eng->d_out_b.p, 0, (size_t)obytes, st));
     TRY(ensure_pin(eng, eng->h_walk, m * 4 + m * (size_t)maxh * 32));
     TRY(ensure_pin(eng, eng->h_str_a, (size_t)obytes + 16));
     TRY(ensure_pin(eng, eng->h_str_b, (size_t)obytes + 16));
@@ -1336,7 +1354,7 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
                  &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
                  &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats, &eng->d_m16, &eng->d_keys0,
-                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd, &eng->d_mat_off};
+                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd, &eng->d_mat_off, &eng->d_swkey};
   for(DevBuf *b : d) b->release();
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};

@@ -92,6 +92,7 @@ struct LongArgs {
   uint8_t *dir;                   /* DIR: traceback flag bytes, row-major per pair; CKPT: the pairs' trace regions */
   const int64_t *dir_off;
   int32_t *score, *xend, *yend;   /* per pair of the launch */
+  unsigned long long *swkey;      /* SW: per pair, best cell so far as (score << 40 | 0xFFFFF - x << 20 | 0xFFFFF - y) */
   int mul_one;
 };
 
@@ -112,8 +113,11 @@ template <int K, bool IS_SW, bool PROF32, bool DIR, bool GEN>
 __device__ __forceinline__ void long_row(int (&hp)[K], int (&ga)[K], int &hl, int &gb, int d,
                                          const unsigned *w, unsigned *dw,
                                          const int open, const int ext, const int mul_one,
-                                         const unsigned lastmask, const bool lastrow)
+                                         const unsigned lastmask, const bool lastrow, int *rowkey = nullptr)
 {
+  /* SW score kernels: the row's best match score with its column, key = M x 16 + (15 - j): a larger
+   * key is a higher score or, at equal score, a smaller column (hit order: score desc, x asc) */
+  int kbest = 0, kprev = 0;
 #pragma unroll
   for(int j = 0; j < K; j++) {
     const int sub = PROF32 ? (int)w[j] : sext_byte_dyn(w[j / 4], j & 3);
@@ -140,6 +144,12 @@ __device__ __forceinline__ void long_row(int (&hp)[K], int (&ga)[K], int &hl, in
       gb = addmax(gb, eB, hlf);
     }
     h = max3(m, ga[j], gb);
+    if(IS_SW && !DIR) {
+      const int kk = m * (mul_one * 16) + (15 - j);   /* IMAD: off the ALU pipe */
+      if(j & 1) kbest = max3(kbest, kprev, kk);
+      else if(j == K - 1) kbest = imax(kbest, kk);
+      kprev = kk;
+    }
     if(DIR) {
       /* five "not equal" bits (sa_fast.cuh), a >= b holds for every pair */
       const int f = imin(h - ga[j], 1) + 2 * imin(h - gb, 1) + 4 * imin(ga[j] - uge, 1) +
@@ -150,6 +160,7 @@ __device__ __forceinline__ void long_row(int (&hp)[K], int (&ga)[K], int &hl, in
     hl = h * mul_one + open;
     hp[j] = hl;
   }
+  if(IS_SW && !DIR && rowkey) *rowkey = kbest;
 }
 
 template <int K, bool IS_SW, bool PROF32, bool DIR, bool NOEND, bool CKPT = false>
@@ -284,6 +295,7 @@ long_kernel(const LongArgs A)
       else hd = (sp.no_start ? 0 : sp.gap_open + (xf - 1) * ext) + open;
 
       int out_h = 0, out_gb = 0;
+      int swbest = 0, swy = 0;   /* SW: this lane's best key in this strip and its row */
       const int nsteps = lb + 31;
       for(int st = 0; st < nsteps; st++) {
         const int y = st - lane + 1;
@@ -345,10 +357,13 @@ long_kernel(const LongArgs A)
 #pragma unroll
             for(int q = 0; q < K / 4; q++) dw[q] = 0;
           }
+          int rowkey = 0;
           if(NOEND && (!more || y == lb))
             long_row<K, IS_SW, PROF32, DIR, true>(hp, ga, hl, gb, hd, w, dw, open, ext, mul_one, lastmask, y == lb);
           else
-            long_row<K, IS_SW, PROF32, DIR, false>(hp, ga, hl, gb, hd, w, dw, open, ext, mul_one, 0u, false);
+            long_row<K, IS_SW, PROF32, DIR, false>(hp, ga, hl, gb, hd, w, dw, open, ext, mul_one, 0u, false, &rowkey);
+          /* a later row replaces the lane's best only with a larger key: at equal (score, x) the smaller y stays */
+          if(IS_SW && !DIR && rowkey > swbest) { swbest = rowkey; swy = y; }
           if(DIR) {
             /* the row stride is a multiple of 16: a lane's 16 bytes are inside or outside as a whole */
             unsigned *drow = (unsigned *)(dirp + (int64_t)(y - 1) * dstride + (xf - 1));
@@ -393,6 +408,20 @@ long_kernel(const LongArgs A)
             if(A.yend) A.yend[p] = lb;
           }
         }
+      }
+      if(IS_SW && !DIR) {
+        /* the strip's best cell under the hit order (score desc, x asc, y asc: smith_waterman.c:71-86),
+         * merged into the pair's by a 64-bit atomic max */
+        int sv = swbest >> 4, sx = xf + 15 - (swbest & 15), sy = swy;
+        if(sv <= 0) { sv = 0; sx = 0; sy = 0; }
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) {
+          const int v2 = __shfl_xor_sync(FULL, sv, o), x2 = __shfl_xor_sync(FULL, sx, o), y2 = __shfl_xor_sync(FULL, sy, o);
+          if(hit_better(v2, x2, y2, sv, sx, sy)) { sv = v2; sx = x2; sy = y2; }
+        }
+        if(lane == 0 && sv > 0)
+          atomicMax(A.swkey + p, ((unsigned long long)sv << 40) | ((unsigned long long)(0xFFFFF - sx) << 20) |
+                                     (unsigned long long)(0xFFFFF - sy));
       }
       __syncwarp();
       if(lane == 0) s_fin[wib] = gs + 1;
@@ -613,6 +642,19 @@ walk_ckpt_kernel(const WalkArgs A, const int8_t *__restrict__ tab8, const int32_
   }
 }
 
+/* SW: the pairs' best-cell keys -> score, x_end, y_end */
+__global__ void long_sw_finish_kernel(const unsigned long long *__restrict__ key, int64_t n, int32_t *__restrict__ score,
+                                      int32_t *__restrict__ xend, int32_t *__restrict__ yend)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const unsigned long long k = key[i];
+  const int sv = (int)(k >> 40);
+  score[i] = sv;
+  if(xend) xend[i] = sv > 0 ? 0xFFFFF - (int)((k >> 20) & 0xFFFFF) : 0;
+  if(yend) yend[i] = sv > 0 ? 0xFFFFF - (int)(k & 0xFFFFF) : 0;
+}
+
 /* ---- host side ---------------------------------------------------------- */
 
 inline size_t long_smem_bytes(int K, int ncodes, bool prof32)
@@ -629,7 +671,9 @@ inline size_t long_smem_bytes(int K, int ncodes, bool prof32)
 inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
                       int64_t max_la, int64_t max_lb, bool want_dir, LongPlan *plan)
 {
-  if(sp.is_sw) return false;
+  /* Smith-Waterman: score and end cell only (traceback of wide local alignments stays with the general
+   * kernel); coordinates and score have to fit the 20 + 20 + 24 bits of the best-cell key */
+  if(sp.is_sw && (want_dir || sp.no_end || max_la >= (1 << 20) || max_lb >= (1 << 20))) return false;
   if(sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
   if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
   if(ft.any_unknown) return false;
@@ -650,7 +694,8 @@ inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   const int padsub = ft.min_sub < -1 ? ft.min_sub : -1;
   const bool fits8 = lo >= -127 && hi <= 127 && (long)padsub - sp.open >= -127 && (long)padsub - sp.open <= 127;
   if(!prof32 && !fits8) return false;
-  plan->K = K; plan->is_sw = false; plan->prof32 = prof32; plan->dir = want_dir; plan->noend = sp.no_end != 0;
+  if(sp.is_sw && (long)(max_la < max_lb ? max_la : max_lb) * (ft.max_sub > 0 ? ft.max_sub : 0) >= (1L << 23)) return false;
+  plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32; plan->dir = want_dir; plan->noend = sp.no_end != 0;
   plan->smem = long_smem_bytes(K, n, prof32);
   if(plan->smem > 100 * 1024) return false;
   const int tw = n + 1;
@@ -662,15 +707,15 @@ inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
       plan->tab32[(size_t)cb * tw + ca] = v;
       if(!prof32) plan->tab8[(size_t)cb * tw + ca] = (int8_t)v;
     }
-  plan->name = want_dir ? "long_nw_dir" : "long_nw_score";
+  plan->name = sp.is_sw ? "long_sw_score_end" : want_dir ? "long_nw_dir" : "long_nw_score";
   plan->ckpt = false;
   return true;
 }
 
-template <int K, bool P32, bool DIR, bool NOEND, bool CKPT = false>
+template <int K, bool P32, bool DIR, bool NOEND, bool CKPT = false, bool IS_SW = false>
 int long_launch_one(const LongPlan &plan, const LongArgs &L, int grid, cudaStream_t st)
 {
-  void (*kfn)(const LongArgs) = long_kernel<K, false, P32, DIR, NOEND, CKPT>;
+  void (*kfn)(const LongArgs) = long_kernel<K, IS_SW, P32, DIR, NOEND, CKPT>;
   if(!smem_opt_in(kfn, plan.smem)) return -1;
   SA_LAUNCH(kfn, grid, LONG_WARPS * 32, plan.smem, st, L);
   return 0;
@@ -689,6 +734,9 @@ inline int long_grid(const LongPlan &plan, int num_sms, int64_t npairs)
 inline int long_launch(const LongPlan &plan, LongArgs L, int grid, cudaStream_t st)
 {
   L.mul_one = 1;
+  if(plan.is_sw)
+    return plan.prof32 ? long_launch_one<16, true, false, false, false, true>(plan, L, grid, st)
+                       : long_launch_one<16, false, false, false, false, true>(plan, L, grid, st);
   if(plan.ckpt) {
     if(plan.prof32) return plan.noend ? long_launch_one<16, true, false, true, true>(plan, L, grid, st)
                                       : long_launch_one<16, true, false, false, true>(plan, L, grid, st);

@@ -323,6 +323,38 @@ def test_wide_pairs_strip_pipeline(engine, big, case, monkeypatch):
                 _check_alignment(engine.alignment(i), NW, o, sa[i], sb[i])
 
 
+@pytest.mark.parametrize("case", ["dna_wide", "protein_wide", "ties"])
+def test_wide_pairs_sw_score(engine, big, case):
+    """Smith-Waterman beyond 512 columns: the strip-pipelined kernel (sa_long.cuh, IS_SW) -- score and the end
+    cell under the reference's hit order (score desc, x asc, y asc), merged over the strips of a pair"""
+    if case == "dna_wide":
+        sa, sb = ragged_batch(31, 40 if big else 6, 3000 if big else 1200, 2500 if big else 90, min_len=1)
+        names = ("sw_cli", "nw_default", "linear_gap")
+    elif case == "protein_wide":
+        sa, sb = ragged_batch(32, 24 if big else 4, 2200 if big else 700, 900 if big else 40,
+                              alphabet=b"ARNDCQEGHILKMFPSTWYVBZX", min_len=1)
+        names = ("blosum62", "pam30")
+    else:
+        # the same motif many times over: equal best scores in different strips, lanes and rows
+        motif = b"ACGTTGCA"
+        sa = [motif * (150 if big else 80), b"T" * 700 + motif + b"T" * 700, motif * 70 + b"G" + motif * 70]
+        sb = [motif * 3, motif, motif * 2]
+        names = ("sw_cli",)
+    a, oa = seqalign.pack(sa)
+    b, ob = seqalign.pack(sb)
+    engine.force_general(0)
+    for name in names:
+        sc = scoring_from_spec(SPECS[name])
+        o = orc_from_scoring(sc)
+        engine.set_scoring(sc)
+        engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+        assert engine.last_kernel == "long_sw_score_end", engine.last_kernel
+        es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+        s, x, y = engine.ends()
+        assert np.array_equal(s, es), (name, np.nonzero(s != es)[0][:8])
+        assert np.array_equal(x, ex) and np.array_equal(y, ey), (name, np.nonzero((x != ex) | (y != ey))[0][:8])
+
+
 def test_empty_inputs(engine):
     sc = scoring_from_spec(SPECS["nw_default"])
     engine.set_scoring(sc)

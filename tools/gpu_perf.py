@@ -47,6 +47,12 @@ for L in (64, 100, 128, 250, 300, 512):
     n = int(2.0e9 / (L * L))
     a, oa, b, ob = synthetic_batch(20 + L, n, L, L)
     timeit("dna%d score-only" % L, "sw_cli", seqalign.SW, 3, a, oa, b, ob, n * L * L)
+# Smith-Waterman beyond 512 columns: strip-pipelined kernel (was the general kernel in round 1)
+for L, n in ((2000, 500), (5000, 100)):
+    a, oa, b, ob = synthetic_batch(40 + L, n, L, L)
+    ref = timeit("dna%d SW score + end cell (wide)" % L, "sw_cli", seqalign.SW, 0, a, oa, b, ob, n * L * L, reps=3)
+    if L == 2000:
+        timeit("dna%d SW general kernel" % L, "sw_cli", seqalign.SW, 1, a, oa, b, ob, n * L * L, reps=1, check=ref)
 # align mode (score + end cell + traceback strings on the host)
 def align(tag, name, algo, a, oa, b, ob, cells, walk=None):
     if walk: os.environ["SEQALIGN_WALK"] = walk
