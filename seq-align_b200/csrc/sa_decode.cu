@@ -266,11 +266,13 @@ __global__ void __launch_bounds__(DEC_TPB) contrib_kernel(const DecArgs A)
 
 constexpr int EMIT_WARPS = DEC_TPB / 32;
 
-/* One line's content, text[cs .. cs+len) -> dst[0 .. len), by a whole warp.  Source and destination
- * have unrelated byte alignments: the body moves destination-aligned 32-bit words, each assembled from
- * the two aligned source words it straddles (one load per lane, the neighbour's word by shuffle, a
- * funnel shift); at most 3 bytes at either end go one by one.  Aligned source words may reach 3 bytes
- * outside the line: inside the text buffer all the same (its base is 16-byte aligned, its end padded). */
+/* One line's content, text[cs .. cs+len) -> dst[0 .. len), by a group of GL lanes (lane = index in the
+ * group).  Source and destination have unrelated byte alignments: the body moves destination-aligned
+ * 32-bit words, each assembled from the two aligned source words it straddles (one load per lane, the
+ * neighbour's word by shuffle, a funnel shift); at most 3 bytes at either end go one by one.  Aligned
+ * source words may reach 3 bytes outside the line: inside the text buffer all the same (its base is
+ * 16-byte aligned, its end padded). */
+template <int GL>
 __device__ __forceinline__ void emit_line(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int len, int lane)
 {
   const int head = imin((int)((4 - ((uintptr_t)dst & 3)) & 3), len);
@@ -280,31 +282,45 @@ __device__ __forceinline__ void emit_line(const uint8_t *__restrict__ src, uint8
   unsigned *dw = (unsigned *)(dst + head);
   const int k8 = 8 * (int)((uintptr_t)sb & 3);
   const unsigned *sw = (const unsigned *)(sb - ((uintptr_t)sb & 3));
-  for(int w0 = 0; w0 < nwords; w0 += 32) {
-    const int w = w0 + lane;
-    /* the words of this round are sw[w0 .. w0+32]: lane l loads sw[w0+l], lane 31 also the one behind */
+  /* every group of the warp runs as many rounds as the longest line among them needs (the shuffle is warp-wide) */
+  int rounds = (nwords + GL - 1) / GL;
+#pragma unroll
+  for(int o = GL; o < 32; o <<= 1) rounds = imax(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+  for(int r = 0; r < rounds; r++) {
+    const int w = r * GL + lane;
+    /* the words of this round are sw[r*GL .. r*GL+GL]: lane l loads sw[r*GL+l], the last lane also the one behind */
     const unsigned lo = w <= nwords ? sw[w] : 0u;
-    unsigned hi = __shfl_down_sync(0xffffffffu, lo, 1);
-    if(lane == 31 && w < nwords && k8) hi = sw[w + 1];
+    unsigned hi = __shfl_down_sync(0xffffffffu, lo, 1, GL);
+    if(lane == GL - 1 && w < nwords && k8) hi = sw[w + 1];
     if(w < nwords) dw[w] = k8 ? (unsigned)((((unsigned long long)hi << 32) | lo) >> k8) : lo;
   }
   const int done = head + 4 * nwords;
   if(lane < len - done) dst[done + lane] = src[done + lane];
 }
 
+/* GL lanes per line: short lines (reads) leave a whole warp mostly idle and, worse, one line at a time per
+ * warp makes the kernel wait out a chain of dependent loads per line (index -> span -> text); with 8 lanes
+ * per line four such chains are in flight per warp */
+template <int GL>
 __global__ void __launch_bounds__(DEC_TPB) emit_kernel(const DecArgs A)
 {
-  const int lane = threadIdx.x & 31;
+  constexpr int PER_WARP = 32 / GL;
+  const int lane = threadIdx.x & 31, gl = lane % GL, grp = lane / GL;
   const int64_t warp0 = (int64_t)blockIdx.x * EMIT_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * EMIT_WARPS;
-  for(int64_t li = warp0; li < A.nlines; li += nwarps) {
-    const int kind = A.kind[li];
-    if(kind == LK_NONE) continue;
-    const int cs = A.cs[li], ce = A.ce[li];
-    const int r = A.rec_excl[li] + A.recflag[li] - 1;
-    const int side = A.split ? (r & 1) : 0;
-    const int at = side ? A.at1[li] : A.at0[li];
-    if((kind & LK_REC) && lane == 0) {
+  for(int64_t l0 = warp0 * PER_WARP; l0 < A.nlines; l0 += nwarps * PER_WARP) {
+    const int64_t li = l0 + grp;
+    int kind = LK_NONE, cs = 0, ce = 0, r = 0, side = 0, at = 0;
+    if(li < A.nlines) {
+      kind = A.kind[li];
+      if(kind != LK_NONE) {
+        cs = A.cs[li]; ce = A.ce[li];
+        r = A.rec_excl[li] + A.recflag[li] - 1;
+        side = A.split ? (r & 1) : 0;
+        at = side ? A.at1[li] : A.at0[li];
+      }
+    }
+    if((kind & LK_REC) && gl == 0) {
       const int s = li == 0 ? 0 : A.nl_pos[li - 1] + 1;
       A.rec_pos[r] = s;
       /* a plain record has no name; a header's span is its name */
@@ -312,7 +328,9 @@ __global__ void __launch_bounds__(DEC_TPB) emit_kernel(const DecArgs A)
       A.name_len[r] = (kind & LK_DATA) ? 0 : ce - cs;
       (side ? A.off1 : A.off0)[A.split ? (r >> 1) : r] = (int64_t)at;
     }
-    if(kind & LK_DATA) emit_line(A.text + cs, (side ? A.out1 : A.out0) + at, ce - cs, lane);
+    /* every lane takes part (warp-wide shuffles inside); lines without data copy nothing */
+    const int len = (kind & LK_DATA) ? ce - cs : 0;
+    emit_line<GL>(A.text + cs, (side ? A.out1 : A.out0) + at, len, gl);
   }
 }
 
@@ -526,10 +544,14 @@ int seqalign_reads_decode(seqalign_reads_t *r, const char *text, size_t bytes, i
   RTRY(scan_i32(r, A.contrib0, nlines, (int *)r->d_a0.p, d_sc + 2));
   if(split) RTRY(scan_i32(r, A.contrib1, nlines, (int *)r->d_a1.p, d_sc + 3));
   else RCU(cudaMemsetAsync(d_sc + 3, 0, 8, st));
-  int egrid = (int)((nlines + EMIT_WARPS - 1) / EMIT_WARPS);
+  /* lanes per line by the average line length: 8 for reads, a whole warp for long lines */
+  const bool long_lines = n / (nlines > 0 ? nlines : 1) > 400;
+  const int per_warp = long_lines ? 1 : 4;
+  int egrid = (int)((nlines + (int64_t)EMIT_WARPS * per_warp - 1) / ((int64_t)EMIT_WARPS * per_warp));
   if(egrid > r->num_sms * 8) egrid = r->num_sms * 8;
   if(egrid < 1) egrid = 1;
-  SA_LAUNCH(emit_kernel, egrid, DEC_TPB, 0, st, A);
+  if(long_lines) SA_LAUNCH(emit_kernel<32>, egrid, DEC_TPB, 0, st, A);
+  else SA_LAUNCH(emit_kernel<8>, egrid, DEC_TPB, 0, st, A);
   RCU(cudaGetLastError());
   RCU(cudaEventRecord(r->ev1, st));
 

@@ -93,7 +93,7 @@ struct seqalign_batch {
   /* inputs on device */
   DevBuf d_seq_a, d_seq_b, d_off_a, d_off_b;
   /* scratch */
-  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd, d_lbnd, d_swkey;
+  DevBuf d_meta, d_counter, d_sub, d_forbid, d_lut, d_tab8, d_bnd, d_lbnd, d_swkey, d_bucket;
   /* score-mode results */
   DevBuf d_score, d_xend, d_yend, d_state;
   /* align-mode wave buffers */
@@ -393,7 +393,7 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
 /* launch the specialised score kernel of `plan` (tables must be on the device) */
 int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScoreParams &sp, const DevBatch &db,
                       int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
-                      cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0)
+                      cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0, const int *d_order = nullptr, int64_t order_count = 0)
 {
   const size_t nn = plan_elems(sp.ncodes);
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
@@ -406,17 +406,18 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
   memset(&F, 0, sizeof(F));
   F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
   F.npairs = (int64_t)db.n; F.sp = sp;
+  if(d_order) { F.order = d_order; F.npairs = order_count; }   /* a length bucket: pair indices through `order` */
   F.tab8 = d_t8;
   F.tab32 = d_t32;
   F.lut = (const uint8_t *)eng->d_lut.p;
   F.counter = d_cnt;
   F.score = d_score; F.xend = d_xend; F.yend = d_yend;
   F.max_lb = (int)max_lb;
-  CU_TRY(cudaEventRecord(ev0, st));
+  if(ev0) CU_TRY(cudaEventRecord(ev0, st));
   int r = fast_launch(plan, F, eng->num_sms, eng->smem_optin, st);
   if(r != 0) return fail(eng, SEQALIGN_ERR_CUDA, "fast kernel launch failed");
   CU_TRY(cudaGetLastError());
-  CU_TRY(cudaEventRecord(ev1, st));
+  if(ev1) CU_TRY(cudaEventRecord(ev1, st));
   eng->last_launches++;
   eng->last_kernel = plan.name;
   return 0;
@@ -507,6 +508,52 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       CU_TRY(cudaMemcpyAsync(d_t32, plan.tab32.data(), nn * 4, cudaMemcpyHostToDevice, st));
       eng->dev_tab32 = plan.tab32;
       eng->dev_tab8 = plan.tab8;
+    }
+    /* reads of different lengths: one launch per shape class over length-sorted pairs (sa_fast.cuh "length
+     * buckets") instead of one launch shaped by the longest pair */
+    const char *nob = getenv("SEQALIGN_NO_BUCKETS");
+    if(plan.s16 && !uniform && db.n >= 4096 && db.n < ((size_t)1 << 31) && !(nob && nob[0] == '1')) {
+      BucketArgs B;
+      memset(&B, 0, sizeof(B));
+      for(const FastShape &sh : kFast16Shapes) {
+        if(B.nclasses == BUCKET_MAX_CLASSES) break;
+        const int w = sh.G * sh.K;
+        if(B.nclasses && w <= B.width[B.nclasses - 1]) continue;
+        B.width[B.nclasses++] = w;
+        if(w >= bm.max_la) break;
+      }
+      while((bm.max_lb >> B.shift) >= BUCKET_LB_BINS) B.shift++;
+      const size_t nbins = (size_t)B.nclasses * BUCKET_LB_BINS;
+      TRY(ensure_dev(eng, eng->d_bucket, (2 * nbins + BUCKET_MAX_CLASSES + 1) * 4 + db.n * 4));
+      B.bins = (int *)eng->d_bucket.p; B.cursor = B.bins + nbins; B.class_start = B.cursor + nbins;
+      B.order = B.class_start + BUCKET_MAX_CLASSES + 1;
+      B.off_a = db.off_a; B.off_b = db.off_b; B.npairs = (int64_t)db.n;
+      CU_TRY(cudaEventRecord(ev0, st));
+      CU_TRY(cudaMemsetAsync(B.bins, 0, nbins * 4, st));
+      const unsigned bgrid = (unsigned)((db.n + 255) / 256);
+      SA_LAUNCH(bucket_hist_kernel, bgrid, 256, 0, st, B);
+      SA_LAUNCH(bucket_scan_kernel, 1, 256, 0, st, B);
+      SA_LAUNCH(bucket_scatter_kernel, bgrid, 256, 0, st, B);
+      CU_TRY(cudaGetLastError());
+      int class_start[BUCKET_MAX_CLASSES + 1];
+      CU_TRY(cudaMemcpyAsync(class_start, B.class_start, (B.nclasses + 1) * 4, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      eng->last_launches += 3;
+      for(int c = 0; c < B.nclasses; c++) {
+        const int64_t cnt = class_start[c + 1] - class_start[c];
+        if(cnt == 0) continue;
+        FastPlan cplan;
+        const int64_t cla = B.width[c] < bm.max_la ? B.width[c] : bm.max_la;
+        if(!fast_plan(eng->scoring, eng->ft, sp, cla, bm.max_lb, want_ends, true, &cplan, false, false) || !cplan.s16 ||
+           cplan.s16_ends != plan.s16_ends)
+          cplan = plan;   /* the batch's own plan holds every pair */
+        TRY(launch_fast_score(eng, cplan, sp, db, bm.max_lb, d_score, d_xend, d_yend, st, nullptr, nullptr, 1 + c,
+                              B.order + class_start[c], cnt));
+      }
+      CU_TRY(cudaEventRecord(ev1, st));
+      eng->last_kernel = plan.name;
+      if(plan_out) *plan_out = plan;
+      return 0;
     }
     TRY(launch_fast_score(eng, plan, sp, db, bm.max_lb, d_score, d_xend, d_yend, st, ev0, ev1));
     if(plan_out) *plan_out = plan;
@@ -840,6 +887,7 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     TRY(ensure_dev(eng, eng->d_which, m * 4));
     TRY(ensure_dev(eng, eng->d_nhits, m * 4));
     TRY(ensure_dev(eng, eng->d_rec, m * (size_t)maxh * 32));
+    CU_TRY(cudaMemsetAsync(eng->d_rec.p, 0, m * (size_t)maxh * 32, st));   /* records past a pair's hit count are copied too */
     TRY(ensure_dev(eng, eng->d_out_a, (size_t)obytes + 16));
     TRY(ensure_dev(eng, eng->d_out_b, (size_t)obytes + 16));
     /* the walks write each pair's strings right-aligned: the part in front stays untouched, and the copy
@@ -1354,7 +1402,7 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
                  &eng->d_sub, &eng->d_forbid, &eng->d_lut, &eng->d_tab8, &eng->d_bnd, &eng->d_score,
                  &eng->d_xend, &eng->d_yend, &eng->d_state, &eng->d_dir, &eng->d_dir_off, &eng->d_out_a,
                  &eng->d_out_b, &eng->d_out_off, &eng->d_walk, &eng->d_mats, &eng->d_m16, &eng->d_keys0,
-                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd, &eng->d_mat_off, &eng->d_swkey};
+                 &eng->d_keys1, &eng->d_mask, &eng->d_ncand, &eng->d_which, &eng->d_nhits, &eng->d_rec, &eng->d_lbnd, &eng->d_mat_off, &eng->d_swkey, &eng->d_bucket};
   for(DevBuf *b : d) b->release();
   PinBuf *h[] = {&eng->h_in_a, &eng->h_in_b, &eng->h_off_a, &eng->h_off_b, &eng->h_meta, &eng->h_res,
                  &eng->h_walk, &eng->h_str_a, &eng->h_str_b};

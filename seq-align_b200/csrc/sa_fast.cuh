@@ -61,6 +61,7 @@ struct FastArgs {
   int max_lb;
   int a_stage, b_stage; /* bytes per pair per stage (multiples of 16) */
   int pad_row;          /* fast16: 1 = the profile has a padding row (couples of different shapes), 0 = uniform batch */
+  const int *order;     /* fast16: work item i is pair order[i] (length buckets, see bucket_* below); null = identity */
 };
 
 struct FastPlan {
@@ -635,8 +636,9 @@ fast16_kernel(const FastArgs A)
     if(lane == 0) {
       uint32_t bytes = 0;
       for(int g = 0; g < NP; g++) {
-        const int64_t p = t * NP + g;
-        if(p >= A.npairs) break;
+        const int64_t wi = t * NP + g;
+        if(wi >= A.npairs) break;
+        const int64_t p = A.order ? (int64_t)A.order[wi] : wi;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;   /* does not fit the plan: skipped, see below */
@@ -645,8 +647,9 @@ fast16_kernel(const FastArgs A)
       }
       mbar_expect_tx(&bar[st], bytes);
       for(int g = 0; g < NP; g++) {
-        const int64_t p = t * NP + g;
-        if(p >= A.npairs) break;
+        const int64_t wi = t * NP + g;
+        if(wi >= A.npairs) break;
+        const int64_t p = A.order ? (int64_t)A.order[wi] : wi;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;
@@ -679,8 +682,10 @@ fast16_kernel(const FastArgs A)
      * cell can reach the pair's best real score (M there is below some earlier H), so neither
      * the running maximum nor the end-cell key needs a mask.  (Uniform batches carry no padding
      * row: only a missing or refused pair has rows past its end there, and its result is not kept.) */
-    const int64_t plo = t * NP + 2 * grp, phi = plo + 1;
-    const bool have_lo = plo < A.npairs, have_hi = phi < A.npairs;
+    const int64_t wlo = t * NP + 2 * grp;
+    const bool have_lo = wlo < A.npairs, have_hi = wlo + 1 < A.npairs;
+    const int64_t plo = !have_lo ? 0 : A.order ? (int64_t)A.order[wlo] : wlo;
+    const int64_t phi = !have_hi ? 0 : A.order ? (int64_t)A.order[wlo + 1] : wlo + 1;
     int la_lo = 0, lb_lo = 0, la_hi = 0, lb_hi = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
     if(have_lo) {
       const int64_t oa = A.off_a[plo], ob = A.off_b[plo];
@@ -867,6 +872,72 @@ fast16_kernel(const FastArgs A)
     stage ^= 1;
     t = tn;
   }
+}
+
+/* ---- length buckets for the packed kernel ---------------------------------
+ * A batch of reads of different lengths is shaped by its longest seq_a (columns) and every couple by
+ * its longer seq_b (rows).  Bucketing gives each pair the narrowest kernel shape that holds its seq_a
+ * and puts pairs of similar len_b next to each other: a counting sort on the key
+ * (shape class, len_b >> shift) -- histogram, one-CTA scan, scatter -- whose output is the `order`
+ * array the kernel reads its pair indices through.  The order inside a bin is whatever the atomics
+ * make it; results are written by pair index, so they do not depend on it. */
+constexpr int BUCKET_LB_BINS = 256;
+constexpr int BUCKET_MAX_CLASSES = 16;
+struct BucketArgs {
+  const int64_t *off_a, *off_b;
+  int64_t npairs;
+  int nclasses;
+  int width[BUCKET_MAX_CLASSES];   /* columns of class c, ascending */
+  int shift;                       /* len_b >> shift < BUCKET_LB_BINS */
+  int *bins;                       /* [nclasses * BUCKET_LB_BINS] counts, then starts */
+  int *cursor;                     /* same size: running positions of the scatter */
+  int *class_start;                /* [nclasses + 1] */
+  int *order;
+};
+
+__device__ __forceinline__ int bucket_key(const BucketArgs &B, int64_t p)
+{
+  const int la = (int)(B.off_a[p + 1] - B.off_a[p]), lb = (int)(B.off_b[p + 1] - B.off_b[p]);
+  int c = 0;
+  while(c + 1 < B.nclasses && la > B.width[c]) c++;
+  return c * BUCKET_LB_BINS + imin(lb >> B.shift, BUCKET_LB_BINS - 1);
+}
+
+__global__ void bucket_hist_kernel(const BucketArgs B)
+{
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(p < B.npairs) atomicAdd(&B.bins[bucket_key(B, p)], 1);
+}
+
+/* one CTA of 256 threads: counts -> starts (in place), a copy for the scatter, the class boundaries */
+__global__ void bucket_scan_kernel(const BucketArgs B)
+{
+  __shared__ int s_part[256];
+  const int nb = B.nclasses * BUCKET_LB_BINS;
+  const int per = (nb + 255) / 256, b0 = threadIdx.x * per;
+  int sum = 0;
+  for(int i = b0; i < b0 + per && i < nb; i++) sum += B.bins[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    int run = 0;
+    for(int i = 0; i < 256; i++) { const int t = s_part[i]; s_part[i] = run; run += t; }
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for(int i = b0; i < b0 + per && i < nb; i++) {
+    const int t = B.bins[i];
+    B.bins[i] = run; B.cursor[i] = run;
+    if(i % BUCKET_LB_BINS == 0) B.class_start[i / BUCKET_LB_BINS] = run;
+    run += t;
+  }
+  if(threadIdx.x == 0) B.class_start[B.nclasses] = (int)B.npairs;
+}
+
+__global__ void bucket_scatter_kernel(const BucketArgs B)
+{
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(p < B.npairs) B.order[atomicAdd(&B.cursor[bucket_key(B, p)], 1)] = (int)p;
 }
 
 /* ---- host side ---------------------------------------------------------- */

@@ -355,6 +355,45 @@ def test_wide_pairs_sw_score(engine, big, case):
         assert np.array_equal(x, ex) and np.array_equal(y, ey), (name, np.nonzero((x != ex) | (y != ey))[0][:8])
 
 
+def test_length_buckets(engine, big, monkeypatch):
+    """reads of different lengths through the packed kernel: pairs are counting-sorted by (shape class of
+    len_a, len_b) on the device and every class gets the narrowest kernel shape that holds it
+    (sa_fast.cuh "length buckets"); scores and end cells must not depend on it"""
+    rng = np.random.default_rng(17)
+    n = 20000 if big else 4200
+    la = rng.integers(1, 151, size=n); lb = rng.integers(1, 151, size=n)
+    la[:7] = (150, 104, 105, 64, 65, 1, 128); lb[:7] = (1, 150, 149, 150, 2, 1, 77)
+    oa = np.zeros(n + 1, np.int64); ob = np.zeros(n + 1, np.int64)
+    np.cumsum(la, out=oa[1:]); np.cumsum(lb, out=ob[1:])
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    A = letters[rng.integers(0, 4, size=int(oa[-1]))]
+    B = letters[rng.integers(0, 4, size=int(ob[-1]))]
+    # half of the pairs related: b starts as a copy of a
+    for i in range(0, n, 2):
+        m = min(la[i], lb[i])
+        B[ob[i]:ob[i] + m] = A[oa[i]:oa[i] + m]
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    o = orc_from_scoring(sc)
+    m_orc = n if not big else 4000
+    es, ex, ey = orc_batch_sw(o, np.ascontiguousarray(A[:oa[m_orc]]), np.ascontiguousarray(oa[:m_orc + 1]),
+                              np.ascontiguousarray(B[:ob[m_orc]]), np.ascontiguousarray(ob[:m_orc + 1]))
+    got = {}
+    for buckets in ("1", "0"):
+        monkeypatch.setenv("SEQALIGN_NO_BUCKETS", "0" if buckets == "1" else "1")
+        for mode in (MODE_SCORE, seqalign.MODE_SCORE_ONLY):
+            engine.submit_packed(SW, mode, A, oa, B, ob)
+            assert engine.last_kernel.startswith("fast16_sw_score"), engine.last_kernel
+            got[(buckets, mode)] = (engine.ends(), engine.last_launches)
+    (s1, x1, y1), l1 = got[("1", MODE_SCORE)]
+    (s0, x0, y0), l0 = got[("0", MODE_SCORE)]
+    assert l1 > l0 + 3        # several shape classes were launched
+    assert np.array_equal(s1, s0) and np.array_equal(x1, x0) and np.array_equal(y1, y0)
+    assert np.array_equal(s1[:m_orc], es) and np.array_equal(x1[:m_orc], ex) and np.array_equal(y1[:m_orc], ey)
+    assert np.array_equal(got[("1", seqalign.MODE_SCORE_ONLY)][0][0], s0)
+
+
 def test_empty_inputs(engine):
     sc = scoring_from_spec(SPECS["nw_default"])
     engine.set_scoring(sc)

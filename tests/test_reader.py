@@ -180,7 +180,7 @@ def _chunked_records(reads, text, chunk, split):
 
 
 @pytest.mark.parity
-@pytest.mark.parametrize("kind", ["fasta", "fasta_wrapped", "fastq", "plain", "plain_crlf"])
+@pytest.mark.parametrize("kind", ["fasta", "fasta_wrapped", "fastq", "plain", "plain_crlf", "plain_long_lines"])
 def test_device_decoder_chunked(reads, kind):
     """a longer file cut at arbitrary byte positions: the held-back tail + carry protocol loses and
     duplicates nothing (records equal to the oracle's on the whole text)"""
@@ -188,7 +188,7 @@ def test_device_decoder_chunked(reads, kind):
     recs = []
     text = b""
     for i in range(40):
-        L = int(rng.integers(1, 90))
+        L = int(rng.integers(1, 90)) if kind != "plain_long_lines" else int(rng.integers(600, 1500))   # long lines: a warp per line
         s = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L))
         nl = b"\r\n" if kind == "plain_crlf" else b"\n"
         if kind == "fasta":
@@ -203,7 +203,7 @@ def test_device_decoder_chunked(reads, kind):
         text = text[:-1]          # no newline at the end of the input
     want, last, _, _ = orc_records(text)
     assert last == 0 and len(want) == 40
-    for chunk in (len(text), 997, 311, 150):
+    for chunk in ((len(text), 997, 311, 150) if kind != "plain_long_lines" else (len(text), 7001)):
         for split in (False, True):
             assert _chunked_records(reads, text, chunk, split) == want, (kind, chunk, split)
 
