@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -103,6 +104,11 @@ struct seqalign_batch {
   /* materialise mode */
   DevBuf d_mats, d_mat_off;
   std::vector<int64_t> mat_off;            /* batch materialise: first int of pair i's match plane, n+1 entries */
+  /* batch materialise in waves: pairs [mat_wave[w], mat_wave[w+1]) fit the device block together; one wave
+   * is resident at a time and seqalign_batch_matrices() re-runs the kernel for the wave it is asked about */
+  std::vector<size_t> mat_wave;
+  int mat_resident = -1;
+  struct { const uint8_t *a, *b; const int64_t *off_a, *off_b; int NB; bool pack, nw; ScoreParams sp; } mat_job;
   PinBuf h_in_a, h_in_b, h_off_a, h_off_b, h_meta, h_res, h_walk, h_str_a, h_str_b;
 
   /* optional host destination of score-mode results (seqalign_batch_set_result_sink) */
@@ -977,6 +983,30 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
 
 /* batch materialise: the three matrices of every pair stay in device memory,
  * seqalign_batch_matrices() copies one pair's planes out */
+/* the materialise kernel over the pairs of wave w; their matrices fill the device block from its start */
+int run_mats_wave(seqalign_batch *eng, int w, cudaStream_t st)
+{
+  const size_t first = eng->mat_wave[w], count = eng->mat_wave[w + 1] - first;
+  MatsArgs M;
+  memset(&M, 0, sizeof(M));
+  M.seq_a = eng->mat_job.a; M.seq_b = eng->mat_job.b;
+  M.off_a = eng->mat_job.off_a + first; M.off_b = eng->mat_job.off_b + first;
+  M.npairs = (int64_t)count; M.sp = eng->mat_job.sp;
+  M.sub = (const int32_t *)eng->d_sub.p; M.lut = (const uint8_t *)eng->d_lut.p;
+  /* mat_off stays absolute; the block pointer is moved back by the wave's first offset instead */
+  M.mats = (int32_t *)eng->d_mats.p - eng->mat_off[first];
+  M.mat_off = (const int64_t *)eng->d_mat_off.p + first;
+  M.score = (int32_t *)eng->d_score.p + first;
+  M.counter = (unsigned long long *)eng->d_counter.p;
+  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
+  if(mats_launch(eng->mat_job.NB, eng->mat_job.pack, eng->mat_job.nw, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
+    return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
+  CU_TRY(cudaGetLastError());
+  eng->last_launches++;
+  eng->mat_resident = w;
+  return 0;
+}
+
 int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
              const int64_t *h_off_a, const int64_t *h_off_b, cudaStream_t st)
 {
@@ -1011,36 +1041,42 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   eng->mat_off.assign(n + 1, 0);
   for(size_t i = 0; i < n; i++)
     eng->mat_off[i + 1] = eng->mat_off[i] + 3 * ((h_off_a[i + 1] - h_off_a[i]) + 1) * ((h_off_b[i + 1] - h_off_b[i]) + 1);
-  const size_t total = (size_t)eng->mat_off[n];
+  /* waves: as many whole pairs as fit three quarters of what the device can give (SEQALIGN_MATS_BUDGET: bytes) */
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-  if(total * 4 > free_b + eng->d_mats.cap - (free_b + eng->d_mats.cap) / 8)
-    return fail(eng, SEQALIGN_ERR_NOMEM, "the matrices of this batch do not fit device memory (12 bytes per cell): submit fewer pairs");
-  TRY(ensure_dev(eng, eng->d_mats, total * 4 + 64));
-  TRY(ensure_dev(eng, eng->d_mat_off, n * 8));
+  size_t budget = (free_b + eng->d_mats.cap) / 4 * 3;
+  const char *benv = getenv("SEQALIGN_MATS_BUDGET");
+  if(benv && atoll(benv) > 0) budget = (size_t)atoll(benv);
+  eng->mat_wave.assign(1, 0);
+  size_t largest = 0;
+  for(size_t i = 0; i < n;) {
+    size_t j = i;
+    while(j < n && (size_t)(eng->mat_off[j + 1] - eng->mat_off[i]) * 4 <= budget) j++;
+    if(j == i) return fail(eng, SEQALIGN_ERR_NOMEM, "the matrices of one pair do not fit device memory (12 bytes per cell)");
+    if((size_t)(eng->mat_off[j] - eng->mat_off[i]) > largest) largest = (size_t)(eng->mat_off[j] - eng->mat_off[i]);
+    eng->mat_wave.push_back(j);
+    i = j;
+  }
+  TRY(ensure_dev(eng, eng->d_mats, largest * 4 + 64));
+  TRY(ensure_dev(eng, eng->d_mat_off, (n + 1) * 8));
   TRY(ensure_dev(eng, eng->d_score, n * 4));
   TRY(ensure_dev(eng, eng->d_counter, COUNTER_BYTES));
-  CU_TRY(cudaMemcpyAsync(eng->d_mat_off.p, eng->mat_off.data(), n * 8, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemsetAsync(eng->d_counter.p, 0, 8, st));
-  MatsArgs M;
-  memset(&M, 0, sizeof(M));
-  M.seq_a = db.a; M.seq_b = db.b; M.off_a = db.off_a; M.off_b = db.off_b;
-  M.npairs = (int64_t)n; M.sp = sp;
-  M.sub = (const int32_t *)eng->d_sub.p; M.lut = (const uint8_t *)eng->d_lut.p;
-  M.mats = (int32_t *)eng->d_mats.p; M.mat_off = (const int64_t *)eng->d_mat_off.p;
-  M.score = (int32_t *)eng->d_score.p;
-  M.counter = (unsigned long long *)eng->d_counter.p;
-  CU_TRY(cudaEventRecord(eng->ev0, st));
+  CU_TRY(cudaMemcpyAsync(eng->d_mat_off.p, eng->mat_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
   /* packed 16-bit prefix scans when every scan value (score + x*|ext|) fits */
   const long shortest = (long)(bm.max_la < bm.max_lb ? bm.max_la : bm.max_lb);
   bool pack = !nw && shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
   /* NW with packed scans: opt-in until it has been timed; every score and scan value must fit int16 */
   if(nw && getenv("SEQALIGN_MATS_NW_PACK") && (long)(bm.max_la + bm.max_lb + 2) * nw_pen - 512L * sp.ext < 32000) pack = true;
-  if(mats_launch(NB, pack, nw, M, eng->ft.ncodes, eng->num_sms, eng->smem_optin, st) != 0)
-    return fail(eng, SEQALIGN_ERR_CUDA, "materialise kernel launch failed");
-  CU_TRY(cudaGetLastError());
+  eng->mat_job.a = db.a; eng->mat_job.b = db.b; eng->mat_job.off_a = db.off_a; eng->mat_job.off_b = db.off_b;
+  eng->mat_job.NB = NB; eng->mat_job.pack = pack; eng->mat_job.nw = nw; eng->mat_job.sp = sp;
+  eng->mat_resident = -1;
+  const int nwaves = (int)eng->mat_wave.size() - 1;
+  CU_TRY(cudaEventRecord(eng->ev0, st));
+  /* every wave once for the scores; the first one again at the end when there are several, so that a reader
+   * going through the pairs in order starts on a resident wave */
+  for(int w = 0; w < nwaves; w++) TRY(run_mats_wave(eng, w, st));
+  if(nwaves > 1) TRY(run_mats_wave(eng, 0, st));
   CU_TRY(cudaEventRecord(eng->ev1, st));
-  eng->last_launches++;
   TRY(ensure_pin(eng, eng->h_res, n * 4));
   CU_TRY(cudaMemcpyAsync(eng->h_res.p, eng->d_score.p, n * 4, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
@@ -1819,7 +1855,15 @@ int seqalign_batch_matrices(seqalign_batch_t *eng, size_t i, int32_t *match, int
   if(eng->mode != SEQALIGN_MODE_MATS || i >= eng->n) return fail(eng, SEQALIGN_ERR_ARG, "no matrices for this index");
   CU_TRY(cudaSetDevice(eng->device));
   const size_t cells = (size_t)(eng->mat_off[i + 1] - eng->mat_off[i]) / 3;
-  const int32_t *src = (const int32_t *)eng->d_mats.p + eng->mat_off[i];
+  /* the wave holding pair i: resident, or made resident by running the kernel over it again (the inputs of
+   * the submit are still on the device; 12 bytes per cell at HBM speed) */
+  int w = eng->mat_resident;
+  if(w < 0 || i < eng->mat_wave[w] || i >= eng->mat_wave[w + 1]) {
+    w = (int)(std::upper_bound(eng->mat_wave.begin(), eng->mat_wave.end(), i) - eng->mat_wave.begin()) - 1;
+    TRY(run_mats_wave(eng, w, eng->stream));
+    CU_TRY(cudaStreamSynchronize(eng->stream));
+  }
+  const int32_t *src = (const int32_t *)eng->d_mats.p + (eng->mat_off[i] - eng->mat_off[eng->mat_wave[w]]);
   CU_TRY(cudaMemcpy(match, src, cells * 4, cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(gap_a, src + cells, cells * 4, cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(gap_b, src + 2 * cells, cells * 4, cudaMemcpyDeviceToHost));

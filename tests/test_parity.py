@@ -546,6 +546,34 @@ def test_batch_matrices(engine, big, name, monkeypatch):
             assert scores[i] == max(em[-1, -1], ega[-1, -1], egb[-1, -1])
 
 
+def test_batch_matrices_in_waves(engine, big, monkeypatch):
+    """MODE_MATS on a batch whose matrices do not fit the device block at once (SEQALIGN_MATS_BUDGET makes
+    that a few KB here): the kernel runs wave by wave, one wave stays resident, seqalign_batch_matrices()
+    re-runs the wave it is asked about -- in order, backwards and at random the matrices are the oracle's"""
+    n = 40 if big else 14
+    sa, sb = ragged_batch(77, n, 60, 60, min_len=1)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    monkeypatch.setenv("SEQALIGN_MATS_BUDGET", str(12 * 61 * 61 * 3))     # about three pairs per wave
+    for algo, is_sw in ((SW, True), (NW, False)):
+        engine.submit(algo, MODE_MATS, sa, sb)
+        launches = engine.last_launches
+        assert launches >= n // 4, launches          # many waves (+ the first one again)
+        scores = engine.scores()
+        order = list(range(n)) + list(range(n - 1, -1, -1)) + [int(v) for v in np.random.default_rng(3).integers(0, n, size=n)]
+        for i in order:
+            m, ga, gb = engine.matrices(i, len(sa[i]), len(sb[i]))
+            rc, em, ega, egb = orc_fill(o, sa[i], sb[i], is_sw)
+            assert rc == 0
+            assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (algo, i)
+            assert scores[i] == (em.max() if is_sw else max(em[-1, -1], ega[-1, -1], egb[-1, -1]))
+    monkeypatch.setenv("SEQALIGN_MATS_BUDGET", "64")
+    with pytest.raises(seqalign.SeqAlignError):                            # one pair alone does not fit
+        engine.submit(SW, MODE_MATS, sa, sb)
+
+
 def test_batch_matrices_rejects_other_shapes(engine):
     """scoring shapes outside the specialised kernel are refused, not approximated"""
     sc = scoring_from_spec(SPECS["no_gaps_a"])
