@@ -85,7 +85,7 @@ def peaks():
 
 def ncu_traffic(kernel_name):
     """dram bytes (read + write) per launch of `kernel_name` on the N=1 workload, from the committed
-    ncu --set full capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that
+    ncu --set full capture (profiles/ncu_traffic.json, taken from the ncu capture it names); None if that
     kernel was not captured"""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))

@@ -106,6 +106,9 @@ struct seqalign_batch {
   std::vector<int64_t> mat_off;            /* batch materialise: first int of pair i's match plane, n+1 entries */
   /* batch materialise in waves: pairs [mat_wave[w], mat_wave[w+1]) fit the device block together; one wave
    * is resident at a time and seqalign_batch_matrices() re-runs the kernel for the wave it is asked about */
+  enum { BUCKET_STREAMS = 4 };
+  cudaStream_t bucket_streams[BUCKET_STREAMS] = {};
+  cudaEvent_t bucket_done[BUCKET_STREAMS] = {}, bucket_ready = nullptr;
   std::vector<size_t> mat_wave;
   int mat_resident = -1;
   struct { const uint8_t *a, *b; const int64_t *off_a, *off_b; int NB; bool pack, nw; ScoreParams sp; } mat_job;
@@ -399,7 +402,8 @@ int launch_general(seqalign_batch *eng, const DevBatch &db, const ScoreParams &s
 /* launch the specialised score kernel of `plan` (tables must be on the device) */
 int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScoreParams &sp, const DevBatch &db,
                       int64_t max_lb, int32_t *d_score, int32_t *d_xend, int32_t *d_yend, cudaStream_t st,
-                      cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0, const int *d_order = nullptr, int64_t order_count = 0)
+                      cudaEvent_t ev0, cudaEvent_t ev1, int slot = 0, const int *d_order = nullptr, int64_t order_count = 0,
+                      const int *d_range = nullptr)
 {
   const size_t nn = plan_elems(sp.ncodes);
   int8_t *d_t8 = (int8_t *)eng->d_tab8.p;
@@ -412,7 +416,7 @@ int launch_fast_score(seqalign_batch *eng, const FastPlan &plan, const ScorePara
   memset(&F, 0, sizeof(F));
   F.seq_a = db.a; F.seq_b = db.b; F.off_a = db.off_a; F.off_b = db.off_b;
   F.npairs = (int64_t)db.n; F.sp = sp;
-  if(d_order) { F.order = d_order; F.npairs = order_count; }   /* a length bucket: pair indices through `order` */
+  if(d_order) { F.order = d_order; F.npairs = order_count; F.range = d_range; }   /* a length bucket: pair indices through `order` */
   F.tab8 = d_t8;
   F.tab32 = d_t32;
   F.lut = (const uint8_t *)eng->d_lut.p;
@@ -541,20 +545,30 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       SA_LAUNCH(bucket_scan_kernel, 1, 256, 0, st, B);
       SA_LAUNCH(bucket_scatter_kernel, bgrid, 256, 0, st, B);
       CU_TRY(cudaGetLastError());
-      int class_start[BUCKET_MAX_CLASSES + 1];
-      CU_TRY(cudaMemcpyAsync(class_start, B.class_start, (B.nclasses + 1) * 4, cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaStreamSynchronize(st));
       eng->last_launches += 3;
-      for(int c = 0; c < B.nclasses; c++) {
-        const int64_t cnt = class_start[c + 1] - class_start[c];
-        if(cnt == 0) continue;
+      /* one launch per shape class, enqueued at once on side streams: the kernels read their ranges from
+       * class_start on the device (an empty class costs one launch that exits), their tails overlap */
+      if(!eng->bucket_streams[0])
+        for(int k = 0; k < seqalign_batch::BUCKET_STREAMS; k++) {
+          CU_TRY(cudaStreamCreateWithFlags(&eng->bucket_streams[k], cudaStreamNonBlocking));
+          CU_TRY(cudaEventCreateWithFlags(&eng->bucket_done[k], cudaEventDisableTiming));
+        }
+      if(!eng->bucket_ready) CU_TRY(cudaEventCreateWithFlags(&eng->bucket_ready, cudaEventDisableTiming));
+      CU_TRY(cudaEventRecord(eng->bucket_ready, st));
+      for(int k = 0; k < seqalign_batch::BUCKET_STREAMS; k++) CU_TRY(cudaStreamWaitEvent(eng->bucket_streams[k], eng->bucket_ready, 0));
+      for(int c = B.nclasses - 1; c >= 0; c--) {   /* widest class first */
         FastPlan cplan;
         const int64_t cla = B.width[c] < bm.max_la ? B.width[c] : bm.max_la;
         if(!fast_plan(eng->scoring, eng->ft, sp, cla, bm.max_lb, want_ends, true, &cplan, false, false) || !cplan.s16 ||
            cplan.s16_ends != plan.s16_ends)
           cplan = plan;   /* the batch's own plan holds every pair */
-        TRY(launch_fast_score(eng, cplan, sp, db, bm.max_lb, d_score, d_xend, d_yend, st, nullptr, nullptr, 1 + c,
-                              B.order + class_start[c], cnt));
+        TRY(launch_fast_score(eng, cplan, sp, db, bm.max_lb, d_score, d_xend, d_yend,
+                              eng->bucket_streams[c % seqalign_batch::BUCKET_STREAMS], nullptr, nullptr, 1 + c, B.order,
+                              (int64_t)db.n, B.class_start + c));
+      }
+      for(int k = 0; k < seqalign_batch::BUCKET_STREAMS; k++) {
+        CU_TRY(cudaEventRecord(eng->bucket_done[k], eng->bucket_streams[k]));
+        CU_TRY(cudaStreamWaitEvent(st, eng->bucket_done[k], 0));
       }
       CU_TRY(cudaEventRecord(ev1, st));
       eng->last_kernel = plan.name;
@@ -1449,6 +1463,11 @@ void seqalign_batch_destroy(seqalign_batch_t *eng)
     if(eng->ev_k1[i]) cudaEventDestroy(eng->ev_k1[i]);
     if(eng->ev_scan[i]) cudaEventDestroy(eng->ev_scan[i]);
   }
+  for(int k = 0; k < seqalign_batch::BUCKET_STREAMS; k++) {
+    if(eng->bucket_streams[k]) cudaStreamDestroy(eng->bucket_streams[k]);
+    if(eng->bucket_done[k]) cudaEventDestroy(eng->bucket_done[k]);
+  }
+  if(eng->bucket_ready) cudaEventDestroy(eng->bucket_ready);
   if(eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   if(eng->scan_stream) cudaStreamDestroy(eng->scan_stream);
   if(eng->ev0) cudaEventDestroy(eng->ev0);

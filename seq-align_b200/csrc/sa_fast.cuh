@@ -62,6 +62,8 @@ struct FastArgs {
   int a_stage, b_stage; /* bytes per pair per stage (multiples of 16) */
   int pad_row;          /* fast16: 1 = the profile has a padding row (couples of different shapes), 0 = uniform batch */
   const int *order;     /* fast16: work item i is pair order[i] (length buckets, see bucket_* below); null = identity */
+  const int *range;     /* fast16 with order: the launch covers order[range[0] .. range[1]) -- read on the device, so
+                           that the launches of all shape classes can be enqueued without waiting for the counts */
 };
 
 struct FastPlan {
@@ -630,15 +632,17 @@ fast16_kernel(const FastArgs A)
    * open == 0 (gap_open = gap_extend = 0): nothing to add and no carry to absorb */
   const unsigned OPENC = open == 0 ? 0u : ((((unsigned)(open - 1) & 0xffffu) << 16) | ((unsigned)open & 0xffffu));
   const unsigned mul_one = (unsigned)A.mul_one;
-  const int64_t nsets = (A.npairs + NP - 1) / NP;
+  const int64_t npairs = A.range ? (int64_t)(A.range[1] - A.range[0]) : A.npairs;
+  const int *order = A.range ? A.order + A.range[0] : A.order;
+  const int64_t nsets = (npairs + NP - 1) / NP;
 
   auto issue = [&](int64_t t, int st) {
     if(lane == 0) {
       uint32_t bytes = 0;
       for(int g = 0; g < NP; g++) {
         const int64_t wi = t * NP + g;
-        if(wi >= A.npairs) break;
-        const int64_t p = A.order ? (int64_t)A.order[wi] : wi;
+        if(wi >= npairs) break;
+        const int64_t p = order ? (int64_t)order[wi] : wi;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;   /* does not fit the plan: skipped, see below */
@@ -648,8 +652,8 @@ fast16_kernel(const FastArgs A)
       mbar_expect_tx(&bar[st], bytes);
       for(int g = 0; g < NP; g++) {
         const int64_t wi = t * NP + g;
-        if(wi >= A.npairs) break;
-        const int64_t p = A.order ? (int64_t)A.order[wi] : wi;
+        if(wi >= npairs) break;
+        const int64_t p = order ? (int64_t)order[wi] : wi;
         const int64_t oa = A.off_a[p], ob = A.off_b[p];
         const int64_t ea = A.off_a[p + 1], eb = A.off_b[p + 1];
         if(ea - oa > G * K || eb - ob > A.max_lb) continue;
@@ -683,9 +687,9 @@ fast16_kernel(const FastArgs A)
      * the running maximum nor the end-cell key needs a mask.  (Uniform batches carry no padding
      * row: only a missing or refused pair has rows past its end there, and its result is not kept.) */
     const int64_t wlo = t * NP + 2 * grp;
-    const bool have_lo = wlo < A.npairs, have_hi = wlo + 1 < A.npairs;
-    const int64_t plo = !have_lo ? 0 : A.order ? (int64_t)A.order[wlo] : wlo;
-    const int64_t phi = !have_hi ? 0 : A.order ? (int64_t)A.order[wlo + 1] : wlo + 1;
+    const bool have_lo = wlo < npairs, have_hi = wlo + 1 < npairs;
+    const int64_t plo = !have_lo ? 0 : order ? (int64_t)order[wlo] : wlo;
+    const int64_t phi = !have_hi ? 0 : order ? (int64_t)order[wlo + 1] : wlo + 1;
     int la_lo = 0, lb_lo = 0, la_hi = 0, lb_hi = 0, sha_lo = 0, shb_lo = 0, sha_hi = 0, shb_hi = 0;
     if(have_lo) {
       const int64_t oa = A.off_a[plo], ob = A.off_b[plo];
@@ -900,7 +904,9 @@ __device__ __forceinline__ int bucket_key(const BucketArgs &B, int64_t p)
   const int la = (int)(B.off_a[p + 1] - B.off_a[p]), lb = (int)(B.off_b[p + 1] - B.off_b[p]);
   int c = 0;
   while(c + 1 < B.nclasses && la > B.width[c]) c++;
-  return c * BUCKET_LB_BINS + imin(lb >> B.shift, BUCKET_LB_BINS - 1);
+  /* longest seq_b first inside a class: the persistent kernel hands out work in this order, and the long jobs
+   * must not be the ones left for the tail */
+  return c * BUCKET_LB_BINS + (BUCKET_LB_BINS - 1 - imin(lb >> B.shift, BUCKET_LB_BINS - 1));
 }
 
 __global__ void bucket_hist_kernel(const BucketArgs B)
