@@ -522,7 +522,9 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     /* reads of different lengths: one launch per shape class over length-sorted pairs (sa_fast.cuh "length
      * buckets") instead of one launch shaped by the longest pair */
     const char *nob = getenv("SEQALIGN_NO_BUCKETS");
-    if(plan.s16 && !uniform && db.n >= 4096 && db.n < ((size_t)1 << 31) && !(nob && nob[0] == '1')) {
+    const char *bmin = getenv("SEQALIGN_BUCKET_MIN");   /* smallest batch that is bucketed (fuzzing lowers it) */
+    const size_t bucket_min = bmin && atoll(bmin) > 0 ? (size_t)atoll(bmin) : 4096;
+    if(plan.s16 && !uniform && db.n >= bucket_min && db.n < ((size_t)1 << 31) && !(nob && nob[0] == '1')) {
       BucketArgs B;
       memset(&B, 0, sizeof(B));
       for(const FastShape &sh : kFast16Shapes) {

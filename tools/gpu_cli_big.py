@@ -14,6 +14,7 @@ from seqalign.synth import synth_batch
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ONLY = sys.argv[3] if len(sys.argv) > 3 else ""        # "sw" / "nw": one tool only
 L = 150
 td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
 path = os.path.join(td, "big.fa")
@@ -51,6 +52,8 @@ def run(tool, args, env):
 
 
 for tool, args in (("smith_waterman", ["--maxhits", "1"]), ("needleman_wunsch", ["--printscores"])):
+    if ONLY and not tool.startswith({"sw": "smith", "nw": "needle"}[ONLY]):
+        continue
     ref_md5 = None
     variants = [("device decoder, 1 GPU", [], {}), ("host reader, 1 GPU", [], {"SEQALIGN_CLI_DECODE": "host"})]
     if G > 1:

@@ -54,8 +54,8 @@ def unsafe(sc, algo):
 
 while time.time() < t_end:
     sc, desc, alpha = model()
-    maxlen = int(([10, 20, 40, 70, 100, 140] if SMALL else [20, 60, 150, 300, 512, 700])[int(rng.integers(0, 6))])
-    n = int(rng.integers(3, 12)) if SMALL else int(rng.integers(3, 400 if maxlen <= 150 else 60))
+    maxlen = int(([10, 20, 40, 70, 100, 140] if SMALL else [20, 60, 150, 300, 512, 700, 1500])[int(rng.integers(0, 6 if SMALL else 7))])
+    n = int(rng.integers(3, 12)) if SMALL else int(rng.integers(3, 400 if maxlen <= 150 else 60 if maxlen <= 700 else 12))
     uniform = rng.random() < 0.15 and maxlen <= 512     # one shape for the whole batch: the packed 16-bit kernel's case
     if uniform:
         la_u, lb_u = int(rng.integers(1, maxlen + 1)), int(rng.integers(1, maxlen + 1))
