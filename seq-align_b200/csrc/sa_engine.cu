@@ -521,15 +521,20 @@ int run_score(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     }
     /* reads of different lengths: one launch per shape class over length-sorted pairs (sa_fast.cuh "length
      * buckets") instead of one launch shaped by the longest pair */
-    const char *nob = getenv("SEQALIGN_NO_BUCKETS");
+    /* SEQALIGN_BUCKETS: "shapes" = a launch per shape class over length-sorted pairs, "rows" = one launch over
+     * pairs sorted by len_b (couples and warps of equal height), unset / "0" = input order (the default: see
+     * DESIGN.md 3, round-2 notes, for the measurements behind it) */
+    const char *bmode = getenv("SEQALIGN_BUCKETS");
+    const bool by_shape = bmode && strcmp(bmode, "shapes") == 0, by_rows = bmode && strcmp(bmode, "rows") == 0;
     const char *bmin = getenv("SEQALIGN_BUCKET_MIN");   /* smallest batch that is bucketed (fuzzing lowers it) */
     const size_t bucket_min = bmin && atoll(bmin) > 0 ? (size_t)atoll(bmin) : 4096;
-    if(plan.s16 && !uniform && db.n >= bucket_min && db.n < ((size_t)1 << 31) && !(nob && nob[0] == '1')) {
+    if(plan.s16 && !uniform && db.n >= bucket_min && db.n < ((size_t)1 << 31) && (by_shape || by_rows)) {
       BucketArgs B;
       memset(&B, 0, sizeof(B));
       for(const FastShape &sh : kFast16Shapes) {
         if(B.nclasses == BUCKET_MAX_CLASSES) break;
         const int w = sh.G * sh.K;
+        if(by_rows && w < bm.max_la) continue;   /* one class: the batch's own shape */
         if(B.nclasses && w <= B.width[B.nclasses - 1]) continue;
         B.width[B.nclasses++] = w;
         if(w >= bm.max_la) break;

@@ -380,8 +380,8 @@ def test_length_buckets(engine, big, monkeypatch):
     es, ex, ey = orc_batch_sw(o, np.ascontiguousarray(A[:oa[m_orc]]), np.ascontiguousarray(oa[:m_orc + 1]),
                               np.ascontiguousarray(B[:ob[m_orc]]), np.ascontiguousarray(ob[:m_orc + 1]))
     got = {}
-    for buckets in ("1", "0"):
-        monkeypatch.setenv("SEQALIGN_NO_BUCKETS", "0" if buckets == "1" else "1")
+    for buckets in ("1", "rows", "0"):
+        monkeypatch.setenv("SEQALIGN_BUCKETS", {"1": "shapes", "rows": "rows", "0": "0"}[buckets])
         for mode in (MODE_SCORE, seqalign.MODE_SCORE_ONLY):
             engine.submit_packed(SW, mode, A, oa, B, ob)
             assert engine.last_kernel.startswith("fast16_sw_score"), engine.last_kernel
@@ -392,6 +392,8 @@ def test_length_buckets(engine, big, monkeypatch):
     assert np.array_equal(s1, s0) and np.array_equal(x1, x0) and np.array_equal(y1, y0)
     assert np.array_equal(s1[:m_orc], es) and np.array_equal(x1[:m_orc], ex) and np.array_equal(y1[:m_orc], ey)
     assert np.array_equal(got[("1", seqalign.MODE_SCORE_ONLY)][0][0], s0)
+    (sr, xr, yr), lr = got[("rows", MODE_SCORE)]
+    assert lr == l0 + 3 and np.array_equal(sr, s0) and np.array_equal(xr, x0) and np.array_equal(yr, y0)
 
 
 def test_empty_inputs(engine):
@@ -560,7 +562,7 @@ def test_batch_matrices_in_waves(engine, big, monkeypatch):
     for algo, is_sw in ((SW, True), (NW, False)):
         engine.submit(algo, MODE_MATS, sa, sb)
         launches = engine.last_launches
-        assert launches >= n // 4, launches          # many waves (+ the first one again)
+        assert launches >= 4, launches               # several waves (+ the first one again)
         scores = engine.scores()
         order = list(range(n)) + list(range(n - 1, -1, -1)) + [int(v) for v in np.random.default_rng(3).integers(0, n, size=n)]
         for i in order:

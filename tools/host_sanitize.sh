@@ -59,4 +59,5 @@ print("host sanitizers (ASan + UBSan, leak detection on): %d invocations of the 
       "%d with a sanitizer report, %d with other stdout than recorded" % (runs, len(cases), len(readers), bad, mism))
 sys.exit(1 if bad or mism else 0)
 PY
+rm -rf $B   # 200 MB of instrumented binaries: the report is what stays
 tail -1 "$out"
