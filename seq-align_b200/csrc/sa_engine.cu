@@ -629,14 +629,15 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
   if(fast_dir && eng->force_mode == 2 && dplan.track == TRACK_TREE) dplan.track = TRACK_COLUMN;
   /* wide pairs / free end gaps (NW): the strip-pipelined kernel, same flag bytes */
   LongPlan lplan;
-  const bool long_dir = !fast_dir && eng->force_mode != 1 &&
-                        long_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, &lplan);
   /* wide pairs trace back through checkpoints and recomputed tiles (0.14 B/cell, fill at score speed);
-   * SEQALIGN_LONG_FLAGS=1 keeps the flag bytes (1 B/cell) */
+   * SEQALIGN_LONG_FLAGS=1 keeps the flag bytes (1 B/cell; NW only: the flag-byte fill does not track SW's best cell) */
   const char *lf_env = getenv("SEQALIGN_LONG_FLAGS");
-  const bool long_ckpt = long_dir && !(lf_env && lf_env[0] == '1');
-  if(long_ckpt) { lplan.ckpt = true; lplan.dir = false; lplan.name = "long_nw_ckpt"; }
-  if(algo == SEQALIGN_SW && !fast_dir) {
+  const bool want_ckpt = !(lf_env && lf_env[0] == '1');
+  const bool long_dir = !fast_dir && eng->force_mode != 1 &&
+                        long_plan(eng->scoring, eng->ft, sp, bm.max_la, bm.max_lb, true, &lplan) && (!lplan.is_sw || want_ckpt);
+  const bool long_ckpt = long_dir && want_ckpt;
+  if(long_ckpt) { lplan.ckpt = true; lplan.dir = false; lplan.name = lplan.is_sw ? "long_sw_ckpt" : "long_nw_ckpt"; }
+  if(algo == SEQALIGN_SW && !fast_dir && !long_dir) {
     TRY(run_score(eng, algo, db, bm, d_score, d_xend, d_yend, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
@@ -814,7 +815,7 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
     c0 = c1;
   }
   eng->last_kernel = fast_dir ? (algo == SEQALIGN_SW ? "fast_sw_dir+walk" : "fast_nw_dir+walk")
-                     : long_ckpt ? "long_nw_ckpt+walk_recompute"
+                     : long_ckpt ? (algo == SEQALIGN_SW ? "long_sw_ckpt+walk_recompute" : "long_nw_ckpt+walk_recompute")
                      : long_dir ? "long_nw_dir+walk"
                                 : (algo == SEQALIGN_SW ? "sw_score+general_dir+walk" : "general_dir+walk");
 
@@ -1086,8 +1087,9 @@ int run_mats(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   /* packed 16-bit prefix scans when every scan value (score + x*|ext|) fits */
   const long shortest = (long)(bm.max_la < bm.max_lb ? bm.max_la : bm.max_lb);
   bool pack = !nw && shortest * (eng->ft.max_sub > 0 ? eng->ft.max_sub : 0) - 512L * sp.ext < 32000 && !getenv("SEQALIGN_MATS_NOPACK");
-  /* NW with packed scans: opt-in until it has been timed; every score and scan value must fit int16 */
-  if(nw && getenv("SEQALIGN_MATS_NW_PACK") && (long)(bm.max_la + bm.max_lb + 2) * nw_pen - 512L * sp.ext < 32000) pack = true;
+  /* NW with packed scans wherever every score and scan value fits int16 (timed on a B200: 69 vs 67 % of the HBM
+   * roofline at 150x150, 73 vs 58 % at 400x400 protein; profiles/mats_nw_r02l.jsonl) */
+  if(nw && !getenv("SEQALIGN_MATS_NOPACK") && (long)(bm.max_la + bm.max_lb + 2) * nw_pen - 512L * sp.ext < 32000) pack = true;
   eng->mat_job.a = db.a; eng->mat_job.b = db.b; eng->mat_job.off_a = db.off_a; eng->mat_job.off_b = db.off_b;
   eng->mat_job.NB = NB; eng->mat_job.pack = pack; eng->mat_job.nw = nw; eng->mat_job.sp = sp;
   eng->mat_resident = -1;

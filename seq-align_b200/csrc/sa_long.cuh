@@ -671,9 +671,10 @@ inline size_t long_smem_bytes(int K, int ncodes, bool prof32)
 inline bool long_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams &sp,
                       int64_t max_la, int64_t max_lb, bool want_dir, LongPlan *plan)
 {
-  /* Smith-Waterman: score and end cell only (traceback of wide local alignments stays with the general
-   * kernel); coordinates and score have to fit the 20 + 20 + 24 bits of the best-cell key */
-  if(sp.is_sw && (want_dir || sp.no_end || max_la >= (1 << 20) || max_lb >= (1 << 20))) return false;
+  /* Smith-Waterman: score and end cell, traceback only through checkpoints (the caller turns want_dir into
+   * plan->ckpt; the flag-byte fill does not track the best cell); coordinates and score have to fit the
+   * 20 + 20 + 24 bits of the best-cell key */
+  if(sp.is_sw && (sp.no_end || max_la >= (1 << 20) || max_lb >= (1 << 20))) return false;
   if(sp.no_gaps_a || sp.no_gaps_b || sp.no_mismatches) return false;
   if(s->gap_open > 0 || s->gap_extend > 0) return false;   /* needs open <= ext <= 0 */
   if(ft.any_unknown) return false;
@@ -734,9 +735,13 @@ inline int long_grid(const LongPlan &plan, int num_sms, int64_t npairs)
 inline int long_launch(const LongPlan &plan, LongArgs L, int grid, cudaStream_t st)
 {
   L.mul_one = 1;
-  if(plan.is_sw)
+  if(plan.is_sw) {
+    if(plan.dir) return -1;   /* SW traces back through checkpoints only */
+    if(plan.ckpt) return plan.prof32 ? long_launch_one<16, true, false, false, true, true>(plan, L, grid, st)
+                                     : long_launch_one<16, false, false, false, true, true>(plan, L, grid, st);
     return plan.prof32 ? long_launch_one<16, true, false, false, false, true>(plan, L, grid, st)
                        : long_launch_one<16, false, false, false, false, true>(plan, L, grid, st);
+  }
   if(plan.ckpt) {
     if(plan.prof32) return plan.noend ? long_launch_one<16, true, false, true, true>(plan, L, grid, st)
                                       : long_launch_one<16, true, false, false, true>(plan, L, grid, st);
@@ -760,7 +765,8 @@ inline int walk_ckpt_launch(const LongPlan &plan, const WalkArgs &W, const int8_
 {
   const size_t smem = walk_ckpt_smem_bytes(W.sp.ncodes, plan.prof32);
   void (*kfn)(const WalkArgs, const int8_t *, const int32_t *, const int);
-  if(plan.prof32) kfn = plan.noend ? walk_ckpt_kernel<false, true, true> : walk_ckpt_kernel<false, false, true>;
+  if(plan.is_sw) kfn = plan.prof32 ? walk_ckpt_kernel<true, false, true> : walk_ckpt_kernel<true, false, false>;
+  else if(plan.prof32) kfn = plan.noend ? walk_ckpt_kernel<false, true, true> : walk_ckpt_kernel<false, false, true>;
   else kfn = plan.noend ? walk_ckpt_kernel<false, true, false> : walk_ckpt_kernel<false, false, false>;
   if(!smem_opt_in(kfn, smem)) return -1;
   SA_LAUNCH(kfn, grid, WK_WARPS * 32, smem, st, W, d_tab8, d_tab32, 1);

@@ -126,9 +126,9 @@ __device__ __forceinline__ void mats_block_head(int j, int lane, int la, const i
  * CS: streaming stores (st.global.cs) -- an experiment, no measurable difference.
  * PACK: the prefix scans of two neighbouring blocks share their shuffles, the two
  * values packed in the halves of a register (needs every scan value in int16).
- * NW + PACK exists but is opt-in (SEQALIGN_MATS_NW_PACK=1): bit-exact in the lane
- * emulator and on the B200 spot check of tools/gpu_mats_nw.py, timed only in the
- * FREE code shape.
+ * NW + PACK is the default wherever every scan value fits (round 2: timed on a B200,
+ * 69 vs 67 % of the HBM roofline at 150x150 DNA, 73 vs 58 % at 400x400 protein;
+ * bit-exact in the GPU fuzz, profiles/fuzz_r02l.json); SEQALIGN_MATS_NOPACK=1 = int32 scans.
  * FREE (NW): free end gaps; a template flag because open / ext as per-row values
  * cost the common rows their loop-invariant x*ext terms (measured: 60 / 43 % of the
  * HBM roofline instead of 67 / 60 %). */

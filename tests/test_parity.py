@@ -353,6 +353,19 @@ def test_wide_pairs_sw_score(engine, big, case):
         s, x, y = engine.ends()
         assert np.array_equal(s, es), (name, np.nonzero(s != es)[0][:8])
         assert np.array_equal(x, ex) and np.array_equal(y, ey), (name, np.nonzero((x != ex) | (y != ey))[0][:8])
+        # the first hit with its traceback: fill with checkpoints + best-cell tracking, recompute walk from the end cell
+        engine.submit_packed(SW, MODE_ALIGN, a, oa, b, ob)
+        assert engine.last_kernel == "long_sw_ckpt+walk_recompute", engine.last_kernel
+        assert np.array_equal(engine.scores(), es)
+        for i in range(len(sa)):
+            nh, hits = orc_sw_hits(o, sa[i], sb[i], 1)
+            al = engine.alignment(i)
+            if nh == 0:
+                assert al is None, (name, i)
+            else:
+                h = hits[0]
+                assert (al.score, al.result_a, al.result_b, al.pos_a, al.pos_b, al.len_a, al.len_b) == \
+                       (h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"], h["len_a"], h["len_b"]), (name, i)
 
 
 def test_length_buckets(engine, big, monkeypatch):
@@ -534,9 +547,11 @@ def test_batch_matrices(engine, big, name, monkeypatch):
             assert rc == 0
             assert np.array_equal(m, em) and np.array_equal(ga, ega) and np.array_equal(gb, egb), (name, nopack, i, a, b)
             assert scores[i] == em.max()
-    for nw_pack in ("", "1"):    # int32 scans (the default) / the opt-in packed 16-bit scans
+    for nw_pack in ("1", ""):    # packed 16-bit scans (the default where every value fits) / int32 scans
         if nw_pack:
-            monkeypatch.setenv("SEQALIGN_MATS_NW_PACK", "1")
+            monkeypatch.delenv("SEQALIGN_MATS_NOPACK", raising=False)
+        else:
+            monkeypatch.setenv("SEQALIGN_MATS_NOPACK", "1")
         engine.submit(NW, MODE_MATS, sa, sb)
         assert engine.last_kernel == ("mats_nw_packed" if nw_pack else "mats_nw")
         scores = engine.scores()

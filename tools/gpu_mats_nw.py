@@ -40,8 +40,8 @@ def batch(tag, scoring, n, L, kind):
     o = orc_from_scoring(scoring)
     for algo, is_sw, nw_pack in ((seqalign.NW, False, ""), (seqalign.NW, False, "1"), (seqalign.SW, True, "")):
         # the opt-in packed 16-bit scans of the NW rows beside the default int32 ones
-        if nw_pack: os.environ["SEQALIGN_MATS_NW_PACK"] = "1"
-        else: os.environ.pop("SEQALIGN_MATS_NW_PACK", None)
+        if nw_pack: os.environ.pop("SEQALIGN_MATS_NOPACK", None)
+        else: os.environ["SEQALIGN_MATS_NOPACK"] = "1"
         best = 1e9
         for r in range(3):
             eng.submit_packed(algo, seqalign.MODE_MATS, a, oa, b, ob)
