@@ -209,11 +209,11 @@ def test_device_decoder_chunked(reads, kind):
 
 
 @pytest.mark.parity
-def test_decoded_reads_align_in_place(reads, engine):
+def test_decoded_reads_align_in_place(reads, engine, big):
     """decode -> seqalign_batch_submit_reads: the DP kernels read the decoder's packed buffers in HBM;
     scores and strings equal the host-packed submit of the same records"""
     from helpers import ragged_batch, scoring_from_spec, SPECS
-    sa, sb = ragged_batch(21, 64, 140, 140, min_len=1)
+    sa, sb = ragged_batch(21, 64 if big else 20, 140 if big else 50, 140 if big else 50, min_len=1)
     text = b"".join(b">a%d\n%s\n>b%d\n%s\n" % (i, sa[i], i, sb[i]) for i in range(len(sa)))
     assert reads.decode(text, final=True, split=True)
     n = reads.records // 2
