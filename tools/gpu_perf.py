@@ -72,5 +72,8 @@ align("dna150 NW align 20k", "nw_default", seqalign.NW, A[:150 * n], OA[:n + 1],
 align("dna150 NW align 20k tiled walk", "nw_default", seqalign.NW, A[:150 * n], OA[:n + 1], B[:150 * n], OB[:n + 1], n * 22500.0, walk="tiled")
 align("prot400 SW align 50k (config 4), thread walk", "blosum62", seqalign.SW, PA, POA, PB, POB, c4, walk="thread")
 align("prot400 SW align 50k (config 4), tiled walk", "blosum62", seqalign.SW, PA, POA, PB, POB, c4, walk="tiled")
+# wide SW pairs with traceback (round 2: checkpoints + recompute walk; was the general kernel)
+a, oa, b, ob = synthetic_batch(2040, 500, 2000, 2000)
+align("dna2000 SW align 500 (wide)", "sw_cli", seqalign.SW, a, oa, b, ob, 500 * 2000.0 * 2000.0)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gpu_perf.json"), "w"), indent=1)
