@@ -774,7 +774,8 @@ int run_align(seqalign_batch *eng, int algo, const DevBatch &db, const BatchMeta
       int8_t *w_t8 = nullptr;
       int32_t *w_t32 = nullptr;
       TRY(upload_plan_tables(eng, lplan.tab8, lplan.tab32, &w_t8, &w_t32, st));
-      if(walk_ckpt_launch(lplan, W, w_t8, w_t32, walk_ckpt_grid(eng->num_sms, (int64_t)m), st) != 0)
+      if(walk_ckpt_launch(lplan, W, w_t8, w_t32,
+                          walk_ckpt_grid(eng->num_sms, (int64_t)m, walk_ckpt_smem_bytes(sp.ncodes, lplan.prof32)), st) != 0)
         return fail(eng, SEQALIGN_ERR_CUDA, "recompute walk launch failed");
     } else if(tiled) {
       int wgrid = (int)((m + WT_WARPS - 1) / WT_WARPS);

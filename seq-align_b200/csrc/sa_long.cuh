@@ -61,7 +61,10 @@ constexpr int LONG_WARPS = 8;
 constexpr int LONG_NEG = -(1 << 29);   /* "minus infinity" of the NW borders: far from INT_MIN, below every real value */
 constexpr int LONG_K = 16;             /* columns per lane */
 constexpr int LONG_STRIP = 32 * LONG_K;
-constexpr int LONG_CK_ROWS = 64;       /* CKPT: a row checkpoint every this many rows */
+#ifndef SA_CK_ROWS
+#define SA_CK_ROWS 64
+#endif
+constexpr int LONG_CK_ROWS = SA_CK_ROWS;   /* CKPT: a row checkpoint every this many rows (a power of two) */
 
 /* CKPT: bytes of one pair's trace region, [strip edges | row checkpoints]:
  *   edge[s][y]  int2 (H', GB) of cell (x = (s+1)*STRIP, y), s < nstrips-1, y in [0, lb]
@@ -773,11 +776,15 @@ inline int walk_ckpt_launch(const LongPlan &plan, const WalkArgs &W, const int8_
   return 0;
 }
 
-/* CTAs of the recompute walk: 2 warps and ~70 KB of shared memory each, three per SM */
-inline int walk_ckpt_grid(int num_sms, int64_t npairs)
+/* CTAs of the recompute walk: 2 warps and their two flag tiles (LONG_CK_ROWS x 512 bytes each) in shared
+ * memory; as many per SM as that leaves room for (64 rows: three) */
+inline int walk_ckpt_grid(int num_sms, int64_t npairs, size_t smem = 70 * 1024)
 {
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if(per_sm < 1) per_sm = 1;
+  if(per_sm > 16) per_sm = 16;
   int64_t g = (npairs + WK_WARPS - 1) / WK_WARPS;
-  if(g > (int64_t)num_sms * 3) g = (int64_t)num_sms * 3;
+  if(g > (int64_t)num_sms * per_sm) g = (int64_t)num_sms * per_sm;
   return g < 1 ? 1 : (int)g;
 }
 
