@@ -178,10 +178,11 @@ static void copy_alignment(alignment_t *dst, const alignment_t *src)
 static int build_device_list(sw_aligner_t *sw, size_t cap)
 {
   const aligner_t *al = &sw->aligner;
+  if(cap > 4096) return 0;   /* beyond the engine's per-pair list (seqalign_batch_set_hit_limits): the host iteration goes on from here */
   seqalign_batch_t *eng = sa_host_engine();
   const size_t la = al->score_width - 1, lb = al->score_height - 1;
   seqalign_batch_set_scoring(eng, al->scoring);
-  seqalign_batch_set_hit_limits(eng, cap, 1);
+  if(seqalign_batch_set_hit_limits(eng, cap, 1) != SEQALIGN_OK) return 0;
   const int rc = seqalign_batch_submit(eng, SEQALIGN_SW, SEQALIGN_MODE_HITS, &al->seq_a, &la, &al->seq_b, &lb, 1);
   if(rc == SEQALIGN_ERR_ARG || rc == SEQALIGN_ERR_NOMEM) return 0;
   sa_host_check(eng, rc);

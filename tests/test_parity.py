@@ -411,6 +411,22 @@ def test_length_buckets(engine, big, monkeypatch):
     assert lr == l0 + 3 and np.array_equal(sr, s0) and np.array_equal(xr, x0) and np.array_equal(yr, y0)
 
 
+def test_classic_sw_fetch_loop_from_device_list(engine):
+    """smith_waterman_align + fetch until exhausted: the first hit from align mode, the rest from the device's
+    multi-hit list, rebuilt eightfold larger each time the caller reads past its end (8 -> 64 -> 512);
+    restriction shapes iterate on the host.  Every hit equals the oracle's, in order."""
+    rng = np.random.default_rng(23)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    a = bytes(letters[rng.integers(0, 4, size=90)]); b = bytes(letters[rng.integers(0, 4, size=80)])
+    for name in ("sw_cli", "no_gaps_a", "no_mismatch"):
+        sc = scoring_from_spec(SPECS[name])
+        hits = seqalign.smith_waterman(a, b, sc)
+        n, want = orc_sw_hits(orc_from_scoring(sc), a, b, 4000)
+        assert len(hits) == n and (name != "sw_cli" or n > 64), (name, len(hits), n)
+        assert [(h.score, h.result_a, h.result_b, h.pos_a, h.pos_b, h.len_a, h.len_b) for h in hits] == \
+               [(w["score"], w["result_a"], w["result_b"], w["pos_a"], w["pos_b"], w["len_a"], w["len_b"]) for w in want], name
+
+
 def test_empty_inputs(engine):
     sc = scoring_from_spec(SPECS["nw_default"])
     engine.set_scoring(sc)
