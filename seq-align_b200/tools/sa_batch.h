@@ -466,6 +466,8 @@ static inline int sa_for_each_batch_dev(const char *path1, const char *path2, in
 static inline void sa_read_input(const char *path1, const char *path2, int interactive, int device, size_t max_pairs,
                                  int want_names, sa_pairs *pairs, void (*flush)(sa_pairs *, sa_reader *))
 {
+  const char *bp = getenv("SEQALIGN_CLI_BATCH_PAIRS");   /* pairs per engine submit (default: the tool's own) */
+  if(bp && atol(bp) > 0) max_pairs = (size_t)atol(bp);
   const char *mode = getenv("SEQALIGN_CLI_DECODE");
   const int dev_ok = !interactive && strcmp(path1, "-") != 0 && (!path2 || strcmp(path2, "-") != 0) &&
                      !(mode && strcmp(mode, "host") == 0);

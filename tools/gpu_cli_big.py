@@ -58,6 +58,9 @@ for tool, args in (("smith_waterman", ["--maxhits", "1"]), ("needleman_wunsch", 
     variants = [("device decoder, 1 GPU", [], {}), ("host reader, 1 GPU", [], {"SEQALIGN_CLI_DECODE": "host"})]
     if G > 1:
         variants += [("device decoder, %d GPUs" % G, ["--gpus", str(G)], {}), ("host reader, %d GPUs" % G, ["--gpus", str(G)], {"SEQALIGN_CLI_DECODE": "host"})]
+    # CLI_BIG_BATCHES=16384,65536,262144: the same run with other numbers of pairs per engine submit
+    for bsz in [x for x in os.environ.get("CLI_BIG_BATCHES", "").split(",") if x]:
+        variants.append(("device decoder, 1 GPU, %s pairs per submit" % bsz, [], {"SEQALIGN_CLI_BATCH_PAIRS": bsz}))
     run(tool, args, {})   # page cache, driver
     for name, extra, env in variants:
         dt, md5, nbytes, phases = run(tool, extra + args, env)
