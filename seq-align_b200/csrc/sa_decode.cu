@@ -326,7 +326,11 @@ __global__ void __launch_bounds__(DEC_TPB) emit_kernel(const DecArgs A)
       /* a plain record has no name; a header's span is its name */
       A.name_pos[r] = (kind & LK_DATA) ? s : cs;
       A.name_len[r] = (kind & LK_DATA) ? 0 : ce - cs;
-      (side ? A.off1 : A.off0)[A.split ? (r >> 1) : r] = (int64_t)at;
+      /* (pointer and index picked in separate statements: gcc 13 with -fsanitize=undefined lost the index of
+       * `(side ? A.off1 : A.off0)[i]` for side 0 in the emulator build) */
+      int64_t *offs = side ? A.off1 : A.off0;
+      const int slot = A.split ? (r >> 1) : r;
+      offs[slot] = (int64_t)at;
     }
     /* every lane takes part (warp-wide shuffles inside); lines without data copy nothing */
     const int len = (kind & LK_DATA) ? ce - cs : 0;
