@@ -588,10 +588,12 @@ __device__ __forceinline__ void fast16_load_rows(unsigned pl, unsigned ph, unsig
  * per cell.  A larger key is a higher score or, at equal score, a smaller
  * column; a later row only replaces an equal score if its column is smaller:
  * that is (score desc, x asc, y asc), smith_waterman.c:71-86. */
-template <int G, int K, bool ENDS>
+template <int G, int K, bool ENDS, bool ORD = false>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast16_kernel(const FastArgs A)
 {
+  /* ORD: pair indices come through A.order / A.range (length buckets).  Its own instantiation: as a run-time
+   * option the indirection cost the plain kernel 16 registers and 3 % of the headline number (measured). */
   constexpr int NG = 32 / G;              /* couples per warp */
   constexpr int NP = 2 * NG;              /* pairs per warp set */
   constexpr int KW = (K + 3) / 4;
@@ -632,8 +634,8 @@ fast16_kernel(const FastArgs A)
    * open == 0 (gap_open = gap_extend = 0): nothing to add and no carry to absorb */
   const unsigned OPENC = open == 0 ? 0u : ((((unsigned)(open - 1) & 0xffffu) << 16) | ((unsigned)open & 0xffffu));
   const unsigned mul_one = (unsigned)A.mul_one;
-  const int64_t npairs = A.range ? (int64_t)(A.range[1] - A.range[0]) : A.npairs;
-  const int *order = A.range ? A.order + A.range[0] : A.order;
+  const int64_t npairs = (ORD && A.range) ? (int64_t)(A.range[1] - A.range[0]) : A.npairs;
+  const int *order = !ORD ? nullptr : A.range ? A.order + A.range[0] : A.order;
   const int64_t nsets = (npairs + NP - 1) / NP;
 
   auto issue = [&](int64_t t, int st) {
@@ -1129,7 +1131,8 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
 #define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
-    void (*kfn)(const FastArgs) = plan.s16_ends ? fast16_kernel<g, k, true> : fast16_kernel<g, k, false>; \
+    void (*kfn)(const FastArgs) = F.order ? (plan.s16_ends ? fast16_kernel<g, k, true, true> : fast16_kernel<g, k, false, true>) \
+                                          : (plan.s16_ends ? fast16_kernel<g, k, true> : fast16_kernel<g, k, false>); \
     /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
     const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
     const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \

@@ -261,7 +261,9 @@ static inline void sa_main_destroy(void)
 }
 
 /* a batch is full at this many pairs or bytes of sequence */
-#define SA_BATCH_MAX_PAIRS ((size_t)1 << 16)
+/* 262,144 pairs per submit: the per-submit costs (synchronisations, table checks, small copies) were visible at
+ * 65,536 -- 2 M pairs of 150 bp: align phase 0.70-0.98 s against 0.55-0.66 s (profiles/cli_batches_r02p.jsonl) */
+#define SA_BATCH_MAX_PAIRS ((size_t)1 << 18)
 #define SA_BATCH_MAX_BYTES ((size_t)256 << 20)
 
 /* Read every pair of one input (path2 == NULL: consecutive records of path1)

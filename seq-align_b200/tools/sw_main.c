@@ -321,7 +321,10 @@ int main(int argc, char **argv)
   for(size_t i = 0; i < opt.nfiles; i++) {
     const char *f1 = opt.files[i].path1, *f2 = opt.files[i].path2;
     if(f1 && *f1 == '\0' && !f2) { wait_on_keystroke = 1; f1 = "-"; }
-    sa_read_input(f1, f2, opt.interactive, 0, SW_BATCH_PAIRS, opt.print_fasta, &pairs, flush_pairs);
+    /* --maxhits 1 runs in align mode (one string pair per pair): large batches; the multi-hit mode reserves
+     * HIT_CAP string pairs and 16 bytes of candidate keys per cell and stays at SW_BATCH_PAIRS */
+    const size_t batch_pairs = (opt.max_hits_set && opt.max_hits == 1 && !opt.print_matrices) ? SA_BATCH_MAX_PAIRS : SW_BATCH_PAIRS;
+    sa_read_input(f1, f2, opt.interactive, 0, batch_pairs, opt.print_fasta, &pairs, flush_pairs);
   }
   sa_pairs_free(&pairs);
   smith_waterman_free(sw);
