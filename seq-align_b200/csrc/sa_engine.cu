@@ -969,9 +969,17 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     if(sgrid > eng->num_sms * 6) sgrid = eng->num_sms * 6;
     SA_LAUNCH(hits_sort_kernel, sgrid, HITS_WARPS * 32, 0, st, H);
     CU_TRY(cudaGetLastError());
-    int wgrid = (int)((m + HITS_WALK_WARPS - 1) / HITS_WALK_WARPS);
-    if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;   /* a warp per pair, 64 warps per SM */
-    SA_LAUNCH(hits_walk_kernel, wgrid, HITS_WALK_WARPS * 32, 0, st, H);
+    /* SEQALIGN_HITS_WALK=warp: a warp per pair (round 1); default: a thread per pair, flat state machine */
+    const char *hw_env = getenv("SEQALIGN_HITS_WALK");
+    if(hw_env && strcmp(hw_env, "warp") == 0) {
+      int wgrid = (int)((m + HITS_WALK_WARPS - 1) / HITS_WALK_WARPS);
+      if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;   /* a warp per pair, 64 warps per SM */
+      SA_LAUNCH(hits_walk_kernel, wgrid, HITS_WALK_WARPS * 32, 0, st, H);
+    } else {
+      int wgrid = (int)((m + HITS_FLAT_THREADS - 1) / HITS_FLAT_THREADS);
+      if(wgrid > eng->num_sms * 16) wgrid = eng->num_sms * 16;
+      SA_LAUNCH(hits_walk_flat_kernel, wgrid, HITS_FLAT_THREADS, 0, st, H);
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(eng->ev1, st));
     eng->last_launches += 2;

@@ -296,6 +296,114 @@ hits_walk_kernel(const HitsArgs A)
   }
 }
 
+/* The same iteration with one THREAD per pair, written as a flat state machine: every pass of the one loop
+ * does a scan step (look at the next candidate) or a walk step (one cell of the current walk) for the
+ * thread's pair, so the 32 pairs of a warp share every instruction they issue instead of one pair owning the
+ * warp.  ncu on the warp-per-pair kernel above showed what that costs: 69 % ALU-pipe and 72 % issue-slot
+ * utilisation spent on 32 lanes computing one walk (profiles/ncu_r02p_all_kernels.csv).  The first
+ * thread-per-pair version of round 1 lost to divergence because its nested loops (candidates / walk) let the
+ * lanes of a warp wait for each other; here a lane that finishes a walk goes straight on with its next
+ * candidate in the same loop.  Marked candidates are skipped one per pass instead of 32 at a time -- a
+ * few instructions each.  Same rules, same outputs as hits_walk_kernel (smith_waterman.c:165-277). */
+constexpr int HITS_FLAT_THREADS = 64;   /* small CTAs: the pairs of a batch spread over every SM */
+
+__global__ void __launch_bounds__(HITS_FLAT_THREADS)
+hits_walk_flat_kernel(const HitsArgs A)
+{
+  const ScoreParams &sp = A.sp;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  enum { PH_LOAD, PH_SCAN, PH_WALK };
+  int phase = PH_LOAD;
+  /* the pair */
+  const uint8_t *a = nullptr, *b = nullptr, *dirp = nullptr;
+  unsigned *mask = nullptr;
+  const unsigned long long *keys = nullptr;
+  uint8_t *ra = nullptr, *rb = nullptr;
+  int64_t stride = 0;
+  int n = 0, cap = 0, c = 0, nh = 0;
+  /* the walk */
+  int xe = 0, ye = 0, score = 0, x = 0, y = 0, st = ST_M, cs = 0, len = 0;
+
+  while(p < A.npairs) {
+    if(phase == PH_LOAD) {
+      const int64_t oa = A.off_a[p], ob = A.off_b[p];
+      const int la = (int)(A.off_a[p + 1] - oa), lb = (int)(A.off_b[p + 1] - ob);
+      a = A.seq_a + oa; b = A.seq_b + ob;
+      stride = dir_stride(la);
+      dirp = A.dir + A.dir_off[p];
+      mask = A.mask + A.dir_off[p] / 32;
+      keys = (A.which[p] ? A.keys1 : A.keys0) + A.dir_off[p];
+      n = A.ncand[p];
+      cap = la + lb;
+      c = 0; nh = 0;
+      phase = PH_SCAN;
+    }
+    if(phase == PH_SCAN) {
+      if(c >= n || nh >= A.max_hits) {
+        A.nhits[p] = nh;
+        p += nthreads;
+        phase = PH_LOAD;
+        continue;
+      }
+      /* next candidate whose end cell is not marked yet (smith_waterman.c:270) */
+      const unsigned long long key = keys[c++];
+      xe = (int)((key >> 16) & 0xffffu); ye = (int)(key & 0xffffu);
+      const int64_t cell = (int64_t)(ye - 1) * stride + (xe - 1);
+      if((mask[cell >> 5] >> (cell & 31)) & 1u) continue;
+      score = (int)(key >> 32);
+      ra = A.out_a + A.out_off[p] + (int64_t)nh * cap;
+      rb = A.out_b + A.out_off[p] + (int64_t)nh * cap;
+      x = xe; y = ye; st = ST_M; cs = score; len = 0;
+      phase = PH_WALK;
+    }
+    /* one cell of the walk (smith_waterman.c:187-199 and 217-244 in one pass: the strings are written
+     * speculatively and only kept if the walk completes) */
+    int64_t cell = 0;
+    if(x != 0 && y != 0) {
+      cell = (int64_t)(y - 1) * stride + (x - 1);
+      const unsigned word = mask[cell >> 5];
+      if((word >> (cell & 31)) & 1u) { phase = PH_SCAN; continue; }   /* ran into a used cell: no hit, its marks stay */
+      mask[cell >> 5] = word | (1u << (cell & 31));
+    }
+    if(cs == 0) {
+      int32_t *r = A.rec + ((int64_t)p * A.max_hits + nh) * 8;
+      r[0] = score; r[1] = x; r[2] = y; r[3] = xe - x; r[4] = ye - y; r[5] = len; r[6] = cap - len; r[7] = 0;
+      nh++;
+      phase = PH_SCAN;
+      continue;
+    }
+    len++;
+    const unsigned f = dirp[cell];
+    const unsigned g_diag = (x > 1 && y > 1) ? dirp[cell - stride - 1] : 0u;
+    const unsigned g_up = y > 1 ? dirp[cell - stride] : 0u;
+    const unsigned g_left = x > 1 ? dirp[cell - 1] : 0u;
+    const unsigned ca = a[x - 1], cb = b[y - 1];
+    ra[cap - len] = st == ST_GA ? '-' : (uint8_t)ca;
+    rb[cap - len] = st == ST_GB ? '-' : (uint8_t)cb;
+    /* predecessor state from the equality flags (as walk_kernel, fmt 1) */
+    int code;
+    if(st == ST_M) {
+      if(x == 1 || y == 1) code = ST_M;
+      else code = !(g_diag & 1) ? ST_GA : !(g_diag & 2) ? ST_GB : ST_M;
+    } else if(st == ST_GA) {
+      if(!(f & 4)) code = ST_GA;
+      else if(y == 1) code = ST_M;
+      else code = !(g_up & 2) ? ST_GB : ST_M;
+    } else {
+      if(x == 1) code = ST_M;
+      else code = (!(g_left & 1) && !(f & 16)) ? ST_GA : !(f & 8) ? ST_GB : ST_M;
+    }
+    int pen;
+    if(st == ST_M) { pen = A.sub[A.lut[cb] * sp.ncodes + A.lut[ca]]; x--; y--; }
+    else if(st == ST_GA) { pen = code == ST_GA ? sp.ext : sp.open; y--; }
+    else { pen = code == ST_GB ? sp.ext : sp.open; x--; }
+    cs -= pen;
+    if(x == 0 || y == 0) cs = 0;
+    st = code;
+  }
+}
+
 } // namespace sa
 
 #endif
