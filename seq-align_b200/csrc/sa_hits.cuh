@@ -346,25 +346,11 @@ hits_walk_flat_kernel(const HitsArgs A)
         phase = PH_LOAD;
         continue;
       }
-      /* next candidate whose end cell is not marked yet (smith_waterman.c:270).  Four candidates are
-       * looked at per pass -- their keys and mask words are independent loads, so the two dependent round
-       * trips of a candidate are paid once per four; most candidates are marked already and only get
-       * skipped.  Nothing marks cells between two scan passes, so taking the first unmarked of the four
-       * is what looking at them one by one would do; the ones behind it are looked at again after its walk. */
-      unsigned long long k4[4];
-      bool open4[4];
-#pragma unroll
-      for(int q = 0; q < 4; q++) k4[q] = c + q < n ? keys[c + q] : 0ull;
-#pragma unroll
-      for(int q = 0; q < 4; q++) {
-        const int64_t cq = (int64_t)((int)(k4[q] & 0xffffu) - 1) * stride + ((int)((k4[q] >> 16) & 0xffffu) - 1);
-        open4[q] = c + q < n && !((mask[cq >> 5] >> (cq & 31)) & 1u);
-      }
-      const int j = open4[0] ? 0 : open4[1] ? 1 : open4[2] ? 2 : open4[3] ? 3 : -1;
-      if(j < 0) { c += 4; continue; }
-      const unsigned long long key = j == 0 ? k4[0] : j == 1 ? k4[1] : j == 2 ? k4[2] : k4[3];
-      c += j + 1;
+      /* next candidate whose end cell is not marked yet (smith_waterman.c:270) */
+      const unsigned long long key = keys[c++];
       xe = (int)((key >> 16) & 0xffffu); ye = (int)(key & 0xffffu);
+      const int64_t cell = (int64_t)(ye - 1) * stride + (xe - 1);
+      if((mask[cell >> 5] >> (cell & 31)) & 1u) continue;
       score = (int)(key >> 32);
       ra = A.out_a + A.out_off[p] + (int64_t)nh * cap;
       rb = A.out_b + A.out_off[p] + (int64_t)nh * cap;
