@@ -16,6 +16,7 @@
  */
 #define _GNU_SOURCE
 #include <stdio.h>
+#include <stdio_ext.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -300,6 +301,12 @@ int main(int argc, char **argv)
   scoring.gap_extend = -1;
   sa_cli_parse(argc, argv, &scoring, SA_TOOL_SW, &opt);
 
+  if(!opt.interactive) {
+    /* millions of short writes per run: a 1 MB buffer and no per-call locking (the helper thread that brings up
+     * the engine never touches stdout); --stdin keeps line-by-line answers */
+    setvbuf(stdout, NULL, _IOFBF, 1 << 20);
+    __fsetlocking(stdout, FSETLOCKING_BYCALLER);
+  }
   sa_t_start = sa_now();
   sa_gpus = opt.gpus_set ? opt.gpus : 1;
   sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
