@@ -76,6 +76,7 @@ struct FastPlan {
   bool prof32 = false;
   bool s16 = false;   /* two pairs per register (fast16_kernel) */
   bool s16_ends = false; /* ... with the SW end cell tracked in 16-bit keys */
+  bool s16_rel = false;  /* ... those keys relative to the lane's row input (scores of 1024 - |open| and more) */
   bool dir = false;   /* also write traceback flag bytes */
   bool hits = false;  /* ... and int16 match scores (multi-hit stage) */
   size_t smem = 0;
@@ -588,7 +589,7 @@ __device__ __forceinline__ void fast16_load_rows(unsigned pl, unsigned ph, unsig
  * per cell.  A larger key is a higher score or, at equal score, a smaller
  * column; a later row only replaces an equal score if its column is smaller:
  * that is (score desc, x asc, y asc), smith_waterman.c:71-86. */
-template <int G, int K, bool ENDS, bool ORD = false>
+template <int G, int K, int ENDS, bool ORD = false>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 fast16_kernel(const FastArgs A)
 {
@@ -754,7 +755,8 @@ fast16_kernel(const FastArgs A)
     unsigned hp[K], ga[K];
 #pragma unroll
     for(int j = 0; j < K; j++) { hp[j] = 0; ga[j] = BB; }
-    unsigned best = ENDS ? BB * 32u : BB, hd = 0, out_h = 0, out_gb = BB;
+    unsigned best = ENDS == 1 ? BB * 32u : BB, hd = 0, out_h = 0, out_gb = BB;
+    unsigned bk_lo = B * 32u, bk_hi = B * 32u;   /* ENDS == 2: the lane's best (M* x 32 + 31 - j), one word per half */
     int ylo = 0, yhi = 0;
     const unsigned mul_key = (unsigned)A.mul_key;
 
@@ -796,6 +798,10 @@ fast16_kernel(const FastArgs A)
           fast16_load_rows<KW, 1>(pl, ph, wl, wh, dsm);
         }
         unsigned d = hd, kprev = ENDS ? 0u : BB, rowkey = 0;
+        /* ENDS == 2: keys relative to the value entering the lane on this row, (M* - H'*_in + 512) x 32 + (31 - j).
+         * 32-bit arithmetic on the packed words is exact because every half of the result is in [0, 1023]
+         * (fast_plan checks the bound) -- a negative half of relc borrows from its neighbour and the sum pays it back. */
+        const unsigned relc = 0x02000200u - hl_in;
 #pragma unroll
         for(int j = 0; j < K; j++) {
           const unsigned sub = pack_sub2_dyn(wl[j / 4], wh[j / 4], j & 3);
@@ -804,7 +810,11 @@ fast16_kernel(const FastArgs A)
           gb = addmax_s16x2(gb, EXT2, hl);
           const unsigned h = max3_s16x2(m, ga[j], gb);
           if constexpr(ENDS) {
-            const unsigned kk = m * mul_key + (unsigned)((31 - j) * 0x10001);   /* both halves: M* x 32 + (31 - j) */
+            const unsigned mk = ENDS == 2 ? m * mul_one + relc : m;
+#ifdef SA_EMU
+            if(ENDS == 2 && ((mk & 0xffffu) > 1023u || (mk >> 16) > 1023u)) __builtin_trap();   /* fast_plan's bound */
+#endif
+            const unsigned kk = mk * mul_key + (unsigned)((31 - j) * 0x10001);   /* both halves: M* x 32 + (31 - j) */
             if(j & 1) rowkey = max3_s16x2(rowkey, kprev, kk);
             else if(j == K - 1) rowkey = max3_s16x2(rowkey, kk, kk);
             kprev = kk;
@@ -817,7 +827,16 @@ fast16_kernel(const FastArgs A)
           hl = h * mul_one + OPENC;   /* packed H* + open, see header */
           hp[j] = hl;
         }
-        if constexpr(ENDS) {
+        if constexpr(ENDS == 2) {
+          /* once per row: the row's best cell back to an absolute score (the key's order inside one row is
+           * the order of the scores), then the same (score x 32 + 31 - j) comparison as below in full words */
+          const unsigned rowm = ((rowkey >> 5) & 0x07ff07ffu) - relc;
+          const unsigned k_lo = (rowm & 0xffffu) * mul_key + (rowkey & 31u);
+          const unsigned k_hi = (rowm >> 16) * mul_key + ((rowkey >> 16) & 31u);
+          const int y = s - lig + 1;
+          if(k_lo > bk_lo) { bk_lo = k_lo; ylo = y; }
+          if(k_hi > bk_hi) { bk_hi = k_hi; yhi = y; }
+        } else if constexpr(ENDS == 1) {
           /* once per row: where the lane's best key grew, this row is its row */
           const unsigned nb = max3_s16x2(best, rowkey, rowkey);
           const unsigned grew = nb ^ best;
@@ -837,7 +856,7 @@ fast16_kernel(const FastArgs A)
       int sv[2], sx[2], sy[2];
 #pragma unroll
       for(int hsel = 0; hsel < 2; hsel++) {
-        const int key = (int)((best >> (16 * hsel)) & 0xffffu);
+        const int key = ENDS == 2 ? (int)(hsel ? bk_hi : bk_lo) : (int)((best >> (16 * hsel)) & 0xffffu);
         sv[hsel] = (key >> 5) - (int)B;
         sx[hsel] = sv[hsel] > 0 ? xf + 31 - (key & 31) : 0;
         sy[hsel] = sv[hsel] > 0 ? (hsel ? yhi : ylo) : 0;
@@ -954,7 +973,7 @@ struct FastShape { int G, K; };
 static const FastShape kFastShapes[] = {
     {8, 8}, {8, 12}, {8, 16}, {8, 20}, {16, 12}, {16, 16}, {32, 10}, {32, 12}, {32, 16}};
 static const FastShape kFast16Shapes[] = {
-    {8, 8}, {8, 12}, {8, 13}, {8, 16}, {8, 19}, {8, 20}, {16, 12}, {16, 16}, {16, 19}, {32, 10}, {32, 12}, {32, 16}};
+    {8, 8}, {8, 12}, {8, 13}, {8, 16}, {8, 19}, {8, 20}, {16, 12}, {16, 16}, {16, 19}, {32, 10}, {32, 12}, {32, 13}, {32, 16}};
 
 inline size_t fast_smem_bytes(int G, int K, int ncodes, bool prof32, int a_stage, int b_stage, bool dir = false)
 {
@@ -1001,17 +1020,33 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   /* packed 16-bit kernel: SW score only, one shape for the whole batch, and
    * every biased value (score + |open|) inside int16 */
   const long best_biased = shortest * (ft.max_sub > 0 ? ft.max_sub : 0) - sp.open;   /* largest M + B */
-  /* ... with the end cell: the 16-bit key is (M + B) x 32 + column, so M + B must stay below 1024 */
-  const bool s16_ends = want_ends && best_biased < 1024 && max_lb <= 32767;
+  /* ... with the end cell: the 16-bit key is (M + B) x 32 + column, so M + B must stay below 1024; larger
+   * scores take keys relative to the lane's input of the row (ends_mode 2), bounded further down */
+  const int ends_mode = !want_ends || max_lb > 32767 ? 0 : best_biased < 1024 ? 1 : 2;
   /* (the packed kernel takes couples of different shapes: padding code for the shorter one) */
-  const bool s16 = sp.is_sw && (!want_ends || s16_ends) && !want_dir && allow_s16 && fits8 &&
-                   best_biased < 32000 && sp.open > -16000 && ft.min_sub > -16000;
+  bool s16 = sp.is_sw && (!want_ends || ends_mode) && !want_dir && allow_s16 && fits8 &&
+             best_biased < 32000 && sp.open > -16000 && ft.min_sub > -16000;
   int G = 0, K = 0;
   if(s16) {
     /* the packed kernel has extra shapes that fit common read lengths tightly */
-    for(const FastShape &sh : kFast16Shapes)
-      if((int64_t)sh.G * sh.K >= max_la) { G = sh.G; K = sh.K; break; }
-  } else {
+    /* relative keys (ends_mode 2): for a lane's columns x0 .. x0+K-1 on row y, D = M[x][y] - H[x0-1][y] obeys
+     *   D <= (j + 1)(max_sub - open)                  (H rises by at most max_sub - open per step, any direction)
+     *   D >= padsub - max_sub + 2 open + (j - 1) ext  (a gap from column x0-1 to x-1 on row y-1 bounds H from below)
+     * and the key holds D - open + 512 in ten bits: the first shape whose K keeps both inside takes the batch */
+    const bool rel = want_ends && ends_mode == 2;
+    for(const FastShape &sh : kFast16Shapes) {
+      if((int64_t)sh.G * sh.K < max_la) continue;
+      if(rel) {
+        const long up = (long)sh.K * ((long)ft.max_sub - sp.open) - sp.open;
+        const long dn = -((long)padsub - ft.max_sub + sp.open + (long)(sh.K - 2) * sp.ext);
+        if(up > 500 || dn > 500) continue;
+      }
+      G = sh.G; K = sh.K;
+      break;
+    }
+    if(!G) s16 = false;
+  }
+  if(!s16) {
     for(const FastShape &sh : kFastShapes)
       if((int64_t)sh.G * sh.K >= max_la && (!want_dir || sh.K % 4 == 0)) { G = sh.G; K = sh.K; break; }
   }
@@ -1023,6 +1058,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   if(s16) prof32 = false;
   plan->s16 = s16;
   plan->s16_ends = s16 && want_ends;
+  plan->s16_rel = s16 && want_ends && ends_mode == 2;
   plan->dir = want_dir;
   plan->G = G; plan->K = K; plan->is_sw = sp.is_sw != 0; plan->prof32 = prof32;
   plan->track = !sp.is_sw ? TRACK_NONE : (!want_ends ? TRACK_NONE : (max_lb <= 2047 ? TRACK_TREE : TRACK_COLUMN));
@@ -1060,7 +1096,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
     plan->name = sp.is_sw ? "fast_sw_dir" : "fast_nw_dir";
     return true;
   }
-  plan->name = !sp.is_sw ? "fast_nw_score" : (s16 && want_ends) ? "fast16_sw_score_end" : s16 ? "fast16_sw_score"
+  plan->name = !sp.is_sw ? "fast_nw_score" : (s16 && want_ends) ? (ends_mode == 2 ? "fast16_sw_score_endrel" : "fast16_sw_score_end") : s16 ? "fast16_sw_score"
              : plan->track == TRACK_NONE ? "fast_sw_score" : plan->track == TRACK_TREE ? "fast_sw_score_end" : "fast_sw_score_endcol";
   return true;
 }
@@ -1131,8 +1167,8 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
 #define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
-    void (*kfn)(const FastArgs) = F.order ? (plan.s16_ends ? fast16_kernel<g, k, true, true> : fast16_kernel<g, k, false, true>) \
-                                          : (plan.s16_ends ? fast16_kernel<g, k, true> : fast16_kernel<g, k, false>); \
+    void (*kfn)(const FastArgs) = F.order ? (plan.s16_rel ? fast16_kernel<g, k, 2, true> : plan.s16_ends ? fast16_kernel<g, k, 1, true> : fast16_kernel<g, k, 0, true>) \
+                                          : (plan.s16_rel ? fast16_kernel<g, k, 2> : plan.s16_ends ? fast16_kernel<g, k, 1> : fast16_kernel<g, k, 0>); \
     /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
     const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
     const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \
@@ -1146,7 +1182,7 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   if(plan.G == g && plan.K == k)                                                              \
     return plan.prof32 ? fast_launch_gkp<g, k, true>(plan, F, num_sms, need, st)               \
                        : fast_launch_gkp<g, k, false>(plan, F, num_sms, need, st)
-  SA_FAST16_CASE(8, 13) SA_FAST16_CASE(8, 19) SA_FAST16_CASE(16, 19)
+  SA_FAST16_CASE(8, 13) SA_FAST16_CASE(8, 19) SA_FAST16_CASE(16, 19) SA_FAST16_CASE(32, 13)
   SA_FAST_CASE(8, 8); SA_FAST_CASE(8, 12); SA_FAST_CASE(8, 16); SA_FAST_CASE(8, 20);
   SA_FAST_CASE(16, 12); SA_FAST_CASE(16, 16);
   SA_FAST_CASE(32, 10); SA_FAST_CASE(32, 12); SA_FAST_CASE(32, 16);

@@ -132,6 +132,51 @@ def test_fast16_tight_shapes(engine, big, la):
         assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey), (la, related)
 
 
+@pytest.mark.parametrize("spec,kind", [
+    (dict(init=[30, -20, -4, -1, 0, 0, 0, 0, 0, 0]), "dna"),          # identical stretches of 36+ letters pass 1024
+    (dict(init=[25, -3, -11, -1, 0, 0, 0, 0, 0, 0]), "dna"),          # cheap mismatches, dear gaps
+    (dict(init=[22, -17, 0, 0, 0, 0, 0, 0, 0, 0]), "dna"),            # free gaps: B = 0
+    (dict(system="BLOSUM62", poke=dict(gap_open=-11, gap_extend=-1)), "protein"),
+])
+def test_packed_end_cells_relative_keys(engine, big, spec, kind):
+    """SW end cells from the packed kernel when (score + |open|) passes 1024: the 16-bit keys become relative
+    to the value entering the lane on the row (fast16_kernel ENDS == 2).  Uniform and ragged batches,
+    related pairs (the best grows row after row) and unrelated ones (ties: x ascending, then y)."""
+    sc = scoring_from_spec(spec)
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    shapes = ((400, 400), (150, 150), (247, 300), (512, 90)) if big else ((120, 100), (97, 96))
+    n = 600 if big else 5
+    seen = set()
+    for la, lb in shapes:
+        for related in (True, False):
+            a, oa, b, ob = synthetic_batch(4100 + la, n, la, lb, kind=kind, related=related)
+            es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+            engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+            seen.add(engine.last_kernel)
+            if kind == "protein" and (la, lb) == shapes[0]:
+                assert engine.last_kernel == "fast16_sw_score_endrel"     # BASELINE config 4's shape
+            s, x, y = engine.ends()
+            assert np.array_equal(s, es), (la, lb, related, np.nonzero(s != es)[0][:8])
+            assert np.array_equal(x, ex) and np.array_equal(y, ey), (la, lb, related)
+    # (a shape whose K breaks fast_plan's bound, or a batch that stays below 1024, goes to the kernels it went to before)
+    assert "fast16_sw_score_endrel" in seen and seen <= {"fast16_sw_score_endrel", "fast16_sw_score_end", "fast_sw_score_end"}, seen
+    # ragged: couples of different shapes, the padding code on both axes
+    alphabet = b"ACGT" if kind == "dna" else b"ARNDCQEGHILKMFPSTWYV"
+    sa, sb = ragged_batch(4200, 400 if big else 9, 400 if big else 110, 380 if big else 100, alphabet=alphabet)
+    # one long identical pair (tryptophan scores 11 against itself, the largest BLOSUM62 entry)
+    sa[0] = sb[0] = bytes((ord("W") if kind == "protein" else alphabet[i % 4]) for i in range(380 if big else 100))
+    a, oa = seqalign.pack(sa)
+    b, ob = seqalign.pack(sb)
+    es, ex, ey = orc_batch_sw(o, a, oa, b, ob)
+    engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
+    assert engine.last_kernel == "fast16_sw_score_endrel", engine.last_kernel
+    s, x, y = engine.ends()
+    assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
+    assert es.max() >= 1024, es.max()      # the case this test is about
+
+
 @pytest.mark.parametrize("name", ["free_gaps", "linear_gap", "nw_default", "blosum62"])
 def test_fast16_gap_models(engine, big, name):
     """packed kernel under gap models at the edges of its "+open" trick: gap_open = gap_extend = 0
@@ -148,8 +193,8 @@ def test_fast16_gap_models(engine, big, name):
     assert np.array_equal(engine.scores(), es)
     engine.force_general(0)
     engine.submit_packed(SW, MODE_SCORE, a, oa, b, ob)
-    # 16-bit keys need (score + |open|) < 1024: 140 x 11 with BLOSUM62 is past that, the int32 tree kernel takes over
-    assert engine.last_kernel == ("fast_sw_score_end" if name == "blosum62" and big else "fast16_sw_score_end")
+    # absolute 16-bit keys need (score + |open|) < 1024: 140 x 11 with BLOSUM62 is past that, the keys turn relative
+    assert engine.last_kernel == ("fast16_sw_score_endrel" if name == "blosum62" and big else "fast16_sw_score_end")
     s, x, y = engine.ends()
     assert np.array_equal(s, es) and np.array_equal(x, ex) and np.array_equal(y, ey)
 
