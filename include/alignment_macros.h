@@ -1,26 +1,32 @@
 /*
- * alignment_macros.h -- index / min / max helper macros of the seq-align C API.
+ * alignment_macros.h -- the small helper macros callers of the seq-align C API expect to find.
  *
- * Drop-in for reference src/alignment_macros.h:11-24 (the reference's tools
- * include it: src/tools/sw_cmdline.c:23).  Matrices are row-major with x (the
- * position in seq_a) running fastest: index = y * width + x.
+ * Same names and meaning as the reference's src/alignment_macros.h:11-24 (its tools include that header,
+ * src/tools/sw_cmdline.c:23, so a drop-in needs them); written here from the documented behaviour.
+ * The score matrices are row-major with x, the position in seq_a, running fastest:
+ *     cell (x, y) of a matrix `width` cells wide sits at  y * width + x.
  */
-#ifndef ALIGNMENT_MACROS_HEADER_SEEN
-#define ALIGNMENT_MACROS_HEADER_SEEN
+#ifndef SEQALIGN_B200_ALIGNMENT_MACROS_H
+#define SEQALIGN_B200_ALIGNMENT_MACROS_H
 
-#define ARR_2D_INDEX(width,i,j) (((unsigned long)(j)*(width)) + (i))
-#define ARR_LOOKUP(arr,width,i,j) arr[ARR_2D_INDEX((width),(i),(j))]
-#define ARR_2D_X(arr_index, arr_width) ((arr_index) % (arr_width))
-#define ARR_2D_Y(arr_index, arr_width) ((arr_index) / (arr_width))
+/* (x, y) <-> linear index; the row offset is computed in unsigned long, like the matrices' size_t fields */
+#define ARR_2D_INDEX(width, x, y)      ((unsigned long)(y) * (width) + (x))
+#define ARR_2D_X(index, width)         ((index) % (width))
+#define ARR_2D_Y(index, width)         ((index) / (width))
+#define ARR_LOOKUP(arr, width, x, y)   ((arr)[ARR_2D_INDEX(width, x, y)])
 
-#define QUOTE(str) #str
+/* stringify */
+#define QUOTE(token)                   #token
 
-#define MAX2(x,y) ((x) >= (y) ? (x) : (y))
-#define MIN2(x,y) ((x) <= (y) ? (x) : (y))
-#define MAX3(x,y,z) MAX2(MAX2(x,y),z)
-#define MIN3(x,y,z) MIN2(MIN2(x,y),z)
-#define MAX4(w,x,y,z) MAX2(MAX2(w,x),MAX2(y,z))
+/* order statistics of two, three and four values; ties keep the first argument, arguments may be
+ * evaluated more than once */
+#define MIN2(a, b)                     ((b) < (a) ? (b) : (a))
+#define MAX2(a, b)                     ((b) > (a) ? (b) : (a))
+#define MIN3(a, b, c)                  MIN2(MIN2(a, b), c)
+#define MAX3(a, b, c)                  MAX2(MAX2(a, b), c)
+#define MAX4(a, b, c, d)               MAX2(MAX2(a, b), MAX2(c, d))
 
-#define ABSDIFF(a,b) ((a) > (b) ? (a)-(b) : (b)-(a))
+/* |a - b| without going through a signed difference (safe for unsigned operands) */
+#define ABSDIFF(a, b)                  ((a) < (b) ? (b) - (a) : (a) - (b))
 
 #endif
