@@ -80,6 +80,7 @@ struct FastPlan {
   bool dir = false;   /* also write traceback flag bytes */
   bool hits = false;  /* ... and int16 match scores (multi-hit stage) */
   size_t smem = 0;
+  int warps = FAST_WARPS;  /* warps per CTA (the packed kernel takes fewer when that leaves more of them resident) */
   int a_stage = 0, b_stage = 0;
   bool pad_row = false; /* fast16: profile with a padding row, for batches whose pairs differ in shape */
 };
@@ -1075,7 +1076,18 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
   if(s16) {
     plan->pad_row = !uniform;
     const size_t warp_bytes = 2 * (size_t)(n + (uniform ? 0 : 1)) * 32 * ((K + 3) / 4) * 4 + 2 * (size_t)(2 * (32 / G)) * (plan->a_stage + plan->b_stage);
-    plan->smem = 64 + 256 + (((size_t)(n + 1) * (n + 1) + 15) & ~(size_t)15) + FAST_WARPS * warp_bytes;
+    /* warps per CTA: four, unless the profile is so large (protein alphabets: 20+ rows of 512 bytes per half) that
+     * few CTAs fit an SM and a smaller CTA leaves more warps resident (228 KB per SM, 1 KB reserved per CTA) */
+    const size_t fixed = 64 + 256 + (((size_t)(n + 1) * (n + 1) + 15) & ~(size_t)15);
+    int best_w = FAST_WARPS, best_res = 0;
+    for(int w = FAST_WARPS; w >= 2; w--) {
+      const int res = w * (int)(233472 / (fixed + (size_t)w * warp_bytes + 1024));
+      if(w == FAST_WARPS) { best_res = res; if(res > 10) break; }
+      else if(res > best_res) { best_res = res; best_w = w; }
+    }
+    if(getenv("SEQALIGN_FAST16_WARPS")) best_w = atoi(getenv("SEQALIGN_FAST16_WARPS")) >= 2 && atoi(getenv("SEQALIGN_FAST16_WARPS")) <= FAST_WARPS ? atoi(getenv("SEQALIGN_FAST16_WARPS")) : best_w;
+    plan->warps = best_w;
+    plan->smem = fixed + (size_t)best_w * warp_bytes;
   }
   if(plan->smem > 200 * 1024) return false;
   /* tables are n+1 rows (code of seq_b, last = padding row) x n+1 columns
@@ -1106,7 +1118,7 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
  * the two runtime calls cost several microseconds on every launch otherwise. */
 struct FastKernelInfo { const void *fn; size_t smem; int device; int per_sm; };
 template <class KF>
-int fast_per_sm(KF kfn, size_t smem)
+int fast_per_sm(KF kfn, size_t smem, int threads = FAST_WARPS * 32)
 {
   thread_local std::vector<FastKernelInfo> cache;
   int dev = 0;
@@ -1115,16 +1127,16 @@ int fast_per_sm(KF kfn, size_t smem)
     if(k.fn == (const void *)kfn && k.device == dev && k.smem == smem) return k.per_sm;
   if(!smem_opt_in(kfn, smem)) return -1;
   int per_sm = 1;
-  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, FAST_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   cache.push_back({(const void *)kfn, smem, dev, per_sm});
   return per_sm;
 }
 
 /* persistent grid: exactly as many CTAs as are resident at once; -1 if the kernel cannot take this much shared memory */
 template <class KF>
-int fast_grid(KF kfn, size_t smem, int num_sms, int64_t need)
+int fast_grid(KF kfn, size_t smem, int num_sms, int64_t need, int threads = FAST_WARPS * 32)
 {
-  const int per_sm = fast_per_sm(kfn, smem);
+  const int per_sm = fast_per_sm(kfn, smem, threads);
   if(per_sm < 0) return -1;
   int64_t grid = (int64_t)num_sms * per_sm;
   if(grid > need) grid = need;
@@ -1164,7 +1176,8 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
   if(plan.smem > smem_optin) return -1;
   const int NG = (plan.s16 ? 2 : 1) * (32 / plan.G);
   const int64_t nsets = (F.npairs + NG - 1) / NG;
-  const int64_t need = (nsets + FAST_WARPS - 1) / FAST_WARPS;
+  const int warps = plan.s16 ? plan.warps : FAST_WARPS;
+  const int64_t need = (nsets + warps - 1) / warps;
 #define SA_FAST16_CASE(g, k)                                                                  \
   if(plan.G == g && plan.K == k && plan.s16) {                                                \
     void (*kfn)(const FastArgs) = F.order ? (plan.s16_rel ? fast16_kernel<g, k, 2, true> : plan.s16_ends ? fast16_kernel<g, k, 1, true> : fast16_kernel<g, k, 0, true>) \
@@ -1172,9 +1185,9 @@ inline int fast_launch(const FastPlan &plan, FastArgs F, int num_sms, size_t sme
     /* SEQALIGN_FAST_PAD_SMEM: extra bytes of (unused) shared memory per CTA, an occupancy knob for experiments */ \
     const char *pad_env = getenv("SEQALIGN_FAST_PAD_SMEM");                                   \
     const size_t smem16 = plan.smem + (pad_env ? (size_t)atoi(pad_env) : 0);                  \
-    const int grid16 = fast_grid(kfn, smem16, num_sms, need);                                 \
+    const int grid16 = fast_grid(kfn, smem16, num_sms, need, warps * 32);                     \
     if(grid16 < 0) return -1;                                                                 \
-    SA_LAUNCH(kfn, grid16, FAST_WARPS * 32, smem16, st, F);                                   \
+    SA_LAUNCH(kfn, grid16, warps * 32, smem16, st, F);                                        \
     return 0;                                                                                 \
   }
 #define SA_FAST_CASE(g, k)                                                                    \
