@@ -1085,7 +1085,10 @@ inline bool fast_plan(const scoring_t *s, const FlatTable &ft, const ScoreParams
       if(w == FAST_WARPS) { best_res = res; if(res > 10) break; }
       else if(res > best_res) { best_res = res; best_w = w; }
     }
-    if(getenv("SEQALIGN_FAST16_WARPS")) best_w = atoi(getenv("SEQALIGN_FAST16_WARPS")) >= 2 && atoi(getenv("SEQALIGN_FAST16_WARPS")) <= FAST_WARPS ? atoi(getenv("SEQALIGN_FAST16_WARPS")) : best_w;
+    if(const char *env = getenv("SEQALIGN_FAST16_WARPS")) {   /* experiment knob: the numbers in DESIGN.md 3 K1 */
+      const int w = atoi(env);
+      if(w >= 2 && w <= FAST_WARPS) best_w = w;
+    }
     plan->warps = best_w;
     plan->smem = fixed + (size_t)best_w * warp_bytes;
   }
