@@ -37,35 +37,39 @@ static void print_zam(void)
     if(*p == '-') *p = '_';
     if(*q == '-') *q = '_';
   }
-  printf("Br1:%s\n    ", result->result_a);
-  for(size_t i = 0; result->result_a[i] != '\0'; i++) {
+  const size_t len = strlen(result->result_a);
+  sa_out_lit("Br1:"); sa_out_mem(result->result_a, len); sa_out_lit("\n    ");
+  char *mid = sa_out_room(len);
+  for(size_t i = 0; i < len; i++) {
     const char x = result->result_a[i], y = result->result_b[i];
-    if(x == '_' || y == '_') { putc(' ', stdout); indels++; }
-    else if((scoring.case_sensitive && x != y) || tolower(x) != tolower(y)) { putc('*', stdout); mismatches++; }
-    else putc('|', stdout);
+    if(x == '_' || y == '_') { mid[i] = ' '; indels++; }
+    else if((scoring.case_sensitive && x != y) || tolower(x) != tolower(y)) { mid[i] = '*'; mismatches++; }
+    else mid[i] = '|';
   }
-  printf("\nBr2:%s\n%i %i\n\n", result->result_b, mismatches, indels);
+  sa_ob_n += len;
+  sa_out_lit("\nBr2:"); sa_out_str(result->result_b); sa_out_chr('\n');
+  sa_out_long(mismatches); sa_out_chr(' '); sa_out_long(indels); sa_out_lit("\n\n");
 }
 
 /* one aligned pair from `result` (reference nw_cmdline.c:94-148) */
 static void print_pair(const char *name_a, const char *name_b)
 {
-  if(opt.zam) { print_zam(); if(opt.interactive) fflush(stdout); return; }
-  if(opt.print_fasta && name_a) { fputs(name_a, stdout); putc('\n', stdout); }
-  if(opt.print_fasta && opt.print_pretty && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
-  if(opt.print_colour) alignment_colour_print_against(result->result_a, result->result_b, scoring.case_sensitive);
-  else fputs(result->result_a, stdout);
-  putc('\n', stdout);
-  if(opt.print_pretty) { alignment_print_spacer(result->result_a, result->result_b, &scoring); putc('\n', stdout); }
-  else if(opt.print_fasta && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
-  if(opt.print_colour) alignment_colour_print_against(result->result_b, result->result_a, scoring.case_sensitive);
-  else fputs(result->result_b, stdout);
-  putc('\n', stdout);
-  if(opt.print_scores) printf("score: %i\n", result->score);
-  putc('\n', stdout);
+  if(opt.zam) { print_zam(); if(opt.interactive) sa_out_flush(); return; }
+  if(opt.print_fasta && name_a) { sa_out_str(name_a); sa_out_chr('\n'); }
+  if(opt.print_fasta && opt.print_pretty && name_b) { sa_out_str(name_b); sa_out_chr('\n'); }
+  if(opt.print_colour) { sa_out_sync(); alignment_colour_print_against(result->result_a, result->result_b, scoring.case_sensitive); }
+  else sa_out_str(result->result_a);
+  sa_out_chr('\n');
+  if(opt.print_pretty) { sa_out_sync(); alignment_print_spacer(result->result_a, result->result_b, &scoring); sa_out_chr('\n'); }
+  else if(opt.print_fasta && name_b) { sa_out_str(name_b); sa_out_chr('\n'); }
+  if(opt.print_colour) { sa_out_sync(); alignment_colour_print_against(result->result_b, result->result_a, scoring.case_sensitive); }
+  else sa_out_str(result->result_b);
+  sa_out_chr('\n');
+  if(opt.print_scores) { sa_out_lit("score: "); sa_out_long(result->score); sa_out_chr('\n'); }
+  sa_out_chr('\n');
   /* the reference flushes after every pair; a batch is flushed once (same
    * bytes), --stdin keeps the per-pair flush its callers wait for */
-  if(opt.interactive) fflush(stdout);
+  if(opt.interactive) sa_out_flush();
 }
 
 /* single-pair API: fills nw's matrices too (for --printmatrices), and reports
@@ -73,7 +77,7 @@ static void print_pair(const char *name_a, const char *name_b)
 static void align_single(const char *a, const char *b, const char *name_a, const char *name_b)
 {
   needleman_wunsch_align(a, b, &scoring, nw, result);
-  if(opt.print_matrices && !opt.zam) alignment_print_matrices(nw);
+  if(opt.print_matrices && !opt.zam) { sa_out_sync(); alignment_print_matrices(nw); }
   print_pair(name_a, name_b);
 }
 
@@ -94,6 +98,7 @@ static void print_batch_matrices(size_t i, const char *a, size_t la, const char 
     fprintf(stderr, "Error: %s\n", seqalign_batch_error(mats_eng));
     exit(EXIT_FAILURE);
   }
+  sa_out_sync();
   alignment_print_matrices(&tmp);
   free(tmp.match_scores); free(tmp.gap_a_scores); free(tmp.gap_b_scores);
 }
@@ -147,7 +152,7 @@ static void flush_pairs(sa_pairs *p, sa_reader *r)
 {
   (void)r;
   align_batch(p);
-  fflush(stdout);
+  sa_out_flush();
   sa_pairs_clear(p);
 }
 
@@ -162,6 +167,7 @@ int main(int argc, char **argv)
     setvbuf(stdout, NULL, _IOFBF, 1 << 20);
     __fsetlocking(stdout, FSETLOCKING_BYCALLER);
   }
+  sa_out_init();
   sa_t_start = sa_now();
   sa_gpus = opt.gpus_set ? opt.gpus : 1;
   sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
@@ -176,7 +182,7 @@ int main(int argc, char **argv)
     one.b[0] = sa_dup(opt.seq2, strlen(opt.seq2)); one.lb[0] = strlen(opt.seq2);
     one.n = 1;
     align_batch(&one);
-    fflush(stdout);
+    sa_out_flush();
     sa_pairs_free(&one);
   }
   sa_pairs pairs;

@@ -32,6 +32,53 @@ static inline void sa_timing_report(void)
             sa_t_align, sa_t_print, sa_now() - sa_t_start);
 }
 
+/* ---- stdout of the batch loop ----------------------------------------------------------------
+ * A pair's lines are put together in one buffer by memcpy and hand-written integer formatting and
+ * handed to stdio a megabyte at a time: through printf / fputs / putc the print phase was the
+ * longest phase of a large run (1 us per pair, 2 s for 2 M pairs, the alignment itself 0.5 s).
+ * Anything else that writes to stdout (the library's matrix, colour and spacer printers, the
+ * interactive prompt) is preceded by sa_out_sync(); exit() reaches it through atexit(). */
+static char *sa_ob = NULL;
+static size_t sa_ob_n = 0, sa_ob_cap = 0;
+static inline void sa_out_sync(void)
+{
+  if(sa_ob_n) fwrite(sa_ob, 1, sa_ob_n, stdout);
+  sa_ob_n = 0;
+}
+static inline void sa_out_flush(void) { sa_out_sync(); fflush(stdout); }
+static inline char *sa_out_room(size_t n)
+{
+  if(sa_ob_n + n > sa_ob_cap) {
+    sa_out_sync();
+    if(n > sa_ob_cap) {
+      size_t cap = sa_ob_cap ? sa_ob_cap : ((size_t)1 << 20);
+      while(cap < n) cap *= 2;
+      char *nb = (char *)realloc(sa_ob, cap);
+      if(!nb) { fprintf(stderr, "Error: Out of memory\n"); exit(EXIT_FAILURE); }
+      sa_ob = nb; sa_ob_cap = cap;
+    }
+  }
+  return sa_ob + sa_ob_n;
+}
+static inline void sa_out_mem(const char *s, size_t n) { memcpy(sa_out_room(n), s, n); sa_ob_n += n; }
+static inline void sa_out_str(const char *s) { sa_out_mem(s, strlen(s)); }
+#define sa_out_lit(s) sa_out_mem("" s, sizeof(s) - 1)
+static inline void sa_out_chr(char c) { *sa_out_room(1) = c; sa_ob_n++; }
+static inline void sa_out_fill(char c, size_t n) { if(n) { memset(sa_out_room(n), c, n); sa_ob_n += n; } }
+static inline void sa_out_ulong(unsigned long v)
+{
+  char tmp[24];
+  int k = 24;
+  do { tmp[--k] = (char)('0' + v % 10); v /= 10; } while(v);
+  sa_out_mem(tmp + k, (size_t)(24 - k));
+}
+static inline void sa_out_long(long v)
+{
+  if(v < 0) { sa_out_chr('-'); sa_out_ulong(0ul - (unsigned long)v); }
+  else sa_out_ulong((unsigned long)v);
+}
+static inline void sa_out_init(void) { sa_out_room(1); atexit(sa_out_sync); }
+
 /* The engine (CUDA context, streams) is created on a helper thread while the main thread parses
  * options, opens the first input and inflates its first chunk: context creation is the largest fixed
  * cost of a run (0.4 s and more).  sa_engine_wait() joins it before the first use. */

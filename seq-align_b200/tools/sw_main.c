@@ -48,28 +48,38 @@ static size_t zmin(size_t a, size_t b) { return a < b ? a : b; }
 static void print_part(const char *row, const char *other, size_t pos, size_t len, const char *whole,
                        size_t spaces_left, size_t spaces_right, size_t ctx_left, size_t ctx_right)
 {
-  fputs("  ", stdout);
-  for(size_t i = 0; i < spaces_left; i++) putc(' ', stdout);
-  if(ctx_left > 0) {
-    if(opt.print_colour) fputs(align_col_context, stdout);
-    printf("%.*s", (int)ctx_left, whole + pos - ctx_left);
-    if(opt.print_colour) fputs(align_col_stop, stdout);
+  sa_out_lit("  ");
+  sa_out_fill(' ', spaces_left);
+  if(opt.print_colour) {
+    /* the library's colour printer writes to stdout itself */
+    sa_out_sync();
+    if(ctx_left > 0) {
+      fputs(align_col_context, stdout);
+      printf("%.*s", (int)ctx_left, whole + pos - ctx_left);
+      fputs(align_col_stop, stdout);
+    }
+    alignment_colour_print_against(row, other, scoring.case_sensitive);
+    if(ctx_right > 0) {
+      fputs(align_col_context, stdout);
+      printf("%.*s", (int)ctx_right, whole + pos + len);
+      fputs(align_col_stop, stdout);
+    }
+  } else {
+    if(ctx_left > 0) sa_out_mem(whole + pos - ctx_left, strnlen(whole + pos - ctx_left, ctx_left));
+    sa_out_str(row);
+    if(ctx_right > 0) sa_out_mem(whole + pos + len, strnlen(whole + pos + len, ctx_right));
   }
-  if(opt.print_colour) alignment_colour_print_against(row, other, scoring.case_sensitive);
-  else fputs(row, stdout);
-  if(ctx_right > 0) {
-    if(opt.print_colour) fputs(align_col_context, stdout);
-    printf("%.*s", (int)ctx_right, whole + pos + len);
-    if(opt.print_colour) fputs(align_col_stop, stdout);
-  }
-  for(size_t i = 0; i < spaces_right; i++) putc(' ', stdout);
-  printf("  [pos: %li; len: %lu]\n", (long)pos, (unsigned long)len);
+  sa_out_fill(' ', spaces_right);
+  sa_out_lit("  [pos: "); sa_out_long((long)pos);
+  sa_out_lit("; len: "); sa_out_ulong((unsigned long)len);
+  sa_out_lit("]\n");
 }
 
 /* the hit in `result` (reference sw_cmdline.c:219-306) */
 static void print_hit(const char *seq_a, const char *seq_b, size_t len_a, size_t len_b, size_t hit_index)
 {
-  printf("hit %zu.%zu score: %i\n", alignment_index, hit_index, result->score);
+  sa_out_lit("hit "); sa_out_ulong(alignment_index); sa_out_chr('.'); sa_out_ulong(hit_index);
+  sa_out_lit(" score: "); sa_out_long(result->score); sa_out_chr('\n');
   size_t ctx_l = 0, ctx_r = 0, ls_a = 0, ls_b = 0, rs_a = 0, rs_b = 0;
   if(opt.context) {
     ctx_l = zmin(zmax(result->pos_a, result->pos_b), opt.context);
@@ -83,31 +93,34 @@ static void print_hit(const char *seq_a, const char *seq_b, size_t len_a, size_t
   print_part(result->result_a, result->result_b, result->pos_a, result->len_a, seq_a, ls_a, rs_a, ctx_l - ls_a, ctx_r - rs_a);
   if(opt.print_pretty) {
     const size_t ml = zmax(ls_a, ls_b), mr = zmax(rs_a, rs_b);
-    fputs("  ", stdout);
-    for(size_t i = 0; i < ml; i++) putc(' ', stdout);
-    for(size_t i = 0; i < ctx_l - ml; i++) putc('.', stdout);
+    sa_out_lit("  ");
+    sa_out_fill(' ', ml);
+    sa_out_fill('.', ctx_l - ml);
+    sa_out_sync();
     alignment_print_spacer(result->result_a, result->result_b, &scoring);
-    for(size_t i = 0; i < ctx_r - mr; i++) putc('.', stdout);
-    for(size_t i = 0; i < mr; i++) putc(' ', stdout);
-    putc('\n', stdout);
+    sa_out_fill('.', ctx_r - mr);
+    sa_out_fill(' ', mr);
+    sa_out_chr('\n');
   }
   print_part(result->result_b, result->result_a, result->pos_b, result->len_b, seq_b, ls_b, rs_b, ctx_l - ls_b, ctx_r - rs_b);
-  printf("\n");
+  sa_out_chr('\n');
   /* flushed per hit where someone waits for it; a batch is flushed once (same bytes) */
-  if(opt.interactive) fflush(stdout);
+  if(opt.interactive) sa_out_flush();
 }
 
 /* pair header up to the blank line (reference sw_cmdline.c:157-190) */
 static void print_header(const char *seq_a, const char *seq_b, const char *name_a, const char *name_b,
                          size_t len_a, size_t len_b, aligner_t *matrices)
 {
-  printf("== Alignment %zu lengths (%lu, %lu):\n", alignment_index, (unsigned long)len_a, (unsigned long)len_b);
-  if(matrices) alignment_print_matrices(matrices);
-  if(opt.print_fasta && name_a) { fputs(name_a, stdout); putc('\n', stdout); }
-  if(opt.print_seq) { fputs(seq_a, stdout); putc('\n', stdout); }
-  if(opt.print_fasta && name_b) { fputs(name_b, stdout); putc('\n', stdout); }
-  if(opt.print_seq) { fputs(seq_b, stdout); putc('\n', stdout); }
-  putc('\n', stdout);
+  sa_out_lit("== Alignment "); sa_out_ulong(alignment_index);
+  sa_out_lit(" lengths ("); sa_out_ulong((unsigned long)len_a); sa_out_lit(", "); sa_out_ulong((unsigned long)len_b);
+  sa_out_lit("):\n");
+  if(matrices) { sa_out_sync(); alignment_print_matrices(matrices); }
+  if(opt.print_fasta && name_a) { sa_out_str(name_a); sa_out_chr('\n'); }
+  if(opt.print_seq) { sa_out_str(seq_a); sa_out_chr('\n'); }
+  if(opt.print_fasta && name_b) { sa_out_str(name_b); sa_out_chr('\n'); }
+  if(opt.print_seq) { sa_out_str(seq_b); sa_out_chr('\n'); }
+  sa_out_chr('\n');
 }
 
 /* --minscore default of a pair (reference sw_cmdline.c:192-202) */
@@ -125,13 +138,13 @@ static int next_hit_wanted(void)
   if(!wait_on_keystroke) return 1;
   int r = 0, answered = 0, next = 0;
   while(!answered) {
-    printf("next [h]it or [a]lignment: ");
-    fflush(stdout);
+    sa_out_lit("next [h]it or [a]lignment: ");
+    sa_out_flush();
     while((r = sa_reader_getc(prompt_input)) != -1 && r != '\n' && r != '\r') {
       if(r == 'h' || r == 'H') { next = 1; answered = 1; }
       else if(r == 'a' || r == 'A') { next = 0; answered = 1; }
     }
-    if(r == -1) { putc('\n', stdout); exit(EXIT_SUCCESS); }
+    if(r == -1) { sa_out_chr('\n'); exit(EXIT_SUCCESS); }
   }
   return next;
 }
@@ -162,13 +175,13 @@ static void align_single(const char *seq_a, const char *seq_b, const char *name_
   const size_t len_a = al->score_width - 1, len_b = al->score_height - 1;
   print_header(seq_a, seq_b, name_a, name_b, len_a, len_b, opt.print_matrices ? al : NULL);
   const int min_score = pair_min_score(len_a, len_b);
-  fflush(stdout);
+  sa_out_flush();
   size_t hit_index = 0;
   while(next_hit_wanted() && smith_waterman_fetch(sw, result) && result->score >= min_score &&
         (!opt.max_hits_set || hit_index < opt.max_hits))
     print_hit(seq_a, seq_b, len_a, len_b, hit_index++);
-  fputs("==\n", stdout);
-  fflush(stdout);
+  sa_out_lit("==\n");
+  sa_out_flush();
   alignment_index++;
 }
 
@@ -277,10 +290,10 @@ static void align_batch(sa_pairs *p)
         print_hit(a[i], b[i], la[i], lb[i], hit_index++);
       }
     }
-    fputs("==\n", stdout);
+    sa_out_lit("==\n");
     alignment_index++;
   }
-  fflush(stdout);
+  sa_out_flush();
   sa_t_print += sa_now() - t1;
 }
 
@@ -307,6 +320,7 @@ int main(int argc, char **argv)
     setvbuf(stdout, NULL, _IOFBF, 1 << 20);
     __fsetlocking(stdout, FSETLOCKING_BYCALLER);
   }
+  sa_out_init();
   sa_t_start = sa_now();
   sa_gpus = opt.gpus_set ? opt.gpus : 1;
   sa_engine_start(&eng, &scoring);   /* the CUDA context comes up while the first input is opened and read */
