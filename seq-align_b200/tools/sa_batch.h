@@ -51,7 +51,9 @@ static inline char *sa_out_room(size_t n)
   if(sa_ob_n + n > sa_ob_cap) {
     sa_out_sync();
     if(n > sa_ob_cap) {
-      size_t cap = sa_ob_cap ? sa_ob_cap : ((size_t)1 << 20);
+      /* SEQALIGN_CLI_OUTBUF=<bytes>: first size of the buffer (the tests replay every recorded invocation with 16) */
+      const char *env = sa_ob_cap ? NULL : getenv("SEQALIGN_CLI_OUTBUF");
+      size_t cap = sa_ob_cap ? sa_ob_cap : (env && atol(env) > 0 ? (size_t)atol(env) : ((size_t)1 << 20));
       while(cap < n) cap *= 2;
       char *nb = (char *)realloc(sa_ob, cap);
       if(!nb) { fprintf(stderr, "Error: Out of memory\n"); exit(EXIT_FAILURE); }

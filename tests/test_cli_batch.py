@@ -100,10 +100,12 @@ def test_batched_invocations(tool_dir, i):
 READERS = {"device": {}, "device_tiny_chunks": {"SEQALIGN_CLI_CHUNK_MB": "-48"}, "host": {"SEQALIGN_CLI_DECODE": "host"},
            # --gpus 3 (the flag is added to argv below): batches cut over three engines -- the box's GPUs, or three
            # engines on the one (emulated) device
-           "three_engines": {"SEQALIGN_CLI_DEVICES": "0,0,0"}, "three_engines_host_reader": {"SEQALIGN_CLI_DEVICES": "0,0,0", "SEQALIGN_CLI_DECODE": "host"}}
+           "three_engines": {"SEQALIGN_CLI_DEVICES": "0,0,0"}, "three_engines_host_reader": {"SEQALIGN_CLI_DEVICES": "0,0,0", "SEQALIGN_CLI_DECODE": "host"},
+           # the print loop's buffer starts at 16 bytes: every sync / grow path of tools/sa_batch.h sa_out_*
+           "tiny_outbuf": {"SEQALIGN_CLI_OUTBUF": "16"}}
 
 
-@pytest.mark.parametrize("reader", ["device_tiny_chunks", "host", "three_engines", "three_engines_host_reader"])
+@pytest.mark.parametrize("reader", ["device_tiny_chunks", "host", "three_engines", "three_engines_host_reader", "tiny_outbuf"])
 @pytest.mark.parametrize("i", range(len(GOLD2)))
 def test_batched_invocations_other_readers(tool_dir, i, reader):
     """the recorded multi-pair invocations again, through the other two ways of reading the input"""
