@@ -21,8 +21,8 @@ typedef aligner_t nw_aligner_t;
 extern "C" {
 #endif
 
-/* zeroed aligner; its matrices grow on demand (only filled when the caller
- * can look at them, see SEQALIGN_SKIP_MATRICES in INTEGRATION.md) */
+/* zeroed aligner; its matrices grow on demand and are filled when something reads them
+ * (deferred matrices: seqalign_host_eager_matrices() / SEQALIGN_EAGER_MATRICES in INTEGRATION.md) */
 nw_aligner_t *needleman_wunsch_new();
 
 /* releases the matrices and the aligner itself */
