@@ -131,6 +131,7 @@ struct seqalign_batch {
   std::vector<int32_t> nhits, hit_rec;       /* n, n*max*8 */
   std::vector<int64_t> hit_off;              /* n+1: string offsets (per pair: max * (la+lb)) */
   std::vector<char> hit_a, hit_b;
+  const char *hit_a_p = nullptr, *hit_b_p = nullptr;   /* as res_a_p / res_b_p: pinned buffers of a one-wave batch, else the vectors */
   int32_t hit_max_used = 0;
 
   double last_ms = 0, last_walk_ms = 0;
@@ -889,8 +890,6 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
   eng->hit_off.assign(n + 1, 0);
   for(size_t i = 0; i < n; i++)
     eng->hit_off[i + 1] = eng->hit_off[i] + (int64_t)maxh * ((h_off_a[i + 1] - h_off_a[i]) + (h_off_b[i + 1] - h_off_b[i]));
-  eng->hit_a.resize((size_t)eng->hit_off[n] + 1);
-  eng->hit_b.resize((size_t)eng->hit_off[n] + 1);
 
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -1009,9 +1008,20 @@ int run_hits(seqalign_batch *eng, const DevBatch &db, const BatchMeta &bm,
     eng->last_ms += ms;
     memcpy(&eng->nhits[c0], hw, m * 4);
     memcpy(&eng->hit_rec[c0 * (size_t)maxh * 8], hw + m, m * (size_t)maxh * 32);
-    if(obytes > 0) {
-      memcpy(&eng->hit_a[(size_t)eng->hit_off[c0]], eng->h_str_a.p, (size_t)obytes);
-      memcpy(&eng->hit_b[(size_t)eng->hit_off[c0]], eng->h_str_b.p, (size_t)obytes);
+    if(c0 == 0 && c1 == n) {
+      eng->hit_a_p = (const char *)eng->h_str_a.p;
+      eng->hit_b_p = (const char *)eng->h_str_b.p;
+    } else {
+      if(c0 == 0) {
+        eng->hit_a.resize((size_t)eng->hit_off[n] + 1);
+        eng->hit_b.resize((size_t)eng->hit_off[n] + 1);
+      }
+      if(obytes > 0) {
+        memcpy(&eng->hit_a[(size_t)eng->hit_off[c0]], eng->h_str_a.p, (size_t)obytes);
+        memcpy(&eng->hit_b[(size_t)eng->hit_off[c0]], eng->h_str_b.p, (size_t)obytes);
+      }
+      eng->hit_a_p = eng->hit_a.data();
+      eng->hit_b_p = eng->hit_b.data();
     }
     c0 = c1;
   }
@@ -1949,8 +1959,8 @@ int seqalign_batch_hit(seqalign_batch_t *eng, size_t i, size_t h, alignment_t *o
   }
   const size_t per = (size_t)(eng->hit_off[i + 1] - eng->hit_off[i]) / (size_t)eng->hit_max_used;
   const size_t base = (size_t)eng->hit_off[i] + h * per + (size_t)r[6];
-  memcpy(out->result_a, &eng->hit_a[base], len);
-  memcpy(out->result_b, &eng->hit_b[base], len);
+  memcpy(out->result_a, eng->hit_a_p + base, len);
+  memcpy(out->result_b, eng->hit_b_p + base, len);
   out->result_a[len] = out->result_b[len] = '\0';
   out->length = len;
   out->score = r[0];

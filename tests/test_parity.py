@@ -1104,6 +1104,30 @@ def test_multi_hit_on_device(engine, big, name):
     engine.set_hit_limits(8, 1)
 
 
+def test_multi_hit_in_waves(engine, big, monkeypatch):
+    """MODE_HITS with the flag-byte budget cut down: the batch runs in several waves and the hit strings are
+    gathered wave by wave (a one-wave batch is read straight from the landing buffers instead)"""
+    n, maxlen = (60, 120) if big else (7, 30)
+    sa, sb = ragged_batch(4477, n, maxlen, maxlen, min_len=1)
+    sc = scoring_from_spec(SPECS["sw_cli"])
+    o = orc_from_scoring(sc)
+    engine.set_scoring(sc)
+    engine.force_general(0)
+    engine.set_hit_limits(5, 1)
+    lists = []
+    for budget in (None, str(2 * (maxlen + 16) * (maxlen + 16) * 4)):
+        if budget:
+            monkeypatch.setenv("SEQALIGN_DIR_BUDGET", budget)
+        engine.submit(SW, MODE_HITS, sa, sb)
+        lists.append([[_hit_tuple(h) for h in engine.hits(i)] for i in range(len(sa))])
+    assert lists[0] == lists[1]
+    for i, (a, b) in enumerate(zip(sa, sb)):
+        nref, ref = orc_sw_hits(o, a, b, 5)
+        assert lists[1][i] == [(h["score"], h["result_a"], h["result_b"], h["pos_a"], h["pos_b"], h["len_a"], h["len_b"])
+                               for h in ref if h["score"] >= 1], (a, b)
+    engine.set_hit_limits(8, 1)
+
+
 def test_multi_hit_golden(engine):
     """the reference's own hit lists (tests/golden/reference_vectors.json, up to six hits per pair)"""
     engine.set_hit_limits(6, 1)
