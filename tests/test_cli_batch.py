@@ -107,10 +107,12 @@ READERS = {"device": {}, "device_tiny_chunks": {"SEQALIGN_CLI_CHUNK_MB": "-48"},
 
 @pytest.mark.parametrize("reader", ["device_tiny_chunks", "host", "three_engines", "three_engines_host_reader", "tiny_outbuf"])
 @pytest.mark.parametrize("i", range(len(GOLD2)))
-def test_batched_invocations_other_readers(tool_dir, i, reader):
+def test_batched_invocations_other_readers(tool_dir, i, reader, backend):
     """the recorded multi-pair invocations again, through the other two ways of reading the input"""
     if tool_dir == REFMAIN:
         pytest.skip("the reference's mains read through align_from_file only")
+    if reader == "tiny_outbuf" and backend == "gpu":
+        pytest.skip("host-side buffer logic: covered in the build container, not worth 54 more processes on the GPU box")
     case = GOLD2[i]
     if reader.startswith("three_engines"):
         if case["tool"] == "lcs":
